@@ -1,0 +1,171 @@
+/* pire_b200.h -- C ABI of the B200-native Pire scan path.
+ *
+ * The reference (yandex/pire) has no plugin/FFI layer: its seam is the
+ * compile-time "Scanner concept" consumed by the templates of pire/run.h
+ * (SURVEY.md 8(b)).  This header is the boundary a maintainer binds instead:
+ * every entry point names the reference interface it replaces.  Signatures use
+ * plain pointers and sizes only; device buffers are caller-owned CUDA pointers.
+ *
+ * Compiled automata cross the boundary as the byte stream written by the
+ * reference's own  Pire::Scanner::Save()  (pire/scanners/multi.h:557-573), so
+ * the regex front end (Lexer -> Fsm -> Compile / Scanner::Glue) stays on the
+ * host, unchanged.  See INTEGRATION.md for the reference-side binding and
+ * include/pire_gpu.hpp for the C++ mirror of Scanner / Runner / Matches.
+ *
+ * All functions return 0 on success or a negative pire_gpu_status; the text of
+ * the last error on the calling thread is available from pire_gpu_last_error().
+ * The run path of the reference never throws and returns no status
+ * (pire/run.h); here bad arguments and CUDA failures are reported instead of
+ * being undefined behaviour.
+ */
+#ifndef PIRE_B200_H
+#define PIRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pire_gpu_scanner pire_gpu_scanner;
+
+typedef enum pire_gpu_status {
+    PIRE_GPU_OK = 0,
+    PIRE_GPU_EINVAL = -1,      /* bad argument */
+    PIRE_GPU_EIMAGE = -2,      /* scanner image rejected (what Scanner::Load/Mmap throw, multi.h:252-272) */
+    PIRE_GPU_ECUDA = -3,       /* CUDA runtime error (message holds cudaGetErrorString) */
+    PIRE_GPU_ENODEVICE = -4,   /* no usable CUDA device: the scan path has NO CPU fallback */
+    PIRE_GPU_EUNSUPPORTED = -5
+} pire_gpu_status;
+
+/* Run flags: which of RunHelper's mark steps surround the bytes (run.h:375-376).
+ * Runner(sc).Begin().Run(p,n).End() == BEGIN|END; the free function
+ * Pire::Matches(sc,b,e) (run.h:396-400) steps neither mark == 0. */
+enum {
+    PIRE_GPU_RUN_BEGIN = 1u,
+    PIRE_GPU_RUN_END = 2u
+};
+
+/* Kernel variants (pire_gpu_scanner_set_variant). */
+enum {
+    PIRE_GPU_VARIANT_AUTO = 0,
+    PIRE_GPU_VARIANT_PLAIN = 1,    /* one shared-memory load per byte, unconditional */
+    PIRE_GPU_VARIANT_PRED = 2      /* load predicated off while the resident state self-loops */
+};
+
+typedef struct pire_gpu_info {
+    uint32_t states;           /* Scanner::Size()          multi.h:134 */
+    uint32_t letters;          /* Scanner::LettersCount()  multi.h:140 */
+    uint32_t regexps;          /* Scanner::RegexpsCount()  multi.h:139 */
+    uint32_t initial;          /* StateIndex(Initialize()) multi.h:161,:281 */
+    uint32_t empty;            /* Scanner::Empty()         multi.h:135 */
+    uint32_t hot_rows;         /* rows of the shared-memory table */
+    uint32_t variant;          /* kernel variant in use */
+    uint32_t tuned;            /* 1 after pire_gpu_scanner_tune */
+    uint64_t table_bytes;      /* device bytes of the complete (L2-resident) table */
+    uint64_t shared_bytes;     /* dynamic shared memory per CTA */
+    int32_t  device;           /* CUDA device, or -1 for a host-only handle */
+    uint32_t reserved;
+} pire_gpu_info;
+
+/* ---- scanner lifetime -----------------------------------------------------
+ * Replaces: Scanner::Load / Scanner::Mmap (multi.h:244-279,:575-599) followed
+ * by taking the address of the scanner for Runner() (run.h:388-389).
+ * `image` is the Scanner::Save() stream of a Pire::Scanner (Relocatable; both
+ * ExitMasks<2> and NoShortcuts variants are accepted).  The handle owns device
+ * copies of its tables and does not retain `image`.  device >= 0 selects the
+ * CUDA device; device == -1 builds a host-only handle (tables + the host
+ * accessors below; every run entry point then fails with PIRE_GPU_ENODEVICE).
+ * A handle is immutable after create/tune: run_batch is re-entrant across
+ * streams, like a const Scanner shared between threads. */
+int  pire_gpu_scanner_create(const void* image, size_t size, int device, pire_gpu_scanner** out);
+void pire_gpu_scanner_destroy(pire_gpu_scanner* sc);
+int  pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out);
+int  pire_gpu_scanner_set_variant(pire_gpu_scanner* sc, uint32_t variant);
+int  pire_gpu_scanner_set_max_hot(pire_gpu_scanner* sc, uint32_t max_hot_rows);
+
+/* ---- the hot path -----------------------------------------------------------
+ * Replaces, for a whole batch of strings at once:
+ *     Pire::Runner(sc).Begin().Run(ptr, len).End()          run.h:365-392
+ *     -> operator bool / Final()                            run.h:380-381, multi.h:143
+ *     -> AcceptedRegexps(state)                             multi.h:149-158
+ *     -> StateIndex(state)                                  multi.h:281-284
+ * String i is d_corpus[d_offsets[i] .. d_offsets[i+1])  (CSR, n+1 offsets), or,
+ * when d_offsets == NULL, d_corpus[i*fixed_len .. (i+1)*fixed_len).  Empty
+ * strings are legal (pire_ut.cpp NullPointer); n == 0 is a no-op.
+ * Outputs (each may be NULL):
+ *   d_match_bits    ceil(n/32) words; bit (i%32) of word i/32 = Final();
+ *                   bits past n in the last word are 0
+ *   d_accept_masks  n words; bit r = regexp id r in AcceptedRegexps (r < 32)
+ *   d_state_idx     n words; StateIndex() of the last state, reference numbering
+ * All pointers are device pointers on the handle's device; the launch is
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default). */
+int pire_gpu_run_batch(const pire_gpu_scanner* sc,
+                       const uint8_t* d_corpus, const uint64_t* d_offsets,
+                       uint64_t fixed_len, uint64_t n, uint32_t flags,
+                       uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx,
+                       void* stream);
+
+/* Same call with HOST buffers (what a Pire user holds: const char* ranges):
+ * copies corpus (+offsets) to the device, runs, copies the requested results
+ * back and synchronises.  corpus_bytes = total bytes of the corpus buffer. */
+int pire_gpu_run_batch_host(const pire_gpu_scanner* sc,
+                            const uint8_t* corpus, uint64_t corpus_bytes, const uint64_t* offsets,
+                            uint64_t fixed_len, uint64_t n, uint32_t flags,
+                            uint32_t* match_bits, uint32_t* accept_masks, uint32_t* state_idx);
+
+/* Re-selects the shared-memory hot rows from the states a device-resident
+ * sample of the workload actually visits (the reference has no counterpart; it
+ * relies on the CPU cache to keep hot rows close).  Only speed depends on it.
+ * Synchronises the device.  Not thread-safe against concurrent runs. */
+int pire_gpu_scanner_tune(pire_gpu_scanner* sc,
+                          const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n_sample, uint32_t flags, void* stream);
+
+/* Number of kernels this library has launched in the calling process. */
+uint64_t pire_gpu_launch_count(void);
+
+/* ---- host-side Scanner concept on the flattened tables ------------------------
+ * Index-space mirror of the concept the templates in run.h consume
+ * (multi.h:137-194,:281-284); used by include/pire_gpu.hpp's HostScanner and by
+ * the parity tests.  States are StateIndex values of the reference. */
+uint32_t pire_gpu_initial(const pire_gpu_scanner* sc);                                   /* Initialize  multi.h:161 */
+uint32_t pire_gpu_next(const pire_gpu_scanner* sc, uint32_t state, uint32_t ch);         /* Next        multi.h:189-192; ch in 0..259 */
+int      pire_gpu_final(const pire_gpu_scanner* sc, uint32_t state);                     /* Final       multi.h:143 */
+int      pire_gpu_dead(const pire_gpu_scanner* sc, uint32_t state);                      /* Dead        multi.h:147 */
+size_t   pire_gpu_accepted_regexps(const pire_gpu_scanner* sc, uint32_t state,
+                                   uint32_t* ids, size_t cap);                           /* AcceptedRegexps multi.h:149-158 */
+
+/* ---- deterministic synthetic corpora (bench + tests) ---------------------------
+ * Counter-based generator, identical bytes on host and device.
+ * kind 0: printable ASCII 0x20..0x7E; every `plant_every`-th string carries one
+ *         planted literal, plants[(i / plant_every) % n_plants].  A literal
+ *         starting with '^' is placed at the start of the string, one starting
+ *         with '$' at its end (for anchored patterns; the marker itself is not
+ *         written), any other at a pseudo-random offset, and then the string's
+ *         last byte is set to `tail` when tail != 0.
+ * `plants` is n_plants NUL-terminated literals back to back (plants_bytes in all). */
+typedef struct pire_gpu_synth {
+    uint64_t seed;
+    uint64_t first_string;     /* global index of string 0 of this buffer (sharding) */
+    uint64_t n_strings;
+    uint32_t string_len;       /* fixed length, multiple of 16 */
+    uint32_t kind;
+    uint32_t plant_every;      /* 0 = never */
+    uint32_t n_plants;
+    const char* plants;
+    uint32_t plants_bytes;
+    uint32_t tail;
+} pire_gpu_synth;
+
+int pire_gpu_synth_fill_device(const pire_gpu_synth* spec, uint8_t* d_corpus, int device, void* stream);
+int pire_gpu_synth_fill_host(const pire_gpu_synth* spec, uint8_t* corpus, uint64_t first, uint64_t count);
+
+const char* pire_gpu_last_error(void);
+const char* pire_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,273 @@
+// oracle/ref_capi.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// A thin extern "C" face over the UNMODIFIED reference library (compiled from
+// /root/reference by oracle/build_ref.sh into oracle/_ref/libpire_ref.so) so
+// that Python tests and bench.py's CPU arm can:
+//   * compile patterns exactly like tests/common.h:40-69 (ParseRegexp) and
+//     tools/bench/bench.cpp:95-132 (CompileRe, incl. Scanner::Glue);
+//   * serialise a compiled scanner with the reference's own Scanner::Save
+//     (pire/scanners/multi.h:557-573) -- the byte stream the product ingests;
+//   * run the reference's own hot path  Runner(sc).Begin().Run(p,n).End()
+//     (pire/run.h:365-392) over a batch of strings, optionally on several
+//     threads (the reference is single-threaded; a built scanner is immutable,
+//     SURVEY.md 8(b) "Threading"), and report Final / AcceptedRegexps /
+//     StateIndex per string.
+// Nothing here is linked into, or called from, the product library.
+
+#include <cstdint>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+#include <stdexcept>
+
+#include <pire.h>
+#include <stub/stl.h>
+#include <stub/memstreams.h>
+
+namespace {
+
+struct RefScanner {
+	Pire::Scanner reloc;                      // Relocatable + ExitMasks<2> (what Save() writes)
+	Pire::NonrelocScanner nonreloc;           // reference's fastest variant (multi.h:1119-1123)
+	Pire::NonrelocScannerNoMask nonrelocNoMask;
+	bool haveVariants = false;
+
+	void MakeVariants()
+	{
+		if (haveVariants)
+			return;
+		nonreloc = Pire::NonrelocScanner(reloc);
+		// NoMask variants differ in Shortcutting policy, so they cannot be
+		// copy-converted (DeepCopy requires equal Shortcutting); they are
+		// built by the compile/glue entry points below.
+		haveVariants = true;
+	}
+};
+
+void SetErr(char* err, size_t errlen, const char* what)
+{
+	if (err && errlen) {
+		std::strncpy(err, what, errlen - 1);
+		err[errlen - 1] = 0;
+	}
+}
+
+// Same option letters as tests/common.h:40-58.
+Pire::Fsm Parse(const char* pattern, const char* options)
+{
+	Pire::Lexer lexer;
+	Pire::TVector<Pire::wchar32> ucs4;
+	bool surround = true;
+	for (; options && *options; ++options) {
+		if (*options == 'i')
+			lexer.AddFeature(Pire::Features::CaseInsensitive());
+		else if (*options == 'u')
+			lexer.SetEncoding(Pire::Encodings::Utf8());
+		else if (*options == 'n')
+			surround = false;
+		else if (*options == 'a')
+			lexer.AddFeature(Pire::Features::AndNotSupport());
+		else
+			throw std::invalid_argument(std::string("Unknown option: ") + *options);
+	}
+	lexer.Encoding().FromLocal(pattern, pattern + std::strlen(pattern), std::back_inserter(ucs4));
+	lexer.Assign(ucs4.begin(), ucs4.end());
+	Pire::Fsm fsm = lexer.Parse();
+	if (surround)
+		fsm.Surround();
+	return fsm;
+}
+
+template<class Sc>
+void RunRange(const Sc& sc, const uint8_t* corpus, const uint64_t* offsets, uint64_t fixedLen,
+              uint64_t lo, uint64_t hi, int withBegin, int withEnd,
+              uint8_t* finalOut, uint32_t* maskOut, uint32_t* stateOut)
+{
+	for (uint64_t i = lo; i < hi; ++i) {
+		const char* b;
+		const char* e;
+		if (offsets) {
+			b = (const char*) corpus + offsets[i];
+			e = (const char*) corpus + offsets[i + 1];
+		} else {
+			b = (const char*) corpus + i * fixedLen;
+			e = b + fixedLen;
+		}
+		Pire::RunHelper<Sc> r = Pire::Runner(sc);
+		if (withBegin)
+			r.Begin();
+		r.Run(b, e);
+		if (withEnd)
+			r.End();
+		typename Sc::State st = r.State();
+		if (finalOut)
+			finalOut[i] = sc.Final(st) ? 1 : 0;
+		if (maskOut) {
+			uint32_t m = 0;
+			auto acc = sc.AcceptedRegexps(st);
+			for (const size_t* p = acc.first; p != acc.second; ++p)
+				if (*p < 32)
+					m |= (1u << *p);
+			maskOut[i] = m;
+		}
+		if (stateOut)
+			stateOut[i] = (uint32_t) sc.StateIndex(st);
+	}
+}
+
+template<class Sc>
+void RunBatch(const Sc& sc, const uint8_t* corpus, const uint64_t* offsets, uint64_t fixedLen,
+              uint64_t n, int withBegin, int withEnd, int threads,
+              uint8_t* finalOut, uint32_t* maskOut, uint32_t* stateOut)
+{
+	if (threads <= 1 || n < 2) {
+		RunRange(sc, corpus, offsets, fixedLen, 0, n, withBegin, withEnd, finalOut, maskOut, stateOut);
+		return;
+	}
+	std::vector<std::thread> pool;
+	uint64_t per = (n + threads - 1) / threads;
+	for (int t = 0; t < threads; ++t) {
+		uint64_t lo = std::min<uint64_t>(n, per * t), hi = std::min<uint64_t>(n, lo + per);
+		if (lo == hi)
+			break;
+		pool.emplace_back([=, &sc] {
+			RunRange(sc, corpus, offsets, fixedLen, lo, hi, withBegin, withEnd, finalOut, maskOut, stateOut);
+		});
+	}
+	for (auto& th : pool)
+		th.join();
+}
+
+// Index -> State needs the protected IndexToState (multi.h:447-450); a
+// member-less subclass view gives access without touching the reference.
+struct PeekScanner : Pire::Scanner {
+	size_t ToState(size_t idx) const { return IndexToState(idx); }
+};
+const PeekScanner& AsPeek(const Pire::Scanner& sc) { return static_cast<const PeekScanner&>(sc); }
+
+} // namespace
+
+extern "C" {
+
+void* pref_compile(const char* pattern, const char* options, char* err, size_t errlen)
+{
+	try {
+		Pire::Fsm fsm = Parse(pattern, options);
+		RefScanner* h = new RefScanner;
+		h->reloc = Pire::Fsm(fsm).Compile<Pire::Scanner>();
+		h->nonrelocNoMask = Pire::Fsm(fsm).Compile<Pire::NonrelocScannerNoMask>();
+		h->MakeVariants();
+		return h;
+	} catch (std::exception& e) {
+		SetErr(err, errlen, e.what());
+		return nullptr;
+	}
+}
+
+// Scanner::Glue (multi.h:1092-1103).  On overflow the reference returns an
+// Empty() scanner; we hand that back as a handle whose pref_empty() is 1.
+void* pref_glue(void* a, void* b, size_t maxSize, char* err, size_t errlen)
+{
+	try {
+		RefScanner* x = (RefScanner*) a;
+		RefScanner* y = (RefScanner*) b;
+		RefScanner* h = new RefScanner;
+		h->reloc = Pire::Scanner::Glue(x->reloc, y->reloc, maxSize);
+		h->nonrelocNoMask = Pire::NonrelocScannerNoMask::Glue(x->nonrelocNoMask, y->nonrelocNoMask, maxSize);
+		h->MakeVariants();
+		return h;
+	} catch (std::exception& e) {
+		SetErr(err, errlen, e.what());
+		return nullptr;
+	}
+}
+
+// A default-constructed (empty) scanner, multi.h:121.
+void* pref_empty_scanner()
+{
+	RefScanner* h = new RefScanner;
+	h->MakeVariants();
+	return h;
+}
+
+void pref_free(void* h) { delete (RefScanner*) h; }
+
+int pref_empty(void* h) { return ((RefScanner*) h)->reloc.Empty() ? 1 : 0; }
+uint64_t pref_size(void* h) { return ((RefScanner*) h)->reloc.Size(); }
+uint64_t pref_letters_count(void* h) { return ((RefScanner*) h)->reloc.LettersCount(); }
+uint64_t pref_regexps_count(void* h) { return ((RefScanner*) h)->reloc.RegexpsCount(); }
+
+uint64_t pref_initial_index(void* h)
+{
+	RefScanner* s = (RefScanner*) h;
+	Pire::Scanner::State st;
+	s->reloc.Initialize(st);
+	return s->reloc.StateIndex(st);
+}
+
+// One Step() (run.h:50-57) in StateIndex space; ch may be BeginMark/EndMark.
+uint64_t pref_next_index(void* h, uint64_t stateIndex, uint32_t ch)
+{
+	const PeekScanner& p = AsPeek(((RefScanner*) h)->reloc);
+	Pire::Scanner::State cur = p.ToState(stateIndex);
+	Pire::Step(p, cur, (Pire::Char) ch);
+	return p.StateIndex(cur);
+}
+
+// Scanner::Save (multi.h:557-573).  Returns the stream length; copies it to buf
+// when cap is large enough.
+uint64_t pref_save(void* h, void* buf, uint64_t cap)
+{
+	std::ostringstream out;
+	((RefScanner*) h)->reloc.Save(&out);
+	std::string s = out.str();
+	if (buf && cap >= s.size())
+		std::memcpy(buf, s.data(), s.size());
+	return s.size();
+}
+
+// variant: 0 = Scanner (reloc, ExitMasks), 1 = NonrelocScanner (ExitMasks),
+//          2 = NonrelocScannerNoMask (pure table walk)
+// offsets == NULL => fixed-length strings of fixedLen bytes, stride fixedLen.
+int pref_run_batch(void* h, int variant, const uint8_t* corpus, const uint64_t* offsets,
+                   uint64_t fixedLen, uint64_t n, int withBegin, int withEnd, int threads,
+                   uint8_t* finalOut, uint32_t* maskOut, uint32_t* stateOut)
+{
+	RefScanner* s = (RefScanner*) h;
+	switch (variant) {
+	case 0: RunBatch(s->reloc, corpus, offsets, fixedLen, n, withBegin, withEnd, threads, finalOut, maskOut, stateOut); return 0;
+	case 1: RunBatch(s->nonreloc, corpus, offsets, fixedLen, n, withBegin, withEnd, threads, finalOut, maskOut, stateOut); return 0;
+	case 2: RunBatch(s->nonrelocNoMask, corpus, offsets, fixedLen, n, withBegin, withEnd, threads, finalOut, maskOut, stateOut); return 0;
+	default: return -1;
+	}
+}
+
+// AcceptedRegexps (multi.h:149-158) for a state index; returns the count.
+uint64_t pref_accepted(void* h, uint64_t stateIndex, uint64_t* ids, uint64_t cap)
+{
+	const PeekScanner& p = AsPeek(((RefScanner*) h)->reloc);
+	auto acc = p.AcceptedRegexps(p.ToState(stateIndex));
+	uint64_t k = 0;
+	for (const size_t* q = acc.first; q != acc.second; ++q, ++k)
+		if (ids && k < cap)
+			ids[k] = *q;
+	return k;
+}
+
+int pref_final(void* h, uint64_t stateIndex)
+{
+	const PeekScanner& p = AsPeek(((RefScanner*) h)->reloc);
+	return p.Final(p.ToState(stateIndex)) ? 1 : 0;
+}
+
+int pref_dead(void* h, uint64_t stateIndex)
+{
+	const PeekScanner& p = AsPeek(((RefScanner*) h)->reloc);
+	return p.Dead(p.ToState(stateIndex)) ? 1 : 0;
+}
+
+unsigned pref_hardware_threads() { return std::thread::hardware_concurrency(); }
+
+} // extern "C"

@@ -1,0 +1,534 @@
+// capi.cu -- the extern "C" boundary declared in include/pire_b200.h.
+//
+// Host side of the scan path: ingest the reference's Scanner::Save() stream
+// (pire_image.cpp), build and upload the device tables (dfa_tables.cpp), launch
+// the sm_100a kernels (scan_kernels.cu).  There is deliberately no CPU scan
+// here: without a CUDA device every run entry point fails with
+// PIRE_GPU_ENODEVICE.
+#include "../../include/pire_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dfa_tables.hpp"
+#include "pire_image.hpp"
+#include "scan_kernels.cuh"
+#include "synth.h"
+
+using namespace pire_b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int Fail(int code, const std::string& what)
+{
+    g_error = what;
+    return code;
+}
+
+int FailCuda(cudaError_t err, const char* where)
+{
+    g_error = std::string(where) + ": " + cudaGetErrorString(err);
+    return PIRE_GPU_ECUDA;
+}
+
+#define CUDA_TRY(expr)                                   \
+    do {                                                 \
+        cudaError_t err__ = (expr);                      \
+        if (err__ != cudaSuccess)                        \
+            return FailCuda(err__, #expr);               \
+    } while (0)
+
+struct DeviceTables {
+    uint8_t* hot8 = nullptr;
+    uint8_t* noexit = nullptr;
+    uint16_t* cls = nullptr;
+    void* full = nullptr;
+    DeviceFin* fin[2] = {nullptr, nullptr};
+    size_t full_bytes = 0;
+
+    void Free()
+    {
+        cudaFree(hot8);
+        cudaFree(noexit);
+        cudaFree(cls);
+        cudaFree(full);
+        cudaFree(fin[0]);
+        cudaFree(fin[1]);
+        *this = DeviceTables();
+    }
+};
+
+} // namespace
+
+struct pire_gpu_scanner {
+    Dfa dfa;
+    ScanTables tab;
+    DeviceTables dev;
+    int device = -1;
+    uint32_t variant = PIRE_GPU_VARIANT_AUTO;
+    uint32_t max_hot = kMaxHot;
+    bool tuned = false;
+    std::vector<uint32_t> hot_order;
+    LaunchPlan plan[3][2];          // [variant][uniform]
+
+    // workspace of the host-buffer entry point
+    std::mutex host_mutex;
+    uint8_t* ws_corpus = nullptr;
+    size_t ws_corpus_bytes = 0;
+    uint64_t* ws_offsets = nullptr;
+    size_t ws_offsets_bytes = 0;
+    uint32_t* ws_out = nullptr;
+    size_t ws_out_bytes = 0;
+    cudaStream_t ws_stream = nullptr;
+};
+
+namespace {
+
+uint32_t ResolveVariant(const pire_gpu_scanner* sc)
+{
+    if (sc->variant == PIRE_GPU_VARIANT_PLAIN || sc->variant == PIRE_GPU_VARIANT_PRED)
+        return sc->variant;
+    // AUTO: predication pays when lanes outside the resident state would
+    // collide with it in the banks, i.e. for large (glued) automata.
+    return sc->tab.states > 64 ? PIRE_GPU_VARIANT_PRED : PIRE_GPU_VARIANT_PLAIN;
+}
+
+int Upload(pire_gpu_scanner* sc)
+{
+    if (sc->device < 0)
+        return PIRE_GPU_OK;
+    CUDA_TRY(cudaSetDevice(sc->device));
+    sc->dev.Free();
+    const ScanTables& t = sc->tab;
+    DeviceTables& d = sc->dev;
+    CUDA_TRY(cudaMalloc(&d.hot8, t.hot8.size()));
+    CUDA_TRY(cudaMemcpy(d.hot8, t.hot8.data(), t.hot8.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.noexit, t.noexit.size()));
+    CUDA_TRY(cudaMemcpy(d.noexit, t.noexit.data(), t.noexit.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.cls, 512));
+    CUDA_TRY(cudaMemcpy(d.cls, t.cls.data(), 512, cudaMemcpyHostToDevice));
+    const void* full_src = t.wide ? (const void*) t.full32.data() : (const void*) t.full16.data();
+    d.full_bytes = t.wide ? t.full32.size() * 4 : t.full16.size() * 2;
+    CUDA_TRY(cudaMalloc(&d.full, d.full_bytes));
+    CUDA_TRY(cudaMemcpy(d.full, full_src, d.full_bytes, cudaMemcpyHostToDevice));
+    for (int w = 0; w < 2; ++w) {
+        static_assert(sizeof(FinEntry) == sizeof(DeviceFin), "fin layout");
+        size_t bytes = t.fin[w].size() * sizeof(FinEntry);
+        CUDA_TRY(cudaMalloc(&d.fin[w], bytes));
+        CUDA_TRY(cudaMemcpy(d.fin[w], t.fin[w].data(), bytes, cudaMemcpyHostToDevice));
+    }
+    for (int v = kVariantPlain; v <= kVariantPred; ++v)
+        for (int u = 0; u < 2; ++u)
+            CUDA_TRY(PlanScan(sc->device, t.hot, v, u != 0, &sc->plan[v][u]));
+    return PIRE_GPU_OK;
+}
+
+void Rebuild(pire_gpu_scanner* sc)
+{
+    BuildScanTables(sc->dfa, sc->hot_order, sc->max_hot, &sc->tab);
+}
+
+bool IsUniform(const uint8_t* corpus, const uint64_t* offsets, uint64_t fixed_len)
+{
+    return offsets == nullptr && fixed_len != 0 && fixed_len % 32 == 0 && fixed_len <= 0xffffffe0ull
+           && (reinterpret_cast<uintptr_t>(corpus) & 31) == 0;
+}
+
+void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, const uint64_t* offsets,
+              uint64_t fixed_len, uint64_t n, uint32_t flags)
+{
+    const ScanTables& t = sc->tab;
+    std::memset(a, 0, sizeof(*a));
+    a->corpus = corpus;
+    a->offsets = offsets;
+    a->fixed_len = fixed_len;
+    a->n = n;
+    a->hot8 = sc->dev.hot8;
+    a->noexit = sc->dev.noexit;
+    a->cls = sc->dev.cls;
+    a->full = sc->dev.full;
+    a->fin = sc->dev.fin[(flags & PIRE_GPU_RUN_END) ? 1 : 0];
+    a->hot = t.hot;
+    a->letters = t.letters;
+    a->wide = t.wide ? 1 : 0;
+    a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
+    a->exit_bitmap0 = t.exit_bitmap0;
+}
+
+int CheckRunnable(const pire_gpu_scanner* sc)
+{
+    if (!sc)
+        return Fail(PIRE_GPU_EINVAL, "null scanner handle");
+    if (sc->device < 0)
+        return Fail(PIRE_GPU_ENODEVICE, "host-only scanner handle: the scan path has no CPU fallback");
+    return PIRE_GPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int pire_gpu_scanner_create(const void* image, size_t size, int device, pire_gpu_scanner** out)
+{
+    if (!out)
+        return Fail(PIRE_GPU_EINVAL, "out is null");
+    *out = nullptr;
+    pire_gpu_scanner* sc = new (std::nothrow) pire_gpu_scanner;
+    if (!sc)
+        return Fail(PIRE_GPU_EINVAL, "out of memory");
+    std::string err = ParsePireImage(image, size, &sc->dfa);
+    if (!err.empty()) {
+        delete sc;
+        return Fail(PIRE_GPU_EIMAGE, err);
+    }
+    sc->device = -1;
+    if (device >= 0) {
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || device >= count) {
+            delete sc;
+            return Fail(PIRE_GPU_ENODEVICE, ce != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(ce)
+                                                              : std::string("CUDA device index out of range"));
+        }
+        ce = PrepareScanKernels(device);
+        if (ce != cudaSuccess) {
+            delete sc;
+            return FailCuda(ce, "PrepareScanKernels");
+        }
+        sc->device = device;
+    }
+    sc->hot_order = StaticHotOrder(sc->dfa);
+    Rebuild(sc);
+    int rc = Upload(sc);
+    if (rc != PIRE_GPU_OK) {
+        pire_gpu_scanner_destroy(sc);
+        return rc;
+    }
+    *out = sc;
+    return PIRE_GPU_OK;
+}
+
+void pire_gpu_scanner_destroy(pire_gpu_scanner* sc)
+{
+    if (!sc)
+        return;
+    if (sc->device >= 0) {
+        cudaSetDevice(sc->device);
+        sc->dev.Free();
+        cudaFree(sc->ws_corpus);
+        cudaFree(sc->ws_offsets);
+        cudaFree(sc->ws_out);
+        if (sc->ws_stream)
+            cudaStreamDestroy(sc->ws_stream);
+    }
+    delete sc;
+}
+
+int pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out)
+{
+    if (!sc || !out)
+        return Fail(PIRE_GPU_EINVAL, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    out->states = sc->dfa.states;
+    out->letters = sc->dfa.letters;
+    out->regexps = sc->dfa.regexps;
+    out->initial = sc->dfa.initial;
+    out->empty = sc->dfa.empty ? 1 : 0;
+    out->hot_rows = sc->tab.hot;
+    out->variant = ResolveVariant(sc);
+    out->tuned = sc->tuned ? 1 : 0;
+    out->table_bytes = sc->tab.wide ? sc->tab.full32.size() * 4 : sc->tab.full16.size() * 2;
+    out->shared_bytes = ScanSharedBytes(sc->tab.hot);
+    out->device = sc->device;
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_scanner_set_variant(pire_gpu_scanner* sc, uint32_t variant)
+{
+    if (!sc || variant > PIRE_GPU_VARIANT_PRED)
+        return Fail(PIRE_GPU_EINVAL, "bad variant");
+    sc->variant = variant;
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_scanner_set_max_hot(pire_gpu_scanner* sc, uint32_t max_hot_rows)
+{
+    if (!sc || max_hot_rows == 0)
+        return Fail(PIRE_GPU_EINVAL, "bad max_hot_rows");
+    sc->max_hot = max_hot_rows < kMaxHot ? max_hot_rows : kMaxHot;
+    Rebuild(sc);
+    return Upload(sc);
+}
+
+int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                       uint64_t fixed_len, uint64_t n, uint32_t flags,
+                       uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END))
+        return Fail(PIRE_GPU_EINVAL, "unknown run flags");
+    if (n == 0)
+        return PIRE_GPU_OK;
+    if (!d_corpus && (d_offsets || fixed_len != 0))
+        return Fail(PIRE_GPU_EINVAL, "null corpus with non-empty strings");
+    if (n > (1ull << 40))
+        return Fail(PIRE_GPU_EINVAL, "too many strings");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    ScanArgs a;
+    FillArgs(sc, &a, d_corpus, d_offsets, fixed_len, n, flags);
+    a.match_bits = d_match_bits;
+    a.accept_masks = d_accept_masks;
+    a.state_idx = d_state_idx;
+    const bool uniform = IsUniform(d_corpus, d_offsets, fixed_len);
+    const uint32_t variant = ResolveVariant(sc);
+    CUDA_TRY(LaunchScan(a, (int) variant, uniform, sc->plan[variant][uniform ? 1 : 0], static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_run_batch_host(const pire_gpu_scanner* csc, const uint8_t* corpus, uint64_t corpus_bytes,
+                            const uint64_t* offsets, uint64_t fixed_len, uint64_t n, uint32_t flags,
+                            uint32_t* match_bits, uint32_t* accept_masks, uint32_t* state_idx)
+{
+    int rc = CheckRunnable(csc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (n == 0)
+        return PIRE_GPU_OK;
+    pire_gpu_scanner* sc = const_cast<pire_gpu_scanner*>(csc);
+    std::lock_guard<std::mutex> lock(sc->host_mutex);
+    CUDA_TRY(cudaSetDevice(sc->device));
+    if (!sc->ws_stream)
+        CUDA_TRY(cudaStreamCreateWithFlags(&sc->ws_stream, cudaStreamNonBlocking));
+    cudaStream_t st = sc->ws_stream;
+
+    const size_t need_corpus = (size_t) corpus_bytes + 64;
+    if (sc->ws_corpus_bytes < need_corpus) {
+        cudaFree(sc->ws_corpus);
+        sc->ws_corpus = nullptr;
+        sc->ws_corpus_bytes = 0;
+        CUDA_TRY(cudaMalloc(&sc->ws_corpus, need_corpus));
+        sc->ws_corpus_bytes = need_corpus;
+    }
+    const size_t need_off = offsets ? (size_t) (n + 1) * 8 : 0;
+    if (sc->ws_offsets_bytes < need_off) {
+        cudaFree(sc->ws_offsets);
+        sc->ws_offsets = nullptr;
+        sc->ws_offsets_bytes = 0;
+        CUDA_TRY(cudaMalloc(&sc->ws_offsets, need_off));
+        sc->ws_offsets_bytes = need_off;
+    }
+    const size_t words = (size_t) ((n + 31) / 32);
+    const size_t need_out = (words + 2 * (size_t) n) * 4;
+    if (sc->ws_out_bytes < need_out) {
+        cudaFree(sc->ws_out);
+        sc->ws_out = nullptr;
+        sc->ws_out_bytes = 0;
+        CUDA_TRY(cudaMalloc(&sc->ws_out, need_out));
+        sc->ws_out_bytes = need_out;
+    }
+    uint32_t* d_bits = match_bits ? sc->ws_out : nullptr;
+    uint32_t* d_masks = accept_masks ? sc->ws_out + words : nullptr;
+    uint32_t* d_states = state_idx ? sc->ws_out + words + n : nullptr;
+
+    if (corpus_bytes)
+        CUDA_TRY(cudaMemcpyAsync(sc->ws_corpus, corpus, corpus_bytes, cudaMemcpyHostToDevice, st));
+    if (offsets)
+        CUDA_TRY(cudaMemcpyAsync(sc->ws_offsets, offsets, need_off, cudaMemcpyHostToDevice, st));
+    rc = pire_gpu_run_batch(sc, sc->ws_corpus, offsets ? sc->ws_offsets : nullptr, fixed_len, n, flags,
+                            d_bits, d_masks, d_states, st);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (match_bits)
+        CUDA_TRY(cudaMemcpyAsync(match_bits, d_bits, words * 4, cudaMemcpyDeviceToHost, st));
+    if (accept_masks)
+        CUDA_TRY(cudaMemcpyAsync(accept_masks, d_masks, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+    if (state_idx)
+        CUDA_TRY(cudaMemcpyAsync(state_idx, d_states, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_scanner_tune(pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n_sample, uint32_t flags, void* stream)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (n_sample == 0)
+        return PIRE_GPU_OK;
+    CUDA_TRY(cudaSetDevice(sc->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long* d_visits = nullptr;
+    const size_t bytes = (size_t) sc->tab.states * sizeof(unsigned long long);
+    CUDA_TRY(cudaMalloc(&d_visits, bytes));
+    cudaError_t ce = cudaMemsetAsync(d_visits, 0, bytes, st);
+    ScanArgs a;
+    FillArgs(sc, &a, d_corpus, d_offsets, fixed_len, n_sample, flags);
+    a.visits = d_visits;
+    if (ce == cudaSuccess)
+        ce = LaunchVisitCount(a, st);
+    std::vector<unsigned long long> by_new(sc->tab.states);
+    if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(by_new.data(), d_visits, bytes, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess)
+        ce = cudaStreamSynchronize(st);
+    cudaFree(d_visits);
+    if (ce != cudaSuccess)
+        return FailCuda(ce, "pire_gpu_scanner_tune");
+    std::vector<uint64_t> by_old(sc->dfa.states, 0);
+    for (uint32_t ns = 0; ns < sc->tab.states; ++ns)
+        by_old[sc->tab.old_of_new[ns]] = by_new[ns];
+    sc->hot_order = HotOrderFromCounts(sc->dfa, by_old);
+    sc->tuned = true;
+    Rebuild(sc);
+    return Upload(sc);
+}
+
+uint64_t pire_gpu_launch_count(void) { return KernelLaunchCount(); }
+
+uint32_t pire_gpu_initial(const pire_gpu_scanner* sc) { return sc ? sc->dfa.initial : 0; }
+
+uint32_t pire_gpu_next(const pire_gpu_scanner* sc, uint32_t state, uint32_t ch)
+{
+    if (!sc || state >= sc->dfa.states || ch >= kMaxCharUnaligned)
+        return 0;
+    return sc->dfa.Next(state, ch);
+}
+
+int pire_gpu_final(const pire_gpu_scanner* sc, uint32_t state)
+{
+    return sc && state < sc->dfa.states && sc->dfa.Final(state);
+}
+
+int pire_gpu_dead(const pire_gpu_scanner* sc, uint32_t state)
+{
+    return sc && state < sc->dfa.states && sc->dfa.Dead(state);
+}
+
+size_t pire_gpu_accepted_regexps(const pire_gpu_scanner* sc, uint32_t state, uint32_t* ids, size_t cap)
+{
+    if (!sc || state >= sc->dfa.states)
+        return 0;
+    size_t k = 0;
+    for (uint32_t at = sc->dfa.acc_begin[state]; at < sc->dfa.acc_begin[state + 1]; ++at, ++k)
+        if (ids && k < cap)
+            ids[k] = sc->dfa.acc_ids[at];
+    return k;
+}
+
+static int FillSynthParams(const pire_gpu_synth* spec, SynthParams* p)
+{
+    if (!spec)
+        return Fail(PIRE_GPU_EINVAL, "null synth spec");
+    if (spec->string_len == 0 || spec->string_len % 16 != 0)
+        return Fail(PIRE_GPU_EINVAL, "string_len must be a positive multiple of 16");
+    if (spec->kind != 0)
+        return Fail(PIRE_GPU_EUNSUPPORTED, "unknown synthetic corpus kind");
+    if (spec->n_plants > (uint32_t) kMaxPlants)
+        return Fail(PIRE_GPU_EINVAL, "too many plants");
+    std::memset(p, 0, sizeof(*p));
+    p->seed = spec->seed;
+    p->first_string = spec->first_string;
+    p->n_strings = spec->n_strings;
+    p->string_len = spec->string_len;
+    p->plant_every = spec->plant_every;
+    p->n_plants = spec->n_plants;
+    p->tail = spec->tail;
+    uint32_t at = 0;
+    const char* lit = spec->plants;
+    const char* lim = spec->plants + spec->plants_bytes;
+    for (uint32_t i = 0; i < spec->n_plants; ++i) {
+        if (lit >= lim)
+            return Fail(PIRE_GPU_EINVAL, "plants buffer shorter than n_plants literals");
+        size_t len = strnlen(lit, (size_t) (lim - lit));
+        if (lit + len >= lim)
+            return Fail(PIRE_GPU_EINVAL, "plants buffer not NUL-terminated");
+        p->plant_off[i] = at;
+        p->plant_mode[i] = lit[0] == '^' ? 1 : lit[0] == '$' ? 2 : 0;
+        at += (uint32_t) (len - (p->plant_mode[i] ? 1 : 0));
+        lit += len + 1;
+    }
+    p->plant_off[spec->n_plants] = at;
+    return PIRE_GPU_OK;
+}
+
+// plants without the separating NULs, indexable by plant_off
+static std::string PackPlants(const pire_gpu_synth* spec)
+{
+    std::string packed;
+    const char* q = spec->plants;
+    for (uint32_t i = 0; i < spec->n_plants; ++i) {
+        size_t len = std::strlen(q);
+        size_t skip = (q[0] == '^' || q[0] == '$') ? 1 : 0;
+        packed.append(q + skip, len - skip);
+        q += len + 1;
+    }
+    return packed;
+}
+
+int pire_gpu_synth_fill_device(const pire_gpu_synth* spec, uint8_t* d_corpus, int device, void* stream)
+{
+    SynthParams p;
+    int rc = FillSynthParams(spec, &p);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (!d_corpus)
+        return Fail(PIRE_GPU_EINVAL, "null device corpus");
+    CUDA_TRY(cudaSetDevice(device));
+    std::string packed = PackPlants(spec);
+    char* d_plants = nullptr;
+    CUDA_TRY(cudaMalloc(&d_plants, packed.size() + 16));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t ce = cudaMemcpyAsync(d_plants, packed.data(), packed.size(), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess)
+        ce = LaunchSynth(p, d_plants, d_corpus, st);
+    if (ce == cudaSuccess)
+        ce = cudaStreamSynchronize(st);
+    cudaFree(d_plants);
+    if (ce != cudaSuccess)
+        return FailCuda(ce, "pire_gpu_synth_fill_device");
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_synth_fill_host(const pire_gpu_synth* spec, uint8_t* corpus, uint64_t first, uint64_t count)
+{
+    SynthParams p;
+    int rc = FillSynthParams(spec, &p);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (!corpus)
+        return Fail(PIRE_GPU_EINVAL, "null corpus");
+    std::string packed = PackPlants(spec);
+    const uint32_t words = p.string_len / 8;
+    for (uint64_t k = 0; k < count; ++k) {
+        const uint64_t gi = p.first_string + first + k;
+        uint8_t* dst = corpus + k * (uint64_t) p.string_len;
+        for (uint32_t w = 0; w < words; ++w) {
+            uint64_t v = SynthWord(p.seed, gi, w, words);
+            std::memcpy(dst + (size_t) w * 8, &v, 8);
+        }
+        uint32_t off = 0;
+        int id = SynthPlant(p, gi, &off);
+        if (id >= 0) {
+            std::memcpy(dst + off, packed.data() + p.plant_off[id], p.plant_off[id + 1] - p.plant_off[id]);
+            if (p.tail && p.plant_mode[id] == 0)
+                dst[p.string_len - 1] = (uint8_t) p.tail;
+        }
+    }
+    return PIRE_GPU_OK;
+}
+
+const char* pire_gpu_last_error(void) { return g_error.c_str(); }
+
+const char* pire_gpu_version(void) { return "pire-b200 0.1 (sm_100a)"; }
+
+} // extern "C"

@@ -1,0 +1,140 @@
+// dfa_tables.cpp -- see dfa_tables.hpp.
+#include "dfa_tables.hpp"
+
+#include <algorithm>
+#include <numeric>
+
+namespace pire_b200 {
+
+std::vector<uint32_t> StaticHotOrder(const Dfa& dfa)
+{
+    std::vector<uint32_t> order;
+    std::vector<uint8_t> seen(dfa.states, 0);
+    order.reserve(dfa.states);
+    auto push = [&](uint32_t s) {
+        if (!seen[s]) {
+            seen[s] = 1;
+            order.push_back(s);
+        }
+    };
+    // The state every string is in after Begin() comes first, then Initialize().
+    push(dfa.Next(dfa.initial, kBeginMark));
+    push(dfa.initial);
+    for (size_t head = 0; head < order.size(); ++head) {
+        uint32_t s = order[head];
+        for (uint32_t b = 0; b < 256; ++b)
+            push(dfa.Next(s, b));
+    }
+    for (uint32_t s = 0; s < dfa.states; ++s)   // unreachable by bytes (only by marks)
+        push(s);
+    return order;
+}
+
+std::vector<uint32_t> HotOrderFromCounts(const Dfa& dfa, const std::vector<uint64_t>& visits)
+{
+    std::vector<uint32_t> fallback = StaticHotOrder(dfa);
+    std::vector<uint32_t> rank(dfa.states);
+    for (uint32_t i = 0; i < dfa.states; ++i)
+        rank[fallback[i]] = i;
+    std::vector<uint32_t> order(dfa.states);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        uint64_t va = a < visits.size() ? visits[a] : 0, vb = b < visits.size() ? visits[b] : 0;
+        if (va != vb)
+            return va > vb;
+        return rank[a] < rank[b];
+    });
+    return order;
+}
+
+void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uint32_t max_hot, ScanTables* out)
+{
+    ScanTables& t = *out;
+    t = ScanTables();
+    t.states = dfa.states;
+    t.letters = dfa.letters;
+    t.hot = std::min<uint32_t>(std::min<uint32_t>(kMaxHot, max_hot), dfa.states);
+    if (t.hot == 0)
+        t.hot = 1;
+    const uint32_t H = t.hot;
+
+    // Renumber: hot states first (in hot_order), the rest in their old order.
+    t.new_of_old.assign(dfa.states, UINT32_MAX);
+    t.old_of_new.clear();
+    t.old_of_new.reserve(dfa.states);
+    for (uint32_t s : hot_order) {
+        if (t.old_of_new.size() == H)
+            break;
+        if (s < dfa.states && t.new_of_old[s] == UINT32_MAX) {
+            t.new_of_old[s] = (uint32_t) t.old_of_new.size();
+            t.old_of_new.push_back(s);
+        }
+    }
+    for (uint32_t s = 0; s < dfa.states; ++s)
+        if (t.new_of_old[s] == UINT32_MAX) {
+            t.new_of_old[s] = (uint32_t) t.old_of_new.size();
+            t.old_of_new.push_back(s);
+        }
+
+    t.cls.resize(256);
+    for (uint32_t b = 0; b < 256; ++b)
+        t.cls[b] = dfa.class_of[b];
+
+    // Complete table in the new numbering.
+    t.wide = dfa.states > 65536;
+    const size_t cells = (size_t) dfa.states * dfa.letters;
+    if (t.wide)
+        t.full32.resize(cells);
+    else
+        t.full16.resize(cells);
+    for (uint32_t ns = 0; ns < dfa.states; ++ns) {
+        const uint32_t* row = &dfa.next[(size_t) t.old_of_new[ns] * dfa.letters];
+        for (uint32_t c = 0; c < dfa.letters; ++c) {
+            uint32_t to = t.new_of_old[row[c]];
+            if (t.wide)
+                t.full32[(size_t) ns * dfa.letters + c] = to;
+            else
+                t.full16[(size_t) ns * dfa.letters + c] = (uint16_t) to;
+        }
+    }
+
+    // Fused hot rows.
+    t.hot8.assign((size_t) (H + 1) * 256, (uint8_t) H);
+    t.noexit.assign(H + 1, 0);
+    for (uint32_t h = 0; h < H; ++h) {
+        const uint32_t* row = &dfa.next[(size_t) t.old_of_new[h] * dfa.letters];
+        bool stays = true;
+        for (uint32_t b = 0; b < 256; ++b) {
+            uint32_t to = t.new_of_old[row[dfa.class_of[b]]];
+            t.hot8[(size_t) h * 256 + b] = (uint8_t) (to < H ? to : H);
+            stays = stays && to == h;
+        }
+        t.noexit[h] = stays ? 1 : 0;    // same predicate as BuildShortcuts' NoExit, multi.h:477-514
+    }
+
+    t.exit_bitmap0 = 0;
+    for (uint32_t b = 0; b < 256; ++b)
+        if (t.hot8[b] != 0)
+            t.exit_bitmap0 |= 1u << (b & 31);
+
+    // What a string that stops in state s reports.
+    for (int with_end = 0; with_end < 2; ++with_end) {
+        t.fin[with_end].resize(dfa.states);
+        for (uint32_t ns = 0; ns < dfa.states; ++ns) {
+            uint32_t os = t.old_of_new[ns];
+            uint32_t last = with_end ? dfa.Next(os, kEndMark) : os;      // RunHelper::End(), run.h:376
+            FinEntry f;
+            f.result = last | (dfa.Final(last) ? 0x80000000u : 0u);      // operator bool, run.h:380-381
+            f.mask = 0;
+            for (uint32_t k = dfa.acc_begin[last]; k < dfa.acc_begin[last + 1]; ++k)
+                if (dfa.acc_ids[k] < 32)
+                    f.mask |= 1u << dfa.acc_ids[k];                      // AcceptedRegexps, multi.h:149-158
+            t.fin[with_end][ns] = f;
+        }
+    }
+
+    t.start[0] = t.new_of_old[dfa.initial];                              // Initialize(), multi.h:161
+    t.start[1] = t.new_of_old[dfa.Next(dfa.initial, kBeginMark)];        // Begin(), run.h:375
+}
+
+} // namespace pire_b200

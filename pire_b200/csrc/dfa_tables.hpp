@@ -1,0 +1,68 @@
+// dfa_tables.hpp -- device table layout for the B200 scan kernels, built on the
+// host from a Dfa (pire_image.hpp).
+//
+// The reference walks  state = row(state)[letter_of[byte]]  with two dependent
+// loads per byte (pire/scanners/multi.h:163-192).  On B200 the walk is bound by
+// shared-memory wavefronts, so the layout is chosen to need ONE one-byte shared
+// load per input byte on the common path:
+//
+//  * states are renumbered so that the H <= 255 most frequently visited ("hot")
+//    states get ids 0..H-1; id H is the "miss" marker;
+//  * hot8[(H+1) x 256]: fused byte-indexed rows for hot states, one u8 per
+//    (state, byte): the next hot id, or H when the target is a cold state.  Row
+//    H maps every byte to H, so a lane that missed keeps running harmlessly to
+//    the end of its 16-byte chunk and is then replayed through the full table.
+//    The address of an entry is (id << 8) | byte -- one PRMT builds it from the
+//    input word and the state register;
+//  * full[states x letters] (u16 when states <= 65536, else u32) + cls[256]:
+//    the complete class-indirect table in the new numbering, L2-resident, used
+//    only for replays, cold states and the unaligned head/tail bytes;
+//  * fin[2][states]: what RunHelper::End()/operator bool/AcceptedRegexps/
+//    StateIndex (run.h:376-381, multi.h:143-158,:281-284) report for a string
+//    that stops in a given state, precomputed for with_end = 0/1, so the
+//    EndMark step and the accept-list walk are one 8-byte load per string;
+//  * start[2]: the state after Initialize() and (optionally) Begin()
+//    (run.h:369,:375) -- identical for every string, so it is computed once here.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "pire_image.hpp"
+
+namespace pire_b200 {
+
+constexpr uint32_t kMaxHot = 255;
+
+struct FinEntry {
+    uint32_t result;   // bit31 = Final(), bits 0..30 = StateIndex() in the reference's numbering
+    uint32_t mask;     // bit i = regexp id i accepted (ids < 32)
+};
+
+struct ScanTables {
+    uint32_t states = 0, letters = 0, hot = 0;
+    bool wide = false;                       // full table entries are u32
+    std::vector<uint32_t> new_of_old, old_of_new;
+    std::vector<uint8_t> hot8;               // (hot + 1) * 256
+    std::vector<uint8_t> noexit;             // [hot + 1]: 1 = no byte leaves this hot state
+    std::vector<uint16_t> cls;               // [256]
+    std::vector<uint16_t> full16;
+    std::vector<uint32_t> full32;
+    std::vector<FinEntry> fin[2];            // [with_end][new id]
+    uint32_t start[2] = {0, 0};              // [with_begin] -> new id
+    uint32_t exit_bitmap0 = 0xffffffffu;     // bit (b & 31) set if byte b may leave hot id 0
+};
+
+// Default hot order: breadth-first from the start states (states near the start
+// dominate on text that rarely matches).  Returns old state ids, best first.
+std::vector<uint32_t> StaticHotOrder(const Dfa& dfa);
+
+// Hot order from observed visit counts (pire_gpu_scanner_tune): old ids by
+// descending count, ties by id; unvisited states are appended in static order.
+std::vector<uint32_t> HotOrderFromCounts(const Dfa& dfa, const std::vector<uint64_t>& visits);
+
+// hot_order lists old state ids, most important first; the first
+// min(kMaxHot, states, max_hot) become hot.
+void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uint32_t max_hot, ScanTables* out);
+
+} // namespace pire_b200

@@ -1,0 +1,581 @@
+// scan_kernels.cu -- hand-written sm_100a kernels for Pire's inner scan loop.
+//
+// Replaces, for a batch of strings, the reference's
+//     Runner(sc).Begin().Run(ptr,len).End()   (pire/run.h:365-392)
+// whose per-byte body is  state = row(state)[letter_of[byte]]
+// (Step run.h:50-57 -> Next/Translate/NextTranslated multi.h:163-192), including
+// the ExitMasks early return on NoExit states (multi.h:955-958).
+//
+// Mapping to the machine (one input string per warp lane):
+//   * The table of hot rows (dfa_tables.hpp) is staged once per persistent CTA
+//     into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier).
+//   * A lane keeps its state as a hot id g in 0..H (H = "not in the table").
+//     One step is   idx = PRMT(word, g)  ->  g = LDS.U8 [idx] :  the PRMT places
+//     input byte k in bits 0..7 and g in bits 8..15, which is the byte address
+//     of the fused row entry.  No class lookup, no multiply, no branch.
+//   * kPred variant: the LDS is predicated off while the lane sits in hot id 0
+//     and the byte cannot leave it (32-slot bitmap probed with a funnel shift),
+//     so fewer lanes hit the banks and the load costs fewer wavefronts.
+//   * Input bytes: each lane streams its own string with 32-byte (uniform
+//     kernel, LDG.256) or 16-byte (generic kernel) read-only vector loads that
+//     bypass L1 allocation, software-prefetched one iteration ahead.
+//   * A lane whose walk leaves the hot rows reads H from then on (row H is a
+//     sink); after the chunk the lane is replayed byte by byte through the
+//     complete class-indirect table in global memory / L2.
+//   * End(): one 8-byte load of the precomputed per-state report; the match bit
+//     of 32 strings is assembled with a warp ballot and written as one word.
+// There is no dense contraction anywhere on this path, hence no tensor cores.
+
+#include "scan_kernels.cuh"
+
+#include <atomic>
+
+namespace pire_b200 {
+
+namespace {
+
+constexpr int kBlock = 512;
+constexpr int kMinBlocksPerSM = 3;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+std::atomic<uint64_t> g_launches{0};
+
+// ---------------------------------------------------------------- PTX helpers
+
+__device__ __forceinline__ uint32_t SmemAddr(const void* p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void FenceBarrierInit()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void MbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(SmemAddr(bar)), "r"(parity) : "memory");
+}
+
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier.
+__device__ __forceinline__ void BulkCopyG2S(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(SmemAddr(dst)),
+                 "l"(src), "r"(bytes), "r"(SmemAddr(bar))
+                 : "memory");
+}
+
+// Streaming read-only loads of the corpus: never re-used by this SM.
+__device__ __forceinline__ uint4 LoadStream16(const uint8_t* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& b)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
+// ---------------------------------------------------------------- shared layout
+
+struct SharedView {
+    uint8_t* hot;        // (H+1)*256
+    uint16_t* cls;       // 256
+    uint8_t* noexit;     // 256 (H+1 used)
+    uint64_t* bar;
+};
+
+__host__ __device__ inline size_t HotBytes(uint32_t hot) { return (size_t) (hot + 1) * 256; }
+
+__device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot)
+{
+    SharedView v;
+    v.hot = smem;
+    v.cls = reinterpret_cast<uint16_t*>(smem + HotBytes(hot));
+    v.noexit = smem + HotBytes(hot) + 512;
+    v.bar = reinterpret_cast<uint64_t*>(smem + HotBytes(hot) + 512 + 256);
+    return v;
+}
+
+// Stage the tables: hot rows by TMA bulk copy, the two small tables by plain loads.
+__device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView& sv)
+{
+    const uint32_t total = (uint32_t) HotBytes(a.hot);
+    if (threadIdx.x == 0) {
+        MbarInit(sv.bar, 1);
+        FenceBarrierInit();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MbarExpectTx(sv.bar, total);
+        constexpr uint32_t kPiece = 16384;
+        for (uint32_t off = 0; off < total; off += kPiece) {
+            uint32_t n = total - off < kPiece ? total - off : kPiece;
+            BulkCopyG2S(sv.hot + off, a.hot8 + off, n, sv.bar);
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        sv.cls[i] = a.cls[i];
+        sv.noexit[i] = i <= a.hot ? a.noexit[i] : 0;
+    }
+    MbarWait(sv.bar, 0);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- the walk
+
+struct Tables {
+    const uint8_t* hot;
+    const uint16_t* cls;
+    const void* full;
+    uint32_t H;
+    uint32_t letters;
+    uint32_t wide;
+    uint32_t m0;
+};
+
+// One byte through the complete table (hot rows first: they are in shared memory).
+__device__ __forceinline__ uint32_t SlowStep(const Tables& t, uint32_t s, uint32_t b)
+{
+    if (s < t.H) {
+        uint32_t h = t.hot[(s << 8) | b];
+        if (h != t.H)
+            return h;
+    }
+    size_t at = (size_t) s * t.letters + t.cls[b];
+    return t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at) : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
+}
+
+// Lane state: g in 0..H; when g == H the real state is `cold`.
+struct LaneState {
+    uint32_t g;
+    uint32_t cold;
+};
+
+__device__ __forceinline__ uint32_t FullState(const Tables& t, const LaneState& s) { return s.g == t.H ? s.cold : s.g; }
+
+__device__ __forceinline__ void SetFull(const Tables& t, LaneState& s, uint32_t full)
+{
+    if (full < t.H) {
+        s.g = full;
+    } else {
+        s.g = t.H;
+        s.cold = full;
+    }
+}
+
+template <bool kPred>
+__device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t w, uint32_t sel)
+{
+    // idx = (g << 8) | byte_k(w): byte address of the fused row entry.
+    uint32_t idx = __byte_perm(w, g, sel);
+    if (kPred) {
+        // bit (byte & 31) of m0: may this byte leave hot id 0?  Lanes resting in
+        // id 0 on a self-looping byte skip the load (fewer bank conflicts).
+        uint32_t probe = __funnelshift_r(t.m0, 0u, idx);
+        if (((probe & 1u) | g) != 0)
+            g = t.hot[idx];
+    } else {
+        g = t.hot[idx];
+    }
+}
+
+template <bool kPred>
+__device__ __forceinline__ void FastWord(const Tables& t, uint32_t& g, uint32_t w)
+{
+    FastStep<kPred>(t, g, w, 0x5540);
+    FastStep<kPred>(t, g, w, 0x5541);
+    FastStep<kPred>(t, g, w, 0x5542);
+    FastStep<kPred>(t, g, w, 0x5543);
+}
+
+// Replay of one 16-byte chunk through the complete table, for a lane that was
+// (or fell) outside the hot rows.  Out of line and by value: it is rare, and
+// keeping it away from the caller keeps the fast loop free of local memory.
+__device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t* cls, const void* full, uint32_t H,
+                                             uint32_t letters_wide, uint32_t from, uint4 v)
+{
+    Tables t;
+    t.hot = hot;
+    t.cls = cls;
+    t.full = full;
+    t.H = H;
+    t.letters = letters_wide & 0x7fffffffu;
+    t.wide = letters_wide >> 31;
+    t.m0 = 0;
+    uint32_t s = from;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        s = SlowStep(t, s, (v.x >> (8 * k)) & 0xffu);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        s = SlowStep(t, s, (v.y >> (8 * k)) & 0xffu);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        s = SlowStep(t, s, (v.z >> (8 * k)) & 0xffu);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        s = SlowStep(t, s, (v.w >> (8 * k)) & 0xffu);
+    return s;
+}
+
+// 16 input bytes.
+template <bool kPred>
+__device__ __forceinline__ void Chunk16(const Tables& t, LaneState& s, uint4 v)
+{
+    const uint32_t before = s.g;
+    uint32_t g = s.g;
+    FastWord<kPred>(t, g, v.x);
+    FastWord<kPred>(t, g, v.y);
+    FastWord<kPred>(t, g, v.z);
+    FastWord<kPred>(t, g, v.w);
+    s.g = g;
+    if (g == t.H) {
+        uint32_t from = before == t.H ? s.cold : before;
+        uint32_t full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, v);
+        SetFull(t, s, full);
+    }
+}
+
+__device__ __forceinline__ void Report(const ScanArgs& a, const Tables& t, const LaneState& s, uint64_t unit, uint64_t i, bool valid)
+{
+    DeviceFin f = a.fin[FullState(t, s)];
+    unsigned matched = __ballot_sync(0xffffffffu, valid && (f.result >> 31));
+    if (a.match_bits && (threadIdx.x & 31) == 0)
+        a.match_bits[unit] = matched;
+    if (valid) {
+        if (a.accept_masks)
+            a.accept_masks[i] = f.mask;
+        if (a.state_idx)
+            a.state_idx[i] = f.result & 0x7fffffffu;
+    }
+}
+
+// ---------------------------------------------------------------- kernels
+
+// Uniform batch: fixed length, length % 32 == 0, corpus 32-byte aligned.
+template <bool kPred>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(const __grid_constant__ ScanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.exit_bitmap0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    const uint32_t len = (uint32_t) a.fixed_len;
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
+
+        LaneState s;
+        SetFull(t, s, a.start);
+
+        if (len != 0) {
+            // Two register sets in ping-pong: the 32 bytes after the ones being walked are
+            // always in flight (software prefetch, one LDG.256 per lane per 32 bytes).
+            uint4 a0, a1, b0, b1;
+            LoadStream32(p, a0, a1);
+            for (uint32_t off = 0;;) {
+                off += 32;
+                const bool more_b = off < len;
+                if (more_b)
+                    LoadStream32(p + off, b0, b1);
+                Chunk16<kPred>(t, s, a0);
+                Chunk16<kPred>(t, s, a1);
+                // multi.h:955-958,:979-982: once no byte can leave any lane's state, the
+                // rest of the strings cannot change the outcome.
+                if (!more_b || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
+                    break;
+                off += 32;
+                const bool more_a = off < len;
+                if (more_a)
+                    LoadStream32(p + off, a0, a1);
+                Chunk16<kPred>(t, s, b0);
+                Chunk16<kPred>(t, s, b1);
+                if (!more_a || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
+                    break;
+            }
+        }
+        Report(a, t, s, unit, i, valid);
+    }
+}
+
+// Generic batch: CSR offsets or arbitrary fixed length / alignment.  Head and
+// tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
+// with its word-aligned body.
+template <bool kPred>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.exit_bitmap0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        uint64_t b = 0, e = 0;
+        if (valid) {
+            if (a.offsets) {
+                b = a.offsets[i];
+                e = a.offsets[i + 1];
+            } else {
+                b = i * a.fixed_len;
+                e = b + a.fixed_len;
+            }
+        }
+        const uint8_t* p = a.corpus + b;
+        const uint8_t* end = a.corpus + e;
+
+        LaneState s;
+        SetFull(t, s, a.start);
+
+        // head: up to the first 16-byte boundary
+        {
+            uint32_t full = FullState(t, s);
+            while (p < end && (reinterpret_cast<uintptr_t>(p) & 15) != 0)
+                full = SlowStep(t, full, *p++);
+            SetFull(t, s, full);
+        }
+        // body: 16-byte chunks, prefetched one ahead; the warp iterates until its
+        // longest lane is done, shorter lanes idle (length binning is the caller's job).
+        const uint32_t chunks = (uint32_t) ((end - p) >> 4);
+        bool parked = false;       // lane sits in a NoExit state: its remaining bytes are irrelevant
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+        if (chunks > 0)
+            cur = LoadStream16(p);
+        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); ++k) {
+            const bool live = k < chunks;
+            if (k + 1 < chunks)
+                nxt = LoadStream16(p + 16 * (size_t) (k + 1));
+            if (live)
+                Chunk16<kPred>(t, s, cur);
+            cur = nxt;
+            // multi.h:955-958,:979-982: a NoExit state cannot be left by any byte.
+            const bool stuck = sv.noexit[s.g] != 0;
+            if (__all_sync(0xffffffffu, !live || stuck)) {
+                parked = live && stuck;
+                if (__all_sync(0xffffffffu, k + 1 >= chunks || parked))
+                    break;
+            }
+        }
+        // tail
+        if (!parked) {
+            p += 16 * (size_t) chunks;
+            uint32_t full = FullState(t, s);
+            while (p < end)
+                full = SlowStep(t, full, *p++);
+            SetFull(t, s, full);
+        }
+        Report(a, t, s, unit, i, valid);
+    }
+}
+
+// Visit counter for pire_gpu_scanner_tune: how many input bytes are consumed in
+// each state (new numbering).  Run-length compressed so that a lane resting in
+// one state issues one atomic per stay, not one per byte.
+__global__ void __launch_bounds__(256) VisitCountKernel(const __grid_constant__ ScanArgs a)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n)
+        return;
+    uint64_t b, e;
+    if (a.offsets) {
+        b = a.offsets[i];
+        e = a.offsets[i + 1];
+    } else {
+        b = i * a.fixed_len;
+        e = b + a.fixed_len;
+    }
+    uint32_t s = a.start;
+    unsigned long long run = 0;
+    for (uint64_t q = b; q < e; ++q) {
+        uint32_t c = a.cls[a.corpus[q]];
+        size_t at = (size_t) s * a.letters + c;
+        uint32_t ns = a.wide ? static_cast<const uint32_t*>(a.full)[at] : (uint32_t) static_cast<const uint16_t*>(a.full)[at];
+        ++run;
+        if (ns != s) {
+            atomicAdd(&a.visits[s], run);
+            run = 0;
+            s = ns;
+        }
+    }
+    if (run)
+        atomicAdd(&a.visits[s], run);
+}
+
+__global__ void __launch_bounds__(256) SynthKernel(const __grid_constant__ SynthParams p, const char* __restrict__ plants, uint8_t* __restrict__ out)
+{
+    const uint32_t pieces = p.string_len / 16;
+    const uint64_t total = p.n_strings * pieces;
+    const uint32_t words = p.string_len / 8;
+    for (uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t local = idx / pieces;
+        const uint32_t piece = (uint32_t) (idx % pieces);
+        const uint64_t gi = p.first_string + local;
+        uint64_t w0 = SynthWord(p.seed, gi, piece * 2, words);
+        uint64_t w1 = SynthWord(p.seed, gi, piece * 2 + 1, words);
+        uint32_t off = 0;
+        int id = SynthPlant(p, gi, &off);
+        if (id >= 0) {
+            const uint32_t len = p.plant_off[id + 1] - p.plant_off[id];
+            const uint32_t lo = piece * 16, hi = lo + 16;
+            const bool touches = (off < hi && off + len > lo) || (p.tail && p.plant_mode[id] == 0 && hi == p.string_len);
+            if (touches) {
+                uint8_t bytes[16];
+                for (int k = 0; k < 8; ++k) {
+                    bytes[k] = (uint8_t) (w0 >> (8 * k));
+                    bytes[8 + k] = (uint8_t) (w1 >> (8 * k));
+                }
+                for (uint32_t k = 0; k < 16; ++k)
+                    bytes[k] = SynthByte(p, plants, gi, lo + k);
+                w0 = w1 = 0;
+                for (int k = 0; k < 8; ++k) {
+                    w0 |= (uint64_t) bytes[k] << (8 * k);
+                    w1 |= (uint64_t) bytes[8 + k] << (8 * k);
+                }
+            }
+        }
+        uint4 v = make_uint4((uint32_t) w0, (uint32_t) (w0 >> 32), (uint32_t) w1, (uint32_t) (w1 >> 32));
+        *reinterpret_cast<uint4*>(out + local * (uint64_t) p.string_len + (uint64_t) piece * 16) = v;
+    }
+}
+
+template <bool kPred>
+const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUniformKernel<kPred>); }
+template <bool kPred>
+const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kPred>); }
+
+const void* KernelFor(int variant, bool uniform)
+{
+    const bool pred = variant == kVariantPred;
+    if (uniform)
+        return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
+    return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
+}
+
+} // namespace
+
+size_t ScanSharedBytes(uint32_t hot) { return HotBytes(hot) + 512 + 256 + 16; }
+
+cudaError_t PrepareScanKernels(int device)
+{
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess)
+        return err;
+    int optin = 0;
+    err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err != cudaSuccess)
+        return err;
+    for (int variant : {(int) kVariantPlain, (int) kVariantPred})
+        for (bool uniform : {false, true}) {
+            err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+            if (err != cudaSuccess)
+                return err;
+        }
+    return cudaSuccess;
+}
+
+cudaError_t PlanScan(int device, uint32_t hot, int variant, bool uniform, LaunchPlan* plan)
+{
+    plan->block = kBlock;
+    plan->shared = ScanSharedBytes(hot);
+    int sms = 0, per_sm = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess)
+        return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KernelFor(variant, uniform), kBlock, plan->shared);
+    if (err != cudaSuccess)
+        return err;
+    if (per_sm < 1)
+        return cudaErrorLaunchOutOfResources;
+    plan->grid = sms * per_sm;     // persistent: every SM holds its full share of CTAs
+    return cudaSuccess;
+}
+
+cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream)
+{
+    if (a.n == 0)
+        return cudaSuccess;
+    uint64_t units = (a.n + 31) / 32;
+    uint64_t want = (units + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
+    void* args[] = {const_cast<ScanArgs*>(&a)};
+    cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
+    if (err == cudaSuccess)
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    return err;
+}
+
+cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream)
+{
+    if (a.n == 0)
+        return cudaSuccess;
+    int grid = (int) ((a.n + 255) / 256);
+    VisitCountKernel<<<grid, 256, 0, stream>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream)
+{
+    if (p.n_strings == 0)
+        return cudaSuccess;
+    uint64_t total = p.n_strings * (p.string_len / 16);
+    uint64_t blocks = (total + 255) / 256;
+    int grid = (int) (blocks < 148ull * 64 ? blocks : 148ull * 64);
+    SynthKernel<<<grid, 256, 0, stream>>>(p, d_plants, d_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+uint64_t KernelLaunchCount() { return g_launches.load(std::memory_order_relaxed); }
+
+} // namespace pire_b200

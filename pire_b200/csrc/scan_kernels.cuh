@@ -1,0 +1,56 @@
+// scan_kernels.cuh -- launch interface between the C ABI (capi.cu) and the
+// sm_100a kernels (scan_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "synth.h"
+
+namespace pire_b200 {
+
+struct DeviceFin {
+    uint32_t result;    // bit31 Final, low bits StateIndex (reference numbering)
+    uint32_t mask;      // accepted regexp ids < 32
+};
+
+// Everything a scan launch reads.  Device pointers.
+struct ScanArgs {
+    const uint8_t* corpus;
+    const uint64_t* offsets;     // CSR (n+1) or nullptr
+    uint64_t fixed_len;          // used when offsets == nullptr
+    uint64_t n;                  // strings
+    const uint8_t* hot8;         // (hot+1)*256 bytes, 16-byte aligned
+    const uint8_t* noexit;       // hot+1 bytes
+    const uint16_t* cls;         // 256
+    const void* full;            // states*letters, u16 or u32
+    const DeviceFin* fin;        // [states] for the chosen with_end
+    uint32_t hot;                // H
+    uint32_t letters;
+    uint32_t wide;               // full is u32
+    uint32_t start;              // state after Initialize()[+Begin()], new numbering
+    uint32_t exit_bitmap0;
+    uint32_t* match_bits;        // may be null
+    uint32_t* accept_masks;      // may be null
+    uint32_t* state_idx;         // may be null
+    unsigned long long* visits;  // tune kernel only: per-state visit counters (new numbering)
+};
+
+struct LaunchPlan {
+    int block = 0;
+    int grid = 0;
+    size_t shared = 0;
+};
+
+enum ScanVariant { kVariantPlain = 1, kVariantPred = 2 };
+
+size_t ScanSharedBytes(uint32_t hot);
+cudaError_t PrepareScanKernels(int device);                       // raises the dynamic smem limit
+cudaError_t PlanScan(int device, uint32_t hot, int variant, bool uniform, LaunchPlan* plan);
+cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
+cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
+cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream);
+
+uint64_t KernelLaunchCount();
+
+} // namespace pire_b200

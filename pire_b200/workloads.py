@@ -1,0 +1,97 @@
+"""The BASELINE.json workloads: pattern sets and synthetic corpora.
+
+The reference names no canonical 10-pattern set; this one starts from the four
+RE2-paper patterns of tools/bench/run-bench:62-65,:72-75 and adds the headline
+pattern of BASELINE.json plus five log-style patterns (SURVEY.md App. D set B),
+glued left to right like tools/bench/bench.cpp:108-132.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+HEADLINE = (rb"hello\s+w.+d$", "")
+
+GLUE10 = [
+    (rb"ABCDEFGHIJKLMNOPQRSTUVWXYZ$", ""),
+    (rb"[XYZ]ABCDEFGHIJKLMNOPQRSTUVWXYZ$", ""),
+    (rb"[ -~]*ABCDEFGHIJKLMNOPQRSTUVWXYZ$", ""),
+    (rb"(\d{3}-|\(\d{3}\)\s+)(\d{3}-\d{4})$", ""),
+    HEADLINE,
+    (rb"error", ""),
+    (rb"fatal", ""),
+    (rb"https?://", ""),
+    (rb"^GET ", ""),
+    (rb"timeout$", ""),
+]
+
+# One literal per regexp id; a leading '^' / '$' pins it to the start / end of the
+# string (the anchored patterns), otherwise it lands at a pseudo-random offset.
+GLUE10_PLANTS = [
+    b"$ABCDEFGHIJKLMNOPQRSTUVWXYZ",
+    b"$XABCDEFGHIJKLMNOPQRSTUVWXYZ",
+    b"$ABCDEFGHIJKLMNOPQRSTUVWXYZ",
+    b"$(555) 123-4567",
+    b"$hello \t world",
+    b"error",
+    b"fatal",
+    b"https://",
+    b"^GET ",
+    b"$timeout",
+]
+
+HEADLINE_PLANTS = [b"$hello \t world"]
+
+
+class SynthSpec:
+    """Deterministic printable-ASCII corpus (pire_b200/csrc/synth.h)."""
+
+    def __init__(self, n_strings, string_len=1024, seed=42, plant_every=8, plants=(), first_string=0):
+        self.n_strings, self.string_len, self.seed = int(n_strings), int(string_len), int(seed)
+        self.plant_every, self.plants, self.first_string = int(plant_every), list(plants), int(first_string)
+
+    def _c(self, first_string=None, n=None):
+        blob = b"\0".join(self.plants) + b"\0"
+        s = N.Synth()
+        s.seed = self.seed
+        s.first_string = self.first_string if first_string is None else first_string
+        s.n_strings = self.n_strings if n is None else n
+        s.string_len = self.string_len
+        s.kind = 0
+        s.plant_every = self.plant_every if self.plants else 0
+        s.n_plants = len(self.plants)
+        s.plants = blob
+        s.plants_bytes = len(blob)
+        s.tail = 0
+        s._keep = blob
+        return s
+
+    def total_bytes(self):
+        return self.n_strings * self.string_len
+
+    def fill_device(self, tensor, stream=None):
+        """Write the whole corpus into a uint8 CUDA tensor of total_bytes()."""
+        import torch
+        assert tensor.is_cuda and tensor.dtype == torch.uint8 and tensor.numel() >= self.total_bytes()
+        if stream is None:
+            stream = torch.cuda.current_stream(tensor.device).cuda_stream
+        s = self._c()
+        N.check(N.lib.pire_gpu_synth_fill_device(C.byref(s), tensor.data_ptr(), tensor.device.index or 0, stream),
+                "pire_gpu_synth_fill_device")
+        return tensor
+
+    def host_sample(self, first, count):
+        """Strings [first, first+count) of the same corpus, generated on the host."""
+        out = np.empty(count * self.string_len, np.uint8)
+        s = self._c()
+        N.check(N.lib.pire_gpu_synth_fill_host(C.byref(s), out.ctypes.data, first, count), "pire_gpu_synth_fill_host")
+        return out
+
+    def shard(self, rank, world):
+        """Contiguous string-index shard, boundaries aligned to 32 strings so bitmap words never straddle ranks."""
+        per = (self.n_strings + world - 1) // world
+        per = (per + 31) // 32 * 32
+        lo = min(self.n_strings, rank * per)
+        hi = min(self.n_strings, lo + per)
+        return SynthSpec(hi - lo, self.string_len, self.seed, self.plant_every, self.plants, self.first_string + lo), lo

@@ -1,0 +1,66 @@
+import base64
+import json
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (HERE, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+class GoldenCase:
+    def __init__(self, d):
+        self.name = d["name"]
+        self.patterns = [(bytes.fromhex(p), o) for p, o in d["patterns"]]
+        self.image = base64.b64decode(d["image"])
+        self.strings = [bytes.fromhex(s) for s in d["strings"]]
+        self.final = d["final"]
+        self.ids = d["ids"]
+        self.state = d["state"]
+        self.begin = bool(d["begin"])
+        self.end = bool(d["end"])
+        self.states, self.letters, self.regexps = d["states"], d["letters"], d["regexps"]
+
+    def mask(self):
+        return [sum(1 << i for i in ids if i < 32) for ids in self.ids]
+
+    def __repr__(self):
+        return "GoldenCase(%s)" % self.name
+
+
+def load_golden():
+    with open(os.path.join(HERE, "golden", "pire_golden.json")) as f:
+        return [GoldenCase(c) for c in json.load(f)["cases"]]
+
+
+GOLDEN = load_golden()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The real reference (oracle/_ref); absent when neither /root/reference nor a prebuilt copy exists."""
+    import refpire
+    if not refpire.have_ref():
+        pytest.skip("oracle/_ref/libpire_ref.so not built (needs /root/reference)")
+    return refpire.Ref()
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("this test is marked gpu but no CUDA device is visible")
+    return 0

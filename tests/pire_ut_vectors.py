@@ -1,0 +1,78 @@
+"""Known-answer vectors of the reference's own unit tests for the scan path.
+
+Transcribed from /root/reference/tests/pire_ut.cpp (ACCEPTS / DENIES macros,
+tests/common.h:195-221).  Each ACCEPTS(str) there asserts that
+``Initialize; Step(BeginMark); Run(str); Step(EndMark)`` (tests/common.h:158-169)
+ends in a state with a non-empty AcceptedRegexps list; DENIES asserts the
+opposite.  Patterns are compiled like tests/common.h:40-69 (ParseRegexp): the
+option letters are 'i' CaseInsensitive, 'u' UTF-8, 'n' no Surround(), 'a' AndNot.
+
+Only tests expressible as (pattern, options) are listed; the Fsm-algebra cases
+(Misc's ``& ~``, Reverse) are compile-time features outside the scan path.
+"""
+
+# (test name @ line in pire_ut.cpp, pattern, options, accepts, denies)
+VECTORS = [
+    ("String@38", b"abc", "", [b"def abc ghi", b"abc"], [b"def abd ghi"]),
+    ("Boundaries@47a", b"^abc", "", [b"abc ghi"], [b"def abc"]),
+    ("Boundaries@47b", b"abc$", "", [b"def abc"], [b"abc ghi"]),
+    ("Primitives@60a", b"abc|def", "", [b"def", b"abc"], [b"deb"]),
+    ("Primitives@60b", b"ad*e", "", [b"xaez", b"xadez", b"xaddez", b"xadddddddddddddddddddddddez"], [b"xafez"]),
+    ("Primitives@60c", b"ad+e", "", [b"xadez", b"xaddez", b"xadddddddddddddddddddddddez"], [b"xaez", b"xafez"]),
+    ("Primitives@60d", b"ad?e", "", [b"xaez", b"xadez"], [b"xaddez", b"xafez"]),
+    ("Primitives@60e", b"a.{1}e", "", [b"axe"], [b"ae", b"axye"]),
+    ("MassAlternatives@109a", b"((abc|def)|ghi)|klm", "", [b"abc", b"def", b"ghi", b"klm"], [b"aei", b"klc"]),
+    ("MassAlternatives@109b", b"(abc|def)|(ghi|klm)", "", [b"abc", b"def", b"ghi", b"klm"], [b"aei", b"klc"]),
+    ("MassAlternatives@109c", b"abc|(def|(ghi|klm))", "", [b"abc", b"def", b"ghi", b"klm"], [b"aei", b"klc"]),
+    ("MassAlternatives@109d", b"abc|(def|ghi)|klm", "", [b"abc", b"def", b"ghi", b"klm"], [b"aei", b"klc"]),
+    ("Composition@120a", rb"^/([^\\/]|\\.)*/[a-z]*$", "",
+     [b"/regexp/i", b"/regexp2/", b"/dir\\/file/", b"/dir\\\\/"],
+     [b"regexp", b"/dir/file/", b"/dir\\\\/file/"]),
+    ("Composition@120b", b"Head(Inner)*Tail", "",
+     [b"HeadInnerTail", b"HeadInnerInnerTail", b"HeadTail"], [b"HeadInneInnerTail"]),
+    ("Repetition@142a", b"^x{3,6}$", "", [b"xxx", b"xxxx", b"xxxxx", b"xxxxxx"], [b"xx", b"xxxxxxx"]),
+    ("Repetition@142b", b"^x{3,}$", "", [b"xxx", b"xxxx", b"x" * 11, b"x" * 47], [b"xx"]),
+    ("Repetition@142c", b"^x{3}$", "", [b"xxx"], [b"x", b"xx", b"xxxx", b"xxxxx", b"x" * 47]),
+    ("Repetition@142d", b"x.{3,10}$", "",
+     [b"b" * (2 * n) + b"x" + b"e" * n for n in range(20) if 3 <= n <= 10],
+     [b"b" * (2 * n) + b"x" + b"e" * n for n in range(20) if not 3 <= n <= 10]),
+    ("UTF8@181a", b"^.$", "u",
+     [b"\x41", b"\xC1\x81", b"\xE1\x81\x82", b"\xF1\x81\x82\x83"],
+     [b"\x81", b"\xC1", b"\xC1\x41", b"\xC1\xC2", b"\xC1\x81\x82", b"\xE1", b"\xE1\x42", b"\xE1\x42\x43",
+      b"\xE1\xC2\xC3", b"\xE1\x82", b"\xE1\x82\x83\x84"]),
+    ("UTF8@181b", b"x\xD0\xA4y", "u", [b"x\xD0\xA4y"], []),
+    ("AndNot@211a", b"<([0-9]+&~123&~456)>", "a", [b"<111>", b"<124>"], [b"<123>", b"<456>", b"<abc>"]),
+    ("AndNot@211b", rb"[0-9]+\&1+", "a", [b"123&111"], [b"111"]),
+    ("Misc@238a", rb"^[^\s=/>]*$", "n", [b"a"], []),
+    ("Misc@238b", rb"\t", "", [b"\t"], []),
+    ("Ranges@251", rb"a\W", "", [b"a,"], [b"ab"]),
+    ("TestShortcuts@628a", b"aaa", "",
+     [b"." * 38 + b"aaa" + b"." * 13], [b"." * 38 + b"aab" + b"." * 13, b"." * 54]),
+    ("TestShortcuts@628b", b"[ab]{3}", "",
+     [b"." * 38 + b"aaa" + b"." * 13, b"." * 38 + b"aab" + b"." * 13, b"." * 38 + b"bbb" + b"." * 13], [b"." * 54]),
+    ("TestShortcuts@628c", b"\xD0\xB0", "u",
+     [b"." * 38 + b"\xD0\xB0" + b"." * 15, b"." * 35 + b"\xD0\xB0" + b"." * 18, b"." * 32 + b"\xD0\xB0" + b"." * 21], []),
+    ("Aligned@729a", b"xy", "", [b"xy"], [b"yz"]),
+    ("Aligned@729b", b"abcde", "",
+     [b"ZZZZZabcdeZZZZZZ", b"ZabcdeZZZ", b"ZZZZZZZZZZZZZabcde"],
+     [b"ZZZZZabcdfZZZZZZ", b"ZxbcdeZZZ", b"ZZZZZZZZZZZZZabcdf"]),
+    # README:58-70 -- "Hello world" against the case-insensitive UTF-8 headline regexp
+    ("README@58", rb"hello\s+w.+d$", "iu", [b"Hello world", b"hello  w..d"], [b"hello wd", b"hello world!"]),
+    # SURVEY.md Appendix A answers for the headline regexp (Latin-1, case-sensitive)
+    ("AppendixA", rb"hello\s+w.+d$", "",
+     [b"hello world", b"hello  w..d", b"xx hello\tworld"], [b"Hello world", b"hello wd", b"hello world!", b""]),
+]
+
+# Aligned@729: the same strings are also run at unaligned addresses there; the
+# parity tests place every vector at several byte offsets inside the corpus.
+
+# TestGlue@648-693: glue "aaa" + "bbb", then "ccc" in front; exact accept-id lists.
+GLUE_CASES = [
+    # (patterns glued left to right as (pattern, opts), [(string, expected ids)])
+    ([(b"aaa", ""), (b"bbb", "")],
+     [(b"aaa", [0]), (b"bbb", [1]), (b"aaabbb", [0, 1]), (b"ccc", [])]),
+    ([(b"ccc", ""), (b"aaa", ""), (b"bbb", "")],      # Glue(sc3, glued): ids shift by one
+     [(b"ccc", [0]), (b"aaa", [1]), (b"bbb", [2]), (b"aaabbbccc", [0, 1, 2])]),
+    ([(b"a", "n"), (b"c", "n")],
+     [(b"ac", [])]),
+]
