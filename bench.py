@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- scanned GB/s of the Pire hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the scan path over one batch of synthetic strings that is
+already resident in HBM: Runner(sc).Begin().Run(str).End() for every string of the
+batch (pire/run.h:365-392), producing the packed match bitmap and the per-string
+accepted-regexp mask; with N > 1 the batch is sharded by string (weak scaling:
+every GPU holds its own 10 GB shard) and the step ends with the one NCCL
+all-reduce of the match bitmap.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload glue10|headline]
+  python bench.py --impl reference ...     # the reference's own CPU scan (oracle/_ref)
+
+One JSON line on stdout (rank 0).  Keys follow the driver's contract; `roofline`
+is for the scan kernel (algorithmic bytes = payload bytes, 1 B read per input
+byte), `e2e` goes through the host-buffer C-ABI call with pinned
+host memory (H2D + D2H inside the timed region), `cpu_baseline` is the reference
+library timed on this box's host cores on a bounded sample of the same corpus.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+STRING_LEN = 1024
+STRINGS_PER_GPU = 9_765_632          # x 1 KiB = 10.000007 GB per GPU (multiple of 32 strings)
+FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
+    ap.add_argument("--workload", default="glue10", choices=["glue10", "headline"])
+    ap.add_argument("--strings", type=int, default=STRINGS_PER_GPU, help="strings per GPU")
+    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred"])
+    ap.add_argument("--no-tune", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--collective", default="allreduce", choices=["allreduce", "allgather"])
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="strings in the CPU-baseline sample")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def cpu_reference(workload, threads, n_sample, reps, first_string=0):
+    """The reference's own scan, Runner(sc).Begin().Run().End() per string with NonrelocScanner
+    (its fastest variant, multi.h:1119-1123), statically partitioned over `threads` host threads."""
+    from refpire import Ref
+    from pire_b200 import workloads as W
+    ref = Ref()
+    patterns = W.GLUE10 if workload == "glue10" else [W.HEADLINE]
+    sc = ref.glue_all(patterns)
+    _, plants, _, _ = W.WORKLOADS[workload]
+    spec = W.SynthSpec(n_sample, STRING_LEN, plants=plants, first_string=first_string)
+    sample = spec.host_sample(0, n_sample)
+    if threads <= 0:
+        threads = ref.hardware_threads()
+    best, matches = 1e30, 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        final, mask, _ = sc.run(sample, fixed_len=STRING_LEN, n=n_sample, variant=1, threads=threads,
+                                want=("final", "mask"))
+        best = min(best, time.perf_counter() - t0)
+        matches = int(final.sum())
+    # single-thread figures on a slice, both with and without the ExitMasks fast-forward
+    k = min(n_sample, 1 << 16)
+    t0 = time.perf_counter()
+    sc.run(sample[: k * STRING_LEN], fixed_len=STRING_LEN, n=k, variant=1, threads=1, want=("final",))
+    t_mask = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sc.run(sample[: k * STRING_LEN], fixed_len=STRING_LEN, n=k, variant=2, threads=1, want=("final",))
+    t_nomask = time.perf_counter() - t0
+    gb = n_sample * STRING_LEN / 1e9
+    return {
+        "value": gb / best, "unit": "GB/s", "cores": threads, "kind": "reference",
+        "sample": "%d x %d B strings of the same synthetic corpus (%.2f GB), best of %d, NonrelocScanner" % (
+            n_sample, STRING_LEN, gb, reps),
+        "matches": matches,
+        "one_thread_GBps": k * STRING_LEN / 1e9 / t_mask,
+        "one_thread_nomask_GBps": k * STRING_LEN / 1e9 / t_nomask,
+    }
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = min(args.cpu_sample, args.strings)
+    t_all = time.perf_counter()
+    cb = cpu_reference(args.workload, 0, per_step, 1)        # warm-up + the single-thread figures
+    times = []
+    from refpire import Ref
+    from pire_b200 import workloads as W
+    ref = Ref()
+    sc = ref.glue_all(W.GLUE10 if args.workload == "glue10" else [W.HEADLINE])
+    spec = W.SynthSpec(per_step, STRING_LEN, plants=W.WORKLOADS[args.workload][1])
+    sample = spec.host_sample(0, per_step)
+    threads = ref.hardware_threads()
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        sc.run(sample, fixed_len=STRING_LEN, n=per_step, variant=1, threads=threads, want=("final", "mask"))
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = per_step * STRING_LEN * args.steps / 1e9 / total
+    cb.update(value=value, cores=threads)
+    line = {
+        "impl": "reference", "metric": "scanned GB/s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%s: %s; each step = a bounded sample of %d x 1 KiB strings on the host" % (
+            args.workload, W.WORKLOADS[args.workload][2], per_step), "host_threads": threads},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "strings_per_s": per_step * args.steps / total,
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import pire_b200 as P
+    from pire_b200 import _native as N
+    from pire_b200 import workloads as W
+    from pire_b200.dist import popcount_bits
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the scan path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    image_name, plants, desc, cfg_index = W.WORKLOADS[args.workload]
+    n_local = args.strings // 32 * 32
+    n_global = n_local * world
+    lo = rank * n_local
+    spec = W.SynthSpec(n_local, STRING_LEN, plants=plants, first_string=lo)
+    corpus = torch.empty(spec.total_bytes(), dtype=torch.uint8, device=dev)
+    spec.fill_device(corpus)
+    batch = P.Batch(corpus, fixed_len=STRING_LEN, n=n_local)
+    payload_local = n_local * STRING_LEN
+
+    sc = P.Scanner(W.load_image(image_name), local)
+    tune_ms = None
+    if not args.no_tune:
+        t0 = time.perf_counter()
+        sc.Tune(batch, min(n_local, 16384))
+        torch.cuda.synchronize()
+        tune_ms = 1e3 * (time.perf_counter() - t0)
+
+    words_local = n_local // 32
+    bits_full = torch.zeros(words_local * world, dtype=torch.int32, device=dev)
+    bits_local = bits_full[rank * words_local:(rank + 1) * words_local]
+    masks = torch.empty(n_local, dtype=torch.int32, device=dev)
+    flags = N.RUN_BEGIN | N.RUN_END
+
+    def scan():
+        sc.run_batch(batch, flags, bits_local, masks, None)
+
+    def step():
+        if world > 1 and args.collective == "allreduce":
+            # shards are disjoint and word aligned: SUM over zero-initialised words == OR
+            if rank > 0:
+                bits_full[: rank * words_local].zero_()
+            if rank < world - 1:
+                bits_full[(rank + 1) * words_local:].zero_()
+        scan()
+        if world > 1:
+            if args.collective == "allreduce":
+                dist.all_reduce(bits_full, op=dist.ReduceOp.SUM)
+            else:
+                dist.all_gather_into_tensor(bits_full, bits_local.clone())
+
+    def time_scan(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            scan()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # kernel variant: measured, not guessed
+    variant_ms = {}
+    if args.variant == "auto":
+        for name, v in (("plain", N.VARIANT_PLAIN), ("pred", N.VARIANT_PRED)):
+            sc.set_variant(v)
+            time_scan(1)
+            variant_ms[name] = time_scan(2)
+        chosen = min(variant_ms, key=variant_ms.get)
+    else:
+        chosen = args.variant
+    sc.set_variant(N.VARIANT_PLAIN if chosen == "plain" else N.VARIANT_PRED)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    launches0 = N.lib.pire_gpu_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    torch.cuda.synchronize()
+    t_begin = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = N.lib.pire_gpu_launch_count() - launches0
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_global * STRING_LEN / 1e9 / (ms_per_step / 1e3)
+
+    # the scan kernel alone (CUDA events around the launches only), for the roofline
+    kernel_ms = time_scan(min(args.steps, 10))
+    matches_global = popcount_bits(bits_full if world > 1 else bits_local)
+    matches_local_masks = int((masks != 0).sum().item())
+
+    # end to end: host buffers through the C ABI, H2D and D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            host = torch.empty(payload_local, dtype=torch.uint8, pin_memory=True)
+            host.copy_(corpus)
+            torch.cuda.synchronize()
+            hb = torch.empty(words_local, dtype=torch.int32, pin_memory=True)
+            hm = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+            hv = host.numpy()
+
+            def e2e_step():
+                N.check(N.lib.pire_gpu_run_batch_host(sc._h, hv.ctypes.data, payload_local, None, STRING_LEN, n_local,
+                                                      flags, hb.data_ptr(), hm.data_ptr(), None), "run_batch_host")
+            e2e_step()
+            e2e_steps = max(1, min(args.steps, 3))
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            assert torch.equal(hb, bits_local.cpu()) and torch.equal(hm, masks.cpu())
+            e2e = {"value": n_global * STRING_LEN / 1e9 / (dt / e2e_steps), "unit": "GB/s",
+                   "h2d_bytes_per_step": payload_local, "d2h_bytes_per_step": words_local * 4 + n_local * 4,
+                   "steps": e2e_steps, "api": "pire_gpu_run_batch_host (pinned host corpus in, bitmap + accept masks out)"}
+            del host, hv
+        except Exception as ex:          # e.g. not enough pinnable host memory
+            e2e = {"value": None, "unit": "GB/s", "error": repr(ex)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    achieved = payload_local / 1e9 / (kernel_ms / 1e3)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+    info = sc.info()
+    line = {
+        "metric": "scanned GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[%d]: %s over %d x 1 KiB synthetic printable-ASCII strings per GPU (%.2f GB/GPU), "
+                        "1/8 of the strings carry a planted match" % (cfg_index, desc, n_local, payload_local / 1e9),
+            "strings_per_gpu": n_local, "string_len": STRING_LEN, "outputs": "match bitmap + u32 accept mask per string",
+            "kernel_variant": chosen, "variant_ms": variant_ms or None, "hot_rows": info.hot_rows, "tuned": bool(info.tuned),
+            "tune_ms": tune_ms, "l2": "input (%.1f GB) is far larger than L2; no flush needed" % (payload_local / 1e9),
+            "collective": (args.collective + " of the match bitmap (NCCL)") if world > 1 else "none (1 GPU)",
+        },
+        "strings_per_s": n_global / (ms_per_step / 1e3),
+        "matches": matches_global, "matches_local_by_mask": matches_local_masks,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "ScanUniformKernel<%s>" % chosen, "kernel_ms": kernel_ms,
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": payload_local},
+        "clocks": clocks,
+        "e2e": e2e,
+    }
+    if not args.no_cpu and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_reference(args.workload, 0, min(args.cpu_sample, n_local), 3)
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

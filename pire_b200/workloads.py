@@ -95,3 +95,20 @@ class SynthSpec:
         lo = min(self.n_strings, rank * per)
         hi = min(self.n_strings, lo + per)
         return SynthSpec(hi - lo, self.string_len, self.seed, self.plant_every, self.plants, self.first_string + lo), lo
+
+
+def load_image(name):
+    """Scanner::Save() image of a BASELINE pattern set ('headline' or 'glue10'),
+    precompiled by tools/compile_patterns.py with the reference's front end."""
+    import lzma
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", name + ".pire.xz")
+    with open(path, "rb") as f:
+        return lzma.decompress(f.read())
+
+
+WORKLOADS = {
+    # name: (image, plants, description, BASELINE.json config index)
+    "headline": ("headline", HEADLINE_PLANTS, r"single regex hello\s+w.+d$ (NonrelocScanner DFA: 11 states)", 1),
+    "glue10": ("glue10", GLUE10_PLANTS, "10 regexes glued into one multi-Scanner (29664 states x 54 letters)", 2),
+}

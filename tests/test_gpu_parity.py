@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+Checkers, in order of authority:
+  1. committed golden fixtures generated from the real reference;
+  2. the real reference itself (oracle/_ref/libpire_ref.so travels to the GPU box);
+  3. the C restatement oracle/pire_oracle.c.
+Bar: bit-exact match bits, accept masks and StateIndex for every string.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from refpire import Oracle, csr
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_run(sc, strings, begin=True, end=True):
+    import pire_b200 as P
+    batch = P.Batch.from_strings(strings)
+    r = P.Runner(sc)
+    if begin:
+        r.Begin()
+    r.Run(batch)
+    if end:
+        r.End()
+    return r.Matches().astype(np.uint8), r.AcceptMasks(), r.States()
+
+
+def checker_run(image, strings, begin, end, ref_sc=None):
+    corpus, offs = csr(strings)
+    if ref_sc is not None:
+        return ref_sc.run(corpus, offs, begin=begin, end=end, variant=0)
+    return Oracle(image).run(corpus, offs, begin=begin, end=end)
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["plain", "pred"])
+@pytest.mark.parametrize("case", GOLDEN, ids=lambda c: c.name)
+def test_golden_vectors(case, variant, cuda_device):
+    import pire_b200 as P
+    sc = P.Scanner(case.image, cuda_device)
+    sc.set_variant(variant)
+    final, mask, state = gpu_run(sc, case.strings, case.begin, case.end)
+    assert final.tolist() == case.final
+    assert mask.tolist() == case.mask()
+    if not sc.Empty():
+        assert state.tolist() == case.state
+    for i, ids in enumerate(case.ids):
+        assert sc.AcceptedRegexps(int(state[i])) == ids
+
+
+def test_alignment_and_ragged_lengths(cuda_device):
+    """pire_ut.cpp Aligned@729 and the head/body/tail split of run.h:186-226: every
+    golden string at every start alignment 0..31, surrounded by junk strings of
+    ragged lengths (0..70), empty strings included."""
+    import pire_b200 as P
+    rng = np.random.default_rng(3)
+    for case in [c for c in GOLDEN if c.begin and c.name.split("@")[0] in ("Aligned", "TestShortcuts", "String", "UTF8")]:
+        sc = P.Scanner(case.image, cuda_device)
+        strings, expect = [], []
+        for shift in range(32):
+            for s, f in zip(case.strings, case.final):
+                strings.append(bytes(rng.integers(0x20, 0x7F, size=shift, dtype=np.uint8)))
+                expect.append(None)
+                strings.append(s)
+                expect.append(f)
+                strings.append(b"")
+                expect.append(None)
+        junk = [bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8)) for n in rng.integers(0, 70, size=50)]
+        strings += junk
+        expect += [None] * len(junk)
+        final, mask, state = gpu_run(sc, strings)
+        f2, m2, s2 = checker_run(case.image, strings, True, True)
+        assert (final == f2).all() and (mask == m2).all() and (state == s2).all(), case.name
+        for got, want in zip(final.tolist(), expect):
+            assert want is None or got == want
+
+
+def test_mark_flag_combinations(cuda_device, ref):
+    import pire_b200 as P
+    sc_ref = ref.compile(rb"^abc$|x+y", "")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    strings = [b"abc", b"zabc", b"abcz", b"xxy", b"", b"x", b"y" * 40 + b"xy", b"abc" * 20]
+    for begin in (False, True):
+        for end in (False, True):
+            got = gpu_run(sc, strings, begin, end)
+            want = checker_run(None, strings, begin, end, sc_ref)
+            for g, w in zip(got, want):
+                assert (g == w).all(), (begin, end)
+
+
+def test_empty_batch_and_empty_scanner(cuda_device):
+    import torch
+    import pire_b200 as P
+    case = next(c for c in GOLDEN if c.name == "EmptyScanner@784")
+    sc = P.Scanner(case.image, cuda_device)
+    assert sc.Empty() and sc.RegexpsCount() == 0
+    final, mask, _ = gpu_run(sc, [b"a string", b"", b"regex" * 100])
+    assert final.tolist() == [0, 0, 0] and mask.tolist() == [0, 0, 0]
+    # n == 0 is a no-op (pire_ut.cpp NullPointer@832: Run(nullptr, nullptr) is legal)
+    batch = P.Batch(torch.zeros(32, dtype=torch.uint8, device="cuda:0"), fixed_len=0, n=0)
+    assert P.Runner(sc).Begin().Run(batch).End().Matches().size == 0
+    # n > 0 strings of length zero
+    batch = P.Batch(torch.zeros(32, dtype=torch.uint8, device="cuda:0"), fixed_len=0, n=5)
+    sc2 = P.Scanner(next(c for c in GOLDEN if c.name == "Misc@238a").image, cuda_device)
+    assert P.Runner(sc2).Begin().Run(batch).End().Matches().tolist() == [True] * 5   # ^[^\s=/>]*$ accepts ""
+
+
+def random_text(rng, n, length, alphabet=None):
+    if alphabet is None:
+        return rng.integers(0x20, 0x7F, size=(n, length), dtype=np.uint8)
+    return rng.choice(np.frombuffer(alphabet, np.uint8), size=(n, length))
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["plain", "pred"])
+def test_uniform_kernel_headline(variant, cuda_device, ref):
+    """Fixed 1 KiB strings (the BASELINE configs' shape) through the uniform kernel,
+    full comparison with the reference on 64 Ki strings, incl. StateIndex."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    sc_ref = ref.compile(*W.HEADLINE)
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    sc.set_variant(variant)
+    n = 65536 + 7                      # ragged last warp
+    spec = W.SynthSpec(n, 1024, plants=W.HEADLINE_PLANTS)
+    dev = torch.empty(spec.total_bytes(), dtype=torch.uint8, device="cuda:0")
+    spec.fill_device(dev)
+    host = spec.host_sample(0, n)
+    assert (dev.cpu().numpy() == host).all()          # host and device generators agree
+    r = P.Runner(sc).Begin().Run(P.Batch(dev, fixed_len=1024, n=n)).End()
+    f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=n, variant=1, threads=8)
+    assert (r.Matches().astype(np.uint8) == f_ref).all()
+    assert (r.AcceptMasks() == m_ref).all()
+    assert (r.States() == s_ref).all()
+    assert int(f_ref.sum()) == (n + 7) // 8
+    # bits past n in the last bitmap word are zero
+    words = r.MatchBits().cpu().numpy().view(np.uint32)
+    assert int(words[-1]) >> (n % 32) == 0
+
+
+@pytest.mark.parametrize("max_hot,tune", [(255, False), (255, True), (6, False), (2, True)],
+                         ids=["static", "tuned", "hot6", "hot2-tuned"])
+def test_glued_ten_patterns(max_hot, tune, cuda_device, ref):
+    """The 10-regexp glued scanner (29 664 states): hot rows in shared memory, the
+    rest replayed through the L2-resident table.  Tiny hot sets force the replay
+    and cold-state paths on almost every chunk."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    sc_ref = ref.glue_all(W.GLUE10)
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    assert (sc.Size(), sc.RegexpsCount()) == (sc_ref.size, 10)
+    n = 16384
+    spec = W.SynthSpec(n, 1024, plants=W.GLUE10_PLANTS)
+    dev = torch.empty(spec.total_bytes(), dtype=torch.uint8, device="cuda:0")
+    spec.fill_device(dev)
+    batch = P.Batch(dev, fixed_len=1024, n=n)
+    sc.set_max_hot(max_hot)
+    if tune:
+        sc.Tune(batch, 4096)
+        assert sc.info().tuned == 1
+    host = spec.host_sample(0, n)
+    f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=n, variant=1, threads=8)
+    assert int((m_ref != 0).sum()) >= n // 8
+    for variant in (1, 2):
+        sc.set_variant(variant)
+        r = P.Runner(sc).Begin().Run(batch).End()
+        assert (r.Matches().astype(np.uint8) == f_ref).all()
+        assert (r.AcceptMasks() == m_ref).all()
+        assert (r.States() == s_ref).all()
+    # every planted literal is reported under its own regexp id
+    for i in range(0, 80, 8):
+        assert m_ref[i] & (1 << ((i // 8) % 10))
+
+
+def test_generic_kernel_mixed_lengths_utf8(cuda_device, ref):
+    """BASELINE config 4's shape: UTF-8 + CaseInsensitive pattern, lengths 16 B..64 KiB
+    (CSR offsets), bytes from the whole 0..255 range."""
+    import pire_b200 as P
+    sc_ref = ref.compile(rb"hello\s+w.+d$", "iu")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    rng = np.random.default_rng(11)
+    lens = np.exp(rng.uniform(np.log(16), np.log(65536), size=600)).astype(int)
+    alphabet = b"abcdehlorw HELOWRD\t" + "привет мир".encode() + bytes(range(0x20, 0x7F))
+    strings = []
+    for i, n in enumerate(lens):
+        body = bytearray(random_text(rng, 1, int(n), alphabet)[0].tobytes())
+        if i % 5 == 0:
+            hit = b"HeLLo \t WoRLD"
+            body[-len(hit):] = hit
+        strings.append(bytes(body))
+    got = gpu_run(sc, strings)
+    want = checker_run(None, strings, True, True, sc_ref)
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    assert int(want[0].sum()) >= len(strings) // 5
+
+
+def test_noexit_early_stop_is_exact(cuda_device, ref):
+    """multi.h:955-958: a state no byte can leave ends the walk early; End() must still be
+    stepped.  'foo' un-anchored parks every matching string in an absorbing state."""
+    import pire_b200 as P
+    sc_ref = ref.compile(rb"foo", "")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    rng = np.random.default_rng(5)
+    strings = [b"foo" + bytes(random_text(rng, 1, 4000)[0]) for _ in range(64)]      # whole warps park
+    strings += [bytes(random_text(rng, 1, 4000)[0]) for _ in range(32)]
+    strings += [b"x" * 100 + b"foo" + b"y" * 3000 for _ in range(16)] + [b"fo" * 900 for _ in range(16)]
+    got = gpu_run(sc, strings)
+    want = checker_run(None, strings, True, True, sc_ref)
+    for g, w in zip(got, want):
+        assert (g == w).all()
+
+
+def test_host_buffer_entry_point(cuda_device, ref):
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    sc_ref = ref.compile(*W.HEADLINE)
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    spec = W.SynthSpec(4096, 1024, plants=W.HEADLINE_PLANTS)
+    host = spec.host_sample(0, 4096)
+    bits, masks, states = sc.run_batch_host(host, fixed_len=1024, n=4096, want_masks=True, want_states=True)
+    f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=4096)
+    got = np.unpackbits(bits.view(np.uint8), bitorder="little")[:4096]
+    assert (got == f_ref).all() and (masks == m_ref).all() and (states == s_ref).all()
+    # CSR through the same entry point
+    strings = [bytes(host[i * 1024: i * 1024 + 100 + i]) for i in range(200)]
+    corpus, offs = csr(strings)
+    bits, masks, states = sc.run_batch_host(corpus, offsets=offs, want_masks=True, want_states=True)
+    f_ref, m_ref, s_ref = sc_ref.run(corpus, offs)
+    assert (np.unpackbits(bits.view(np.uint8), bitorder="little")[:200] == f_ref).all() and (states == s_ref).all()
+
+
+def test_full_size_properties(cuda_device, ref):
+    """BASELINE config 1 at full size (2^20 x 1 KiB): the match vector is bit-exact against
+    the reference run on all host cores; at 4x that size only size-independent
+    properties are checked (planted count, determinism, shard decomposition)."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    from pire_b200.dist import shard_bounds
+    sc_ref = ref.compile(*W.HEADLINE)
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    n = 1 << 20
+    spec = W.SynthSpec(n, 1024, plants=W.HEADLINE_PLANTS)
+    dev = torch.empty(spec.total_bytes(), dtype=torch.uint8, device="cuda:0")
+    spec.fill_device(dev)
+    r = P.Runner(sc).Begin().Run(P.Batch(dev, fixed_len=1024, n=n)).End()
+    got = r.Matches()
+    host = dev.cpu().numpy()
+    f_ref, _, _ = sc_ref.run(host, fixed_len=1024, n=n, variant=1, threads=ref.hardware_threads(), want=("final",))
+    assert (got.astype(np.uint8) == f_ref).all()
+    assert int(got.sum()) == n // 8
+    del host
+    # shards of the same corpus give the same bits as the whole
+    whole = r.MatchBits().cpu().numpy()
+    parts = []
+    for rank in range(4):
+        lo, hi = shard_bounds(n, rank, 4)
+        sub = P.Batch(dev[lo * 1024: hi * 1024], fixed_len=1024, n=hi - lo)
+        parts.append(P.Runner(sc).Begin().Run(sub).End().MatchBits().cpu().numpy())
+    assert (np.concatenate(parts) == whole).all()
