@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
     ap.add_argument("--workload", default="glue10", choices=["glue10", "headline"])
     ap.add_argument("--strings", type=int, default=STRINGS_PER_GPU, help="strings per GPU")
-    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv"])
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -256,14 +256,14 @@ def main():
     # kernel variant: measured, not guessed
     variant_ms = {}
     if args.variant == "auto":
-        for name, v in (("plain", N.VARIANT_PLAIN), ("pred", N.VARIANT_PRED)):
+        for name, v in (("plain", N.VARIANT_PLAIN), ("pred", N.VARIANT_PRED), ("priv", N.VARIANT_PRIV)):
             sc.set_variant(v)
             time_scan(1)
             variant_ms[name] = time_scan(2)
         chosen = min(variant_ms, key=variant_ms.get)
     else:
         chosen = args.variant
-    sc.set_variant(N.VARIANT_PLAIN if chosen == "plain" else N.VARIANT_PRED)
+    sc.set_variant({"plain": N.VARIANT_PLAIN, "pred": N.VARIANT_PRED, "priv": N.VARIANT_PRIV}[chosen])
 
     def barrier():
         if world > 1:
@@ -362,7 +362,7 @@ def main():
         "matches": matches_global, "matches_local_by_mask": matches_local_masks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "ScanUniformKernel<%s>" % chosen, "kernel_ms": kernel_ms,
+                     "traffic": traffic, "kernel": "ScanUniformPrivKernel" if chosen == "priv" else "ScanUniformKernel<%s>" % chosen, "kernel_ms": kernel_ms,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": payload_local},
         "clocks": clocks,

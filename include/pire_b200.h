@@ -51,7 +51,8 @@ enum {
 enum {
     PIRE_GPU_VARIANT_AUTO = 0,
     PIRE_GPU_VARIANT_PLAIN = 1,    /* one shared-memory load per byte, unconditional */
-    PIRE_GPU_VARIANT_PRED = 2      /* load predicated off while the resident state self-loops */
+    PIRE_GPU_VARIANT_PRED = 2,     /* load predicated off while the resident state self-loops */
+    PIRE_GPU_VARIANT_PRIV = 3      /* hottest rows replicated per bank: conflict-free loads (fixed-length ASCII-heavy batches) */
 };
 
 typedef struct pire_gpu_info {

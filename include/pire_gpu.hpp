@@ -1,0 +1,199 @@
+// pire_gpu.hpp -- header-only C++ mirror of Pire's Scanner / Runner / Matches
+// surface over the C ABI of include/pire_b200.h.
+//
+// For a code base that already uses Pire:
+//
+//     Pire::Scanner sc = Pire::Lexer("hello\\s+w.+d$").Parse().Surround().Compile<Pire::Scanner>();
+//     Pire::Gpu::Scanner gsc(sc, /*device*/ 0);              // Scanner::Save() -> device tables
+//     Pire::Gpu::Batch batch{d_corpus, d_offsets, 0, n};     // strings resident in HBM
+//     Pire::Gpu::BatchRunner r = Pire::Gpu::Runner(gsc);
+//     r.Begin().Run(batch).End();                            // run.h:365-392, for the whole batch
+//     r.Matches(i);  r.AcceptedRegexps(i);
+//
+// Pire::Gpu::Scanner also satisfies the reference's compile-time "Scanner concept"
+// (pire/scanners/multi.h:137-194,:281-284) on the HOST in index space, so the
+// reference's own templates -- Pire::Step, Pire::Run, Pire::Runner, LongestPrefix,
+// ShortestPrefix (pire/run.h) -- compile against it unchanged; the parity tests use
+// that to prove the ingest is lossless.  The host concept is for verification and
+// for the prefix/suffix scans that have not moved to the device yet; the batch
+// path never falls back to it.
+//
+// This header does not include any Pire header: the templated constructor only
+// needs `sc.Save(std::ostream*)`.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "pire_b200.h"
+
+namespace Pire {
+namespace Gpu {
+
+// Counterpart of Pire::Error (pire/stub/stl.h:213-217).
+class Error : public std::runtime_error {
+public:
+    Error(int code, const std::string& what) : std::runtime_error(what), Code(code) {}
+    int Code;
+};
+
+inline void Check(int rc, const char* where)
+{
+    if (rc != PIRE_GPU_OK)
+        throw Error(rc, std::string(where) + ": " + pire_gpu_last_error());
+}
+
+// A batch of strings on the device: CSR offsets (n+1) or fixed length.
+struct Batch {
+    const uint8_t* Corpus;
+    const uint64_t* Offsets;     // nullptr => fixed-length strings
+    uint64_t FixedLen;
+    uint64_t Count;
+};
+
+class Scanner {
+public:
+    // ---- Scanner concept (host, index space) --------------------------------
+    typedef uint32_t State;
+    typedef uint32_t Action;
+    typedef unsigned short Char;     // Pire::Char, pire/defs.h:59
+
+    Scanner() : Handle(nullptr) {}
+
+    // From a Scanner::Save() stream (multi.h:557-573).  device = -1: host only.
+    Scanner(const void* image, size_t size, int device = 0) : Handle(nullptr)
+    {
+        Check(pire_gpu_scanner_create(image, size, device, &Handle), "pire_gpu_scanner_create");
+    }
+
+    // From any Pire scanner type whose Save() writes the multi-Scanner format
+    // (Pire::Scanner, Pire::NonrelocScanner and their NoMask variants).
+    template <class PireScanner>
+    explicit Scanner(const PireScanner& sc, int device = 0) : Handle(nullptr)
+    {
+        std::ostringstream out;
+        sc.Save(&out);
+        const std::string image = out.str();
+        Check(pire_gpu_scanner_create(image.data(), image.size(), device, &Handle), "pire_gpu_scanner_create");
+    }
+
+    Scanner(Scanner&& o) noexcept : Handle(o.Handle), AcceptCache(std::move(o.AcceptCache)) { o.Handle = nullptr; }
+    Scanner& operator=(Scanner&& o) noexcept
+    {
+        if (this != &o) {
+            pire_gpu_scanner_destroy(Handle);
+            Handle = o.Handle;
+            AcceptCache = std::move(o.AcceptCache);
+            o.Handle = nullptr;
+        }
+        return *this;
+    }
+    Scanner(const Scanner&) = delete;
+    Scanner& operator=(const Scanner&) = delete;
+    ~Scanner() { pire_gpu_scanner_destroy(Handle); }
+
+    size_t Size() const { return Info().states; }                       // multi.h:134
+    bool Empty() const { return Info().empty != 0; }                    // multi.h:135
+    size_t RegexpsCount() const { return Info().regexps; }              // multi.h:139
+    size_t LettersCount() const { return Info().letters; }              // multi.h:140
+
+    void Initialize(State& st) const { st = pire_gpu_initial(Handle); }                       // multi.h:161
+    Action Next(State& st, Char c) const { st = pire_gpu_next(Handle, st, c); return 0; }     // multi.h:189-192
+    void TakeAction(State&, Action) const {}                                                  // multi.h:194
+    bool Final(const State& st) const { return pire_gpu_final(Handle, st) != 0; }             // multi.h:143
+    bool Dead(const State& st) const { return pire_gpu_dead(Handle, st) != 0; }               // multi.h:147
+    size_t StateIndex(State st) const { return st; }                                          // multi.h:281-284
+
+    // multi.h:149-158.  The returned range stays valid for the scanner's lifetime.
+    std::pair<const size_t*, const size_t*> AcceptedRegexps(const State& st) const
+    {
+        if (AcceptCache.size() <= st)
+            AcceptCache.resize((size_t) st + 1);
+        std::vector<size_t>& slot = AcceptCache[st];
+        if (slot.empty()) {
+            uint32_t ids[64];
+            size_t k = pire_gpu_accepted_regexps(Handle, st, ids, 64);
+            std::vector<uint32_t> big;
+            const uint32_t* src = ids;
+            if (k > 64) {
+                big.resize(k);
+                pire_gpu_accepted_regexps(Handle, st, big.data(), k);
+                src = big.data();
+            }
+            slot.assign(src, src + k);
+            slot.push_back(static_cast<size_t>(-1));     // keep a terminator like m_final does
+        }
+        return std::make_pair(slot.data(), slot.data() + slot.size() - 1);
+    }
+
+    // ---- device ----------------------------------------------------------------
+    void Tune(const Batch& sample, unsigned flags = PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END, void* stream = nullptr)
+    {
+        Check(pire_gpu_scanner_tune(Handle, sample.Corpus, sample.Offsets, sample.FixedLen, sample.Count, flags, stream),
+              "pire_gpu_scanner_tune");
+    }
+
+    pire_gpu_info Info() const
+    {
+        pire_gpu_info info;
+        Check(pire_gpu_scanner_info(Handle, &info), "pire_gpu_scanner_info");
+        return info;
+    }
+
+    pire_gpu_scanner* Raw() const { return Handle; }
+
+private:
+    pire_gpu_scanner* Handle;
+    mutable std::vector<std::vector<size_t>> AcceptCache;
+};
+
+// Counterpart of Pire::RunHelper (run.h:365-386) for a device batch.  Results are
+// written to caller-owned device buffers (any may be null); MatchesHost() etc. are
+// conveniences that copy them back through the host entry point.
+class BatchRunner {
+public:
+    explicit BatchRunner(const Scanner& sc) : Sc(&sc), Flags(0), Ran(false) {}
+
+    BatchRunner& Begin() { Flags |= PIRE_GPU_RUN_BEGIN; return *this; }      // run.h:375
+    BatchRunner& End() { Flags |= PIRE_GPU_RUN_END; return *this; }          // run.h:376
+    BatchRunner& Run(const Batch& b) { Input = b; Ran = true; return *this; } // run.h:372
+
+    // Launches the fused Begin/Run/End pass on `stream` (cudaStream_t as void*).
+    void Launch(uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream = nullptr) const
+    {
+        if (!Ran)
+            throw Error(PIRE_GPU_EINVAL, "BatchRunner::Run() was not called");
+        Check(pire_gpu_run_batch(Sc->Raw(), Input.Corpus, Input.Offsets, Input.FixedLen, Input.Count, Flags, d_match_bits,
+                                 d_accept_masks, d_state_idx, stream),
+              "pire_gpu_run_batch");
+    }
+
+private:
+    const Scanner* Sc;
+    Batch Input;
+    unsigned Flags;
+    bool Ran;
+};
+
+inline BatchRunner Runner(const Scanner& sc) { return BatchRunner(sc); }     // run.h:388-389
+
+// Host-buffer counterpart of `bool Pire::Runner(sc).Begin().Run(p, n).End()` for many
+// strings at once (CSR): fills `matched[i]`.
+inline void MatchesHost(const Scanner& sc, const uint8_t* corpus, const uint64_t* offsets, uint64_t n,
+                        std::vector<bool>& matched, unsigned flags = PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END)
+{
+    std::vector<uint32_t> bits((n + 31) / 32);
+    Check(pire_gpu_run_batch_host(sc.Raw(), corpus, n ? offsets[n] : 0, offsets, 0, n, flags, bits.data(), nullptr, nullptr),
+          "pire_gpu_run_batch_host");
+    matched.resize(n);
+    for (uint64_t i = 0; i < n; ++i)
+        matched[i] = (bits[i / 32] >> (i % 32)) & 1u;
+}
+
+} // namespace Gpu
+} // namespace Pire

@@ -51,6 +51,7 @@ struct DeviceTables {
     uint16_t* cls = nullptr;
     void* full = nullptr;
     DeviceFin* fin[2] = {nullptr, nullptr};
+    uint32_t* priv_packed = nullptr;
     size_t full_bytes = 0;
 
     void Free()
@@ -61,6 +62,7 @@ struct DeviceTables {
         cudaFree(full);
         cudaFree(fin[0]);
         cudaFree(fin[1]);
+        cudaFree(priv_packed);
         *this = DeviceTables();
     }
 };
@@ -75,8 +77,9 @@ struct pire_gpu_scanner {
     uint32_t variant = PIRE_GPU_VARIANT_AUTO;
     uint32_t max_hot = kMaxHot;
     bool tuned = false;
+    bool priv_ok = false;
     std::vector<uint32_t> hot_order;
-    LaunchPlan plan[3][2];          // [variant][uniform]
+    LaunchPlan plan[4][2];          // [variant][uniform]
 
     // workspace of the host-buffer entry point
     std::mutex host_mutex;
@@ -93,7 +96,7 @@ namespace {
 
 uint32_t ResolveVariant(const pire_gpu_scanner* sc)
 {
-    if (sc->variant == PIRE_GPU_VARIANT_PLAIN || sc->variant == PIRE_GPU_VARIANT_PRED)
+    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_PRIV)
         return sc->variant;
     // AUTO: predication pays when lanes outside the resident state would
     // collide with it in the banks, i.e. for large (glued) automata.
@@ -124,9 +127,21 @@ int Upload(pire_gpu_scanner* sc)
         CUDA_TRY(cudaMalloc(&d.fin[w], bytes));
         CUDA_TRY(cudaMemcpy(d.fin[w], t.fin[w].data(), bytes, cudaMemcpyHostToDevice));
     }
-    for (int v = kVariantPlain; v <= kVariantPred; ++v)
-        for (int u = 0; u < 2; ++u)
-            CUDA_TRY(PlanScan(sc->device, t.hot, v, u != 0, &sc->plan[v][u]));
+    CUDA_TRY(cudaMalloc(&d.priv_packed, t.priv_packed.size() * 4));
+    CUDA_TRY(cudaMemcpy(d.priv_packed, t.priv_packed.data(), t.priv_packed.size() * 4, cudaMemcpyHostToDevice));
+    sc->priv_ok = false;
+    for (int v = kVariantPlain; v <= kVariantPriv; ++v)
+        for (int u = 0; u < 2; ++u) {
+            cudaError_t pe = PlanScan(sc->device, t.hot, t.priv_rows, v, u != 0, &sc->plan[v][u]);
+            if (v == kVariantPriv && u == 1) {
+                sc->priv_ok = pe == cudaSuccess;     // needs ~225 KB of shared memory per CTA
+                if (pe != cudaSuccess)
+                    (void) cudaGetLastError();
+                continue;
+            }
+            if (pe != cudaSuccess)
+                return FailCuda(pe, "PlanScan");
+        }
     return PIRE_GPU_OK;
 }
 
@@ -160,6 +175,8 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->wide = t.wide ? 1 : 0;
     a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
     a->exit_bitmap0 = t.exit_bitmap0;
+    a->priv_packed = sc->dev.priv_packed;
+    a->priv_rows = t.priv_rows;
 }
 
 int CheckRunnable(const pire_gpu_scanner* sc)
@@ -245,14 +262,14 @@ int pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out)
     out->variant = ResolveVariant(sc);
     out->tuned = sc->tuned ? 1 : 0;
     out->table_bytes = sc->tab.wide ? sc->tab.full32.size() * 4 : sc->tab.full16.size() * 2;
-    out->shared_bytes = ScanSharedBytes(sc->tab.hot);
+    out->shared_bytes = ScanSharedBytes(sc->tab.hot, ResolveVariant(sc) == PIRE_GPU_VARIANT_PRIV ? sc->tab.priv_rows : 0);
     out->device = sc->device;
     return PIRE_GPU_OK;
 }
 
 int pire_gpu_scanner_set_variant(pire_gpu_scanner* sc, uint32_t variant)
 {
-    if (!sc || variant > PIRE_GPU_VARIANT_PRED)
+    if (!sc || variant > PIRE_GPU_VARIANT_PRIV)
         return Fail(PIRE_GPU_EINVAL, "bad variant");
     sc->variant = variant;
     return PIRE_GPU_OK;
@@ -289,7 +306,9 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     a.accept_masks = d_accept_masks;
     a.state_idx = d_state_idx;
     const bool uniform = IsUniform(d_corpus, d_offsets, fixed_len);
-    const uint32_t variant = ResolveVariant(sc);
+    uint32_t variant = ResolveVariant(sc);
+    if (variant == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
+        variant = PIRE_GPU_VARIANT_PLAIN;       // the private-row kernel exists for uniform batches only
     CUDA_TRY(LaunchScan(a, (int) variant, uniform, sc->plan[variant][uniform ? 1 : 0], static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
 }

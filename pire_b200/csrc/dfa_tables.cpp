@@ -117,6 +117,27 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
         if (t.hot8[b] != 0)
             t.exit_bitmap0 |= 1u << (b & 31);
 
+    // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,
+    // the last id being the sink.
+    {
+        uint32_t real = std::min<uint32_t>(H, kMaxPrivRows - 1);
+        uint32_t rows = (real + 1 + 3) / 4 * 4;
+        real = std::min<uint32_t>(H, rows - 1);
+        const uint32_t sink = rows - 1;
+        t.priv_rows = rows;
+        t.priv_packed.assign((size_t) (rows / 4) * 128, 0);
+        for (uint32_t r = 0; r < rows; ++r)
+            for (uint32_t b = 0; b < 128; ++b) {
+                uint32_t to = sink;
+                if (r < real) {
+                    uint32_t h = t.hot8[(size_t) r * 256 + b];
+                    if (h < real)
+                        to = h;
+                }
+                t.priv_packed[(size_t) (r / 4) * 128 + b] |= to << (8 * (r % 4));
+            }
+    }
+
     // What a string that stops in state s reports.
     for (int with_end = 0; with_end < 2; ++with_end) {
         t.fin[with_end].resize(dfa.states);

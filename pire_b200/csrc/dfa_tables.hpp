@@ -33,6 +33,7 @@
 namespace pire_b200 {
 
 constexpr uint32_t kMaxHot = 255;
+constexpr uint32_t kMaxPrivRows = 40;     // lane-private rows incl. the sink (10 quads x 16 KB of shared memory)
 
 struct FinEntry {
     uint32_t result;   // bit31 = Final(), bits 0..30 = StateIndex() in the reference's numbering
@@ -51,6 +52,14 @@ struct ScanTables {
     std::vector<FinEntry> fin[2];            // [with_end][new id]
     uint32_t start[2] = {0, 0};              // [with_begin] -> new id
     uint32_t exit_bitmap0 = 0xffffffffu;     // bit (b & 31) set if byte b may leave hot id 0
+
+    // Lane-private rows (kernel variant PRIV): the first priv_rows-1 hot ids, plus a sink
+    // row (id priv_rows-1) that absorbs every transition into a non-private state.  Only
+    // bytes 0..127 are covered.  priv_packed[q*128 + b] holds the four entries of quad q
+    // (rows 4q..4q+3) for byte b; the kernel replicates each word into all 32 banks so that
+    // lane l only ever touches bank l: one wavefront per load, no conflicts by construction.
+    uint32_t priv_rows = 0;                  // multiple of 4
+    std::vector<uint32_t> priv_packed;       // (priv_rows / 4) * 128
 };
 
 // Default hot order: breadth-first from the start states (states near the start

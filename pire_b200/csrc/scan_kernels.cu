@@ -101,6 +101,7 @@ __device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& 
 // ---------------------------------------------------------------- shared layout
 
 struct SharedView {
+    uint8_t* priv;       // (priv_rows/4) * 16 KB, PRIV variant only (else empty)
     uint8_t* hot;        // (H+1)*256
     uint16_t* cls;       // 256
     uint8_t* noexit;     // 256 (H+1 used)
@@ -108,10 +109,13 @@ struct SharedView {
 };
 
 __host__ __device__ inline size_t HotBytes(uint32_t hot) { return (size_t) (hot + 1) * 256; }
+__host__ __device__ inline size_t PrivBytes(uint32_t priv_rows) { return (size_t) (priv_rows / 4) * 16384; }
 
-__device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot)
+__device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot, uint32_t priv_rows = 0)
 {
     SharedView v;
+    v.priv = smem;
+    smem += PrivBytes(priv_rows);
     v.hot = smem;
     v.cls = reinterpret_cast<uint16_t*>(smem + HotBytes(hot));
     v.noexit = smem + HotBytes(hot) + 512;
@@ -147,6 +151,7 @@ __device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView&
 // ---------------------------------------------------------------- the walk
 
 struct Tables {
+    uint32_t hot_saddr;       // shared-window address of hot (for PTX loads)
     const uint8_t* hot;
     const uint16_t* cls;
     const void* full;
@@ -194,9 +199,21 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
     if (kPred) {
         // bit (byte & 31) of m0: may this byte leave hot id 0?  Lanes resting in
         // id 0 on a self-looping byte skip the load (fewer bank conflicts).
-        uint32_t probe = __funnelshift_r(t.m0, 0u, idx);
-        if (((probe & 1u) | g) != 0)
-            g = t.hot[idx];
+        // Spelled in PTX so that the load stays one predicated LDS [R+UR]
+        // (SHF, LOP3 -> predicate, @p LDS) instead of a re-derived address.
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 probe, addr;\n"
+            "shf.r.wrap.b32 probe, %2, 0, %1;\n"
+            "and.b32 probe, probe, 1;\n"
+            "or.b32 probe, probe, %0;\n"
+            "setp.ne.u32 p, probe, 0;\n"
+            "add.u32 addr, %1, %3;\n"
+            "@p ld.shared.u8 %0, [addr];\n"
+            "}\n"
+            : "+r"(g)
+            : "r"(idx), "r"(t.m0), "r"(t.hot_saddr));
     } else {
         g = t.hot[idx];
     }
@@ -218,6 +235,7 @@ __device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t*
                                              uint32_t letters_wide, uint32_t from, uint4 v)
 {
     Tables t;
+    t.hot_saddr = 0;
     t.hot = hot;
     t.cls = cls;
     t.full = full;
@@ -284,6 +302,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     StageTables(a, sv);
 
     Tables t;
+    t.hot_saddr = SmemAddr(sv.hot);
     t.hot = sv.hot;
     t.cls = sv.cls;
     t.full = a.full;
@@ -346,6 +365,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
     StageTables(a, sv);
 
     Tables t;
+    t.hot_saddr = SmemAddr(sv.hot);
     t.hot = sv.hot;
     t.cls = sv.cls;
     t.full = a.full;
@@ -415,6 +435,151 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
             SetFull(t, s, full);
         }
         Report(a, t, s, unit, i, valid);
+    }
+}
+
+// ---------------------------------------------------------------- PRIV variant
+//
+// The plain walk is bound by shared-memory wavefronts once lanes sit in different
+// rows (glued scanners: ~2.4 wavefronts per load, ncu r01).  Here the hottest rows
+// are replicated into all 32 banks: lane l reads only bank l, so every load is one
+// wavefront whatever the states and bytes are.  Layout (byte address inside the
+// private region):   [19:14] quad q   [13:7] byte b (< 128)   [6:2] lane   [1:0] row-in-quad s
+// A lane's state is S = (q << 14) | (lane << 2) | s; one step is
+//     e = LDS.U8 [priv + S + (b << 7)];   S = ((e * 0x1001) & 0xFC003) | (lane << 2)
+// (e = 4q' + s'; the multiply drops s' into bits 1:0 and q' into bits 19:14).  Rows
+// that are not private map to the sink row; a lane found in the sink after a 4-byte
+// word (or a word holding a byte >= 128) re-walks that word through the shared
+// hot rows / the complete table and re-enters a private row when it can.
+
+constexpr int kPrivBlock = 1024;
+constexpr uint32_t kPrivMask = 0x000FC003u;
+
+struct PrivLane {
+    uint32_t S;         // private row address (relative to the private region) or the lane's sink
+    uint32_t other;     // complete state while S == sink
+};
+
+__device__ __forceinline__ uint32_t PrivAddrOf(uint32_t id, uint32_t lane4) { return ((id >> 2) << 14) | lane4 | (id & 3u); }
+__device__ __forceinline__ uint32_t PrivIdOf(uint32_t S) { return ((S >> 14) << 2) | (S & 3u); }
+
+__device__ __forceinline__ void PrivStep(const uint8_t* priv, uint32_t& S, uint32_t b, uint32_t lane4)
+{
+    uint32_t e = priv[S + (b << 7)];
+    S = ((e * 0x1001u) & kPrivMask) | lane4;
+}
+
+// Re-walk of one word for a lane that is (or fell) outside the private rows.
+__device__ __noinline__ uint2 PrivSlowWord(const uint8_t* hot, const uint16_t* cls, const void* full, uint32_t H,
+                                           uint32_t letters_wide, uint32_t real_rows, uint32_t state, uint32_t w)
+{
+    Tables t;
+    t.hot_saddr = 0;
+    t.hot = hot;
+    t.cls = cls;
+    t.full = full;
+    t.H = H;
+    t.letters = letters_wide & 0x7fffffffu;
+    t.wide = letters_wide >> 31;
+    t.m0 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        state = SlowStep(t, state, (w >> (8 * k)) & 0xffu);
+    return make_uint2(state, state < real_rows ? 1u : 0u);
+}
+
+__device__ __forceinline__ void PrivWord(const ScanArgs& a, const SharedView& sv, PrivLane& s, uint32_t w, uint32_t lane4,
+                                         uint32_t sink, uint32_t real_rows)
+{
+    const uint32_t before = s.S;
+    uint32_t S = s.S;
+    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4440), lane4);
+    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4441), lane4);
+    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4442), lane4);
+    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4443), lane4);
+    if (S == sink || (w & 0x80808080u) != 0) {
+        uint32_t from = before == sink ? s.other : PrivIdOf(before);
+        uint2 r = PrivSlowWord(sv.hot, sv.cls, a.full, a.hot, a.letters | (a.wide << 31), real_rows, from, w);
+        if (r.y) {
+            S = PrivAddrOf(r.x, lane4);
+        } else {
+            S = sink;
+            s.other = r.x;
+        }
+    }
+    s.S = S;
+}
+
+__global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __grid_constant__ ScanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    SharedView sv = CarveShared(smem, a.hot, a.priv_rows);
+    StageTables(a, sv);
+    {
+        // replicate every packed word into the 32 banks
+        const uint32_t words = (a.priv_rows / 4) * 128 * 32;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sv.priv);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+            dst[i] = __ldg(a.priv_packed + (i >> 5));
+        __syncthreads();
+    }
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane4 = lane << 2;
+    const uint32_t real_rows = a.priv_rows - 1 < a.hot ? a.priv_rows - 1 : a.hot;
+    const uint32_t sink = PrivAddrOf(a.priv_rows - 1, lane4);
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * (kPrivBlock / 32);
+    const uint32_t len = (uint32_t) a.fixed_len;
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * (kPrivBlock / 32) + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
+
+        PrivLane s;
+        s.other = a.start;
+        s.S = a.start < real_rows ? PrivAddrOf(a.start, lane4) : sink;
+
+        uint4 c0, c1, d0, d1;
+        LoadStream32(p, c0, c1);
+        for (uint32_t off = 0;;) {
+            off += 32;
+            const bool more_d = off < len;
+            if (more_d)
+                LoadStream32(p + off, d0, d1);
+            PrivWord(a, sv, s, c0.x, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c0.y, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c0.z, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c0.w, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c1.x, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c1.y, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c1.z, lane4, sink, real_rows);
+            PrivWord(a, sv, s, c1.w, lane4, sink, real_rows);
+            if (!more_d)
+                break;
+            off += 32;
+            const bool more_c = off < len;
+            if (more_c)
+                LoadStream32(p + off, c0, c1);
+            PrivWord(a, sv, s, d0.x, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d0.y, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d0.z, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d0.w, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d1.x, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d1.y, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d1.z, lane4, sink, real_rows);
+            PrivWord(a, sv, s, d1.w, lane4, sink, real_rows);
+            if (!more_c)
+                break;
+        }
+
+        Tables t;
+        t.H = a.hot;
+        LaneState fs;
+        fs.g = a.hot;
+        fs.cold = s.S == sink ? s.other : PrivIdOf(s.S);
+        Report(a, t, fs, unit, i, valid);
     }
 }
 
@@ -495,6 +660,8 @@ const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGener
 
 const void* KernelFor(int variant, bool uniform)
 {
+    if (variant == kVariantPriv && uniform)
+        return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
     const bool pred = variant == kVariantPred;
     if (uniform)
         return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
@@ -503,7 +670,7 @@ const void* KernelFor(int variant, bool uniform)
 
 } // namespace
 
-size_t ScanSharedBytes(uint32_t hot) { return HotBytes(hot) + 512 + 256 + 16; }
+size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows) { return PrivBytes(priv_rows) + HotBytes(hot) + 512 + 256 + 16; }
 
 cudaError_t PrepareScanKernels(int device)
 {
@@ -514,7 +681,7 @@ cudaError_t PrepareScanKernels(int device)
     err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err != cudaSuccess)
         return err;
-    for (int variant : {(int) kVariantPlain, (int) kVariantPred})
+    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv})
         for (bool uniform : {false, true}) {
             err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (err != cudaSuccess)
@@ -523,15 +690,16 @@ cudaError_t PrepareScanKernels(int device)
     return cudaSuccess;
 }
 
-cudaError_t PlanScan(int device, uint32_t hot, int variant, bool uniform, LaunchPlan* plan)
+cudaError_t PlanScan(int device, uint32_t hot, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
 {
-    plan->block = kBlock;
-    plan->shared = ScanSharedBytes(hot);
+    const bool priv = variant == kVariantPriv && uniform;
+    plan->block = priv ? kPrivBlock : kBlock;
+    plan->shared = ScanSharedBytes(hot, priv ? priv_rows : 0);
     int sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess)
         return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KernelFor(variant, uniform), kBlock, plan->shared);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KernelFor(variant, uniform), plan->block, plan->shared);
     if (err != cudaSuccess)
         return err;
     if (per_sm < 1)
@@ -545,7 +713,8 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     if (a.n == 0)
         return cudaSuccess;
     uint64_t units = (a.n + 31) / 32;
-    uint64_t want = (units + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const uint64_t warps_per_block = (uint64_t) plan.block / 32;
+    uint64_t want = (units + warps_per_block - 1) / warps_per_block;
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
     void* args[] = {const_cast<ScanArgs*>(&a)};
     cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);

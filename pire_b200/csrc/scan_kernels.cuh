@@ -30,6 +30,8 @@ struct ScanArgs {
     uint32_t wide;               // full is u32
     uint32_t start;              // state after Initialize()[+Begin()], new numbering
     uint32_t exit_bitmap0;
+    const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
+    uint32_t priv_rows;
     uint32_t* match_bits;        // may be null
     uint32_t* accept_masks;      // may be null
     uint32_t* state_idx;         // may be null
@@ -42,11 +44,11 @@ struct LaunchPlan {
     size_t shared = 0;
 };
 
-enum ScanVariant { kVariantPlain = 1, kVariantPred = 2 };
+enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3 };
 
-size_t ScanSharedBytes(uint32_t hot);
+size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows);
 cudaError_t PrepareScanKernels(int device);                       // raises the dynamic smem limit
-cudaError_t PlanScan(int device, uint32_t hot, int variant, bool uniform, LaunchPlan* plan);
+cudaError_t PlanScan(int device, uint32_t hot, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
 cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream);

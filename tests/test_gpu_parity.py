@@ -112,7 +112,7 @@ def random_text(rng, n, length, alphabet=None):
     return rng.choice(np.frombuffer(alphabet, np.uint8), size=(n, length))
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["plain", "pred"])
+@pytest.mark.parametrize("variant", [1, 2, 3], ids=["plain", "pred", "priv"])
 def test_uniform_kernel_headline(variant, cuda_device, ref):
     """Fixed 1 KiB strings (the BASELINE configs' shape) through the uniform kernel,
     full comparison with the reference on 64 Ki strings, incl. StateIndex."""
@@ -163,12 +163,12 @@ def test_glued_ten_patterns(max_hot, tune, cuda_device, ref):
     host = spec.host_sample(0, n)
     f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=n, variant=1, threads=8)
     assert int((m_ref != 0).sum()) >= n // 8
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         sc.set_variant(variant)
         r = P.Runner(sc).Begin().Run(batch).End()
-        assert (r.Matches().astype(np.uint8) == f_ref).all()
-        assert (r.AcceptMasks() == m_ref).all()
-        assert (r.States() == s_ref).all()
+        assert (r.Matches().astype(np.uint8) == f_ref).all(), variant
+        assert (r.AcceptMasks() == m_ref).all(), variant
+        assert (r.States() == s_ref).all(), variant
     # every planted literal is reported under its own regexp id
     for i in range(0, 80, 8):
         assert m_ref[i] & (1 << ((i // 8) % 10))
@@ -195,6 +195,33 @@ def test_generic_kernel_mixed_lengths_utf8(cuda_device, ref):
     for g, w in zip(got, want):
         assert (g == w).all()
     assert int(want[0].sum()) >= len(strings) // 5
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3], ids=["plain", "pred", "priv"])
+def test_uniform_kernel_binary_bytes(variant, cuda_device, ref):
+    """Fixed-length strings over the whole byte range (UTF-8 pattern): the private-row
+    kernel covers bytes < 128 only and must re-walk every word holding a byte >= 128."""
+    import torch
+    import pire_b200 as P
+    sc_ref = ref.compile("привет|hello\\s+w.+d$".encode(), "iu")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    sc.set_variant(variant)
+    rng = np.random.default_rng(17)
+    n, length = 3000, 256
+    alphabet = "привет ПРИВЕТ hello world HELLO WORLD\t".encode() + bytes(range(256))
+    host = random_text(rng, n, length, alphabet)
+    for i in range(0, n, 3):
+        hit = "ПрИвЕт".encode() if i % 2 else b"HeLLo  WoRLd"
+        host[i, -len(hit):] = np.frombuffer(hit, np.uint8)
+    host = np.ascontiguousarray(host).reshape(-1)
+    dev = torch.from_numpy(host).to("cuda:0")
+    batch = P.Batch(dev, fixed_len=length, n=n)
+    sc.Tune(batch, 512)
+    r = P.Runner(sc).Begin().Run(batch).End()
+    f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=length, n=n)
+    assert (r.Matches().astype(np.uint8) == f_ref).all()
+    assert (r.States() == s_ref).all()
+    assert int(f_ref.sum()) >= n // 3
 
 
 def test_noexit_early_stop_is_exact(cuda_device, ref):

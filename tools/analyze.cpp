@@ -118,6 +118,43 @@ int main(int argc, char** argv)
                     t.exit_bitmap0, __builtin_popcount(t.exit_bitmap0));
     }
 
+    // Private-row model: P most visited rows are lane-private (never conflict); a lane that
+    // needs another row misses.  Report per-lane-step, per-warp-word(4 B) and per-warp-chunk(16 B) miss rates.
+    {
+        std::vector<uint32_t> rank(dfa.states, UINT32_MAX);
+        std::vector<uint32_t> ord = HotOrderFromCounts(dfa, visits);
+        for (uint32_t i = 0; i < ord.size(); ++i)
+            rank[ord[i]] = i;
+        for (uint32_t P : {16u, 24u, 32u, 40u, 48u, 56u, 64u, 72u, 96u, 128u}) {
+            uint64_t lane_steps = 0, lane_miss = 0, words = 0, word_miss = 0, chunks16 = 0, chunk_miss = 0, nonascii = 0;
+            for (uint64_t base = 0; base + 32 <= n; base += 32) {
+                uint32_t st[32];
+                for (int l = 0; l < 32; ++l)
+                    st[l] = start;
+                bool cm = false;
+                for (uint32_t k = 0; k < len; ++k) {
+                    bool wm = false;
+                    for (int l = 0; l < 32; ++l) {
+                        uint8_t b = corpus[(base + l) * len + k];
+                        ++lane_steps;
+                        bool miss = rank[st[l]] >= P || b >= 128;
+                        nonascii += b >= 128;
+                        lane_miss += miss;
+                        wm = wm || miss;
+                        st[l] = dfa.Next(st[l], b);
+                    }
+                    static bool wacc = false;
+                    wacc = wacc || wm;
+                    cm = cm || wm;
+                    if ((k & 3) == 3) { ++words; word_miss += wacc; wacc = false; }
+                    if ((k & 15) == 15) { ++chunks16; chunk_miss += cm; cm = false; }
+                }
+            }
+            std::printf("private P=%3u: lane-step miss %.5f  warp-word(4B) miss %.4f  warp-chunk(16B) miss %.4f\n", P,
+                        (double) lane_miss / lane_steps, (double) word_miss / words, (double) chunk_miss / chunks16);
+        }
+    }
+
     // Warp model.
     const uint32_t H = t.hot;
     const char* fm = std::getenv("FILTER");

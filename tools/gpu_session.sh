@@ -23,7 +23,7 @@ micro)
   ;;
 bench)
   for wl in glue10 headline; do
-    for v in plain pred; do
+    for v in plain pred priv; do
       timeout 600 python bench.py --workload $wl --variant $v --steps 10 --warmup 3 --no-e2e --no-cpu > $OUT/bench_${wl}_${v}.json 2> $OUT/bench_${wl}_${v}.err
       python - <<PY
 import json
@@ -41,8 +41,8 @@ PY
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
       python bench.py --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant plain > $OUT/ncu_bench.log 2>&1
-  for v in plain pred; do
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniformKernel -s 3 -c 1 -f -o $OUT/prof_glue10_$v \
+  for v in ${NCU_VARIANTS:-plain priv}; do
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniform -s 3 -c 1 -f -o $OUT/prof_glue10_$v \
         python bench.py --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant $v > $OUT/ncu_full_$v.log 2>&1
   done
   ls -la $OUT/*.ncu-rep
