@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--collective", default="allreduce", choices=["allreduce", "allgather"])
-    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="strings in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 22, help="strings in the CPU-baseline sample (per step of the reference arm)")
     return ap.parse_args()
 
 
@@ -253,17 +253,15 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    # kernel variant: measured, not guessed
+    # kernel variant: measured on this batch by the library, not guessed
+    names = {N.VARIANT_PLAIN: "plain", N.VARIANT_PRED: "pred", N.VARIANT_PRIV: "priv"}
     variant_ms = {}
     if args.variant == "auto":
-        for name, v in (("plain", N.VARIANT_PLAIN), ("pred", N.VARIANT_PRED), ("priv", N.VARIANT_PRIV)):
-            sc.set_variant(v)
-            time_scan(1)
-            variant_ms[name] = time_scan(2)
-        chosen = min(variant_ms, key=variant_ms.get)
+        variant_ms = sc.AutoSelect(batch)
+        chosen = names[sc.info().variant]
     else:
         chosen = args.variant
-    sc.set_variant({"plain": N.VARIANT_PLAIN, "pred": N.VARIANT_PRED, "priv": N.VARIANT_PRIV}[chosen])
+        sc.set_variant({v: k for k, v in names.items()}[chosen])
 
     def barrier():
         if world > 1:
@@ -298,6 +296,13 @@ def main():
     kernel_ms = time_scan(min(args.steps, 10))
     matches_global = popcount_bits(bits_full if world > 1 else bits_local)
     matches_local_masks = int((masks != 0).sum().item())
+    # consistency: the all-reduced bitmap holds exactly the union of the shards' matches,
+    # and every planted string (1/8) is reported
+    local_pop = torch.tensor([popcount_bits(bits_local)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(local_pop, op=dist.ReduceOp.SUM)
+    assert int(local_pop.item()) == matches_global, (int(local_pop.item()), matches_global)
+    assert matches_local_masks == popcount_bits(bits_local) and matches_local_masks >= n_local // 8
 
     # end to end: host buffers through the C ABI, H2D and D2H inside the timed region
     e2e = None

@@ -124,6 +124,16 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc,
                           const uint8_t* d_corpus, const uint64_t* d_offsets,
                           uint64_t fixed_len, uint64_t n_sample, uint32_t flags, void* stream);
 
+/* Times every kernel variant that can serve this batch shape (two launches each,
+ * results discarded) and makes the fastest one the handle's AUTO choice for that
+ * shape (fixed-length/aligned vs generic).  ms_out[4] (may be NULL) receives the
+ * milliseconds per variant id, 0 for variants that do not apply.  Which variant
+ * wins depends on the automaton and the text, so it is
+ * measured rather than guessed.  Synchronises the device. */
+int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc,
+                                const uint8_t* d_corpus, const uint64_t* d_offsets,
+                                uint64_t fixed_len, uint64_t n, uint32_t flags, void* stream, float* ms_out);
+
 /* Number of kernels this library has launched in the calling process. */
 uint64_t pire_gpu_launch_count(void);
 

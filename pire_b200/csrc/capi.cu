@@ -75,6 +75,7 @@ struct pire_gpu_scanner {
     DeviceTables dev;
     int device = -1;
     uint32_t variant = PIRE_GPU_VARIANT_AUTO;
+    uint32_t auto_choice[2] = {0, 0};   // [uniform]: measured by pire_gpu_scanner_autoselect, 0 = heuristic
     uint32_t max_hot = kMaxHot;
     bool tuned = false;
     bool priv_ok = false;
@@ -94,10 +95,12 @@ struct pire_gpu_scanner {
 
 namespace {
 
-uint32_t ResolveVariant(const pire_gpu_scanner* sc)
+uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform = true)
 {
     if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_PRIV)
         return sc->variant;
+    if (sc->auto_choice[uniform ? 1 : 0])
+        return sc->auto_choice[uniform ? 1 : 0];
     // AUTO: predication pays when lanes outside the resident state would
     // collide with it in the banks, i.e. for large (glued) automata.
     return sc->tab.states > 64 ? PIRE_GPU_VARIANT_PRED : PIRE_GPU_VARIANT_PLAIN;
@@ -174,7 +177,8 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->letters = t.letters;
     a->wide = t.wide ? 1 : 0;
     a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
-    a->exit_bitmap0 = t.exit_bitmap0;
+    a->exit_bitmap0 = (uint32_t) t.exit_bitmap0;
+    a->exit_bitmap0_hi = (uint32_t) (t.exit_bitmap0 >> 32);
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
 }
@@ -306,7 +310,7 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     a.accept_masks = d_accept_masks;
     a.state_idx = d_state_idx;
     const bool uniform = IsUniform(d_corpus, d_offsets, fixed_len);
-    uint32_t variant = ResolveVariant(sc);
+    uint32_t variant = ResolveVariant(sc, uniform);
     if (variant == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
         variant = PIRE_GPU_VARIANT_PLAIN;       // the private-row kernel exists for uniform batches only
     CUDA_TRY(LaunchScan(a, (int) variant, uniform, sc->plan[variant][uniform ? 1 : 0], static_cast<cudaStream_t>(stream)));
@@ -410,6 +414,64 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc, const uint8_t* d_corpus, const u
     sc->tuned = true;
     Rebuild(sc);
     return Upload(sc);
+}
+
+int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                                uint64_t fixed_len, uint64_t n, uint32_t flags, void* stream, float* ms_out)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (ms_out)
+        for (int v = 0; v < 4; ++v)
+            ms_out[v] = 0.f;
+    if (n == 0)
+        return PIRE_GPU_OK;
+    CUDA_TRY(cudaSetDevice(sc->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool uniform = IsUniform(d_corpus, d_offsets, fixed_len);
+    uint32_t* scratch = nullptr;
+    const size_t words = (size_t) ((n + 31) / 32);
+    CUDA_TRY(cudaMalloc(&scratch, (words + n) * 4));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess)
+        ce = cudaEventCreate(&e1);
+    const uint32_t saved = sc->variant;
+    uint32_t best = 0;
+    float best_ms = 0.f;
+    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_PRIV && ce == cudaSuccess; ++v) {
+        if (v == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
+            continue;
+        sc->variant = v;
+        float ms = 0.f;
+        for (int rep = 0; rep < 2 && rc == PIRE_GPU_OK; ++rep) {      // first launch warms, second is timed
+            cudaEventRecord(e0, st);
+            rc = pire_gpu_run_batch(sc, d_corpus, d_offsets, fixed_len, n, flags, scratch, scratch + words, nullptr, st);
+            cudaEventRecord(e1, st);
+            ce = cudaEventSynchronize(e1);
+            if (ce == cudaSuccess)
+                ce = cudaEventElapsedTime(&ms, e0, e1);
+        }
+        if (rc != PIRE_GPU_OK)
+            break;
+        if (ms_out)
+            ms_out[v] = ms;
+        if (best == 0 || ms < best_ms) {
+            best = v;
+            best_ms = ms;
+        }
+    }
+    sc->variant = saved;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(scratch);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (ce != cudaSuccess)
+        return FailCuda(ce, "pire_gpu_scanner_autoselect");
+    sc->auto_choice[uniform ? 1 : 0] = best;
+    return PIRE_GPU_OK;
 }
 
 uint64_t pire_gpu_launch_count(void) { return KernelLaunchCount(); }

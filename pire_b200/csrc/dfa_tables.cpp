@@ -115,7 +115,7 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
     t.exit_bitmap0 = 0;
     for (uint32_t b = 0; b < 256; ++b)
         if (t.hot8[b] != 0)
-            t.exit_bitmap0 |= 1u << (b & 31);
+            t.exit_bitmap0 |= 1ull << (b & 63);
 
     // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,
     // the last id being the sink.

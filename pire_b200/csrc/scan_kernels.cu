@@ -14,7 +14,7 @@
 //     input byte k in bits 0..7 and g in bits 8..15, which is the byte address
 //     of the fused row entry.  No class lookup, no multiply, no branch.
 //   * kPred variant: the LDS is predicated off while the lane sits in hot id 0
-//     and the byte cannot leave it (32-slot bitmap probed with a funnel shift),
+//     and the byte cannot leave it (64-slot bitmap probed with one 64-bit shift),
 //     so fewer lanes hit the banks and the load costs fewer wavefronts.
 //   * Input bytes: each lane streams its own string with 32-byte (uniform
 //     kernel, LDG.256) or 16-byte (generic kernel) read-only vector loads that
@@ -29,6 +29,12 @@
 #include "scan_kernels.cuh"
 
 #include <atomic>
+
+// One dynamic shared-memory array for every kernel of this file, with an unmangled
+// PTX name so that inline PTX can address it as a link-time constant.
+extern "C" {
+extern __shared__ __align__(128) uint8_t pire_b200_smem[];
+}
 
 namespace pire_b200 {
 
@@ -158,7 +164,7 @@ struct Tables {
     uint32_t H;
     uint32_t letters;
     uint32_t wide;
-    uint32_t m0;
+    uint32_t m0, m0hi;        // 64-slot exit bitmap of hot id 0
 };
 
 // One byte through the complete table (hot rows first: they are in shared memory).
@@ -197,23 +203,28 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
     // idx = (g << 8) | byte_k(w): byte address of the fused row entry.
     uint32_t idx = __byte_perm(w, g, sel);
     if (kPred) {
-        // bit (byte & 31) of m0: may this byte leave hot id 0?  Lanes resting in
-        // id 0 on a self-looping byte skip the load (fewer bank conflicts).
-        // Spelled in PTX so that the load stays one predicated LDS [R+UR]
-        // (SHF, LOP3 -> predicate, @p LDS) instead of a re-derived address.
+        // bit (byte & 63) of the 64-slot exit bitmap: may this byte leave hot id 0?
+        // Lanes resting in id 0 on a self-looping byte skip the load (fewer bank
+        // conflicts).  Spelled in PTX so that the load stays one predicated
+        // LDS [R+UR] (LOP3, SHF.R.U64, LOP3 -> predicate, @p LDS).
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            ".reg .b32 probe, addr;\n"
-            "shf.r.wrap.b32 probe, %2, 0, %1;\n"
+            ".reg .b32 slot, probe, addr;\n"
+            ".reg .b64 mask, shifted;\n"
+            "and.b32 slot, %1, 63;\n"
+            "mov.b64 mask, {%2, %3};\n"
+            "shr.u64 shifted, mask, slot;\n"
+            "cvt.u32.u64 probe, shifted;\n"
             "and.b32 probe, probe, 1;\n"
             "or.b32 probe, probe, %0;\n"
             "setp.ne.u32 p, probe, 0;\n"
-            "add.u32 addr, %1, %3;\n"
+            "mov.u32 addr, pire_b200_smem;\n"          // hot rows start the dynamic array (kPred kernels)
+            "add.u32 addr, addr, %1;\n"
             "@p ld.shared.u8 %0, [addr];\n"
             "}\n"
             : "+r"(g)
-            : "r"(idx), "r"(t.m0), "r"(t.hot_saddr));
+            : "r"(idx), "r"(t.m0), "r"(t.m0hi));
     } else {
         g = t.hot[idx];
     }
@@ -243,6 +254,7 @@ __device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t*
     t.letters = letters_wide & 0x7fffffffu;
     t.wide = letters_wide >> 31;
     t.m0 = 0;
+    t.m0hi = 0;
     uint32_t s = from;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -297,7 +309,7 @@ __device__ __forceinline__ void Report(const ScanArgs& a, const Tables& t, const
 template <bool kPred>
 __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(const __grid_constant__ ScanArgs a)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv);
 
@@ -310,6 +322,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.exit_bitmap0;
+    t.m0hi = a.exit_bitmap0_hi;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
@@ -360,7 +373,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 template <bool kPred>
 __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv);
 
@@ -373,6 +386,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.exit_bitmap0;
+    t.m0hi = a.exit_bitmap0_hi;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
@@ -482,6 +496,7 @@ __device__ __noinline__ uint2 PrivSlowWord(const uint8_t* hot, const uint16_t* c
     t.letters = letters_wide & 0x7fffffffu;
     t.wide = letters_wide >> 31;
     t.m0 = 0;
+    t.m0hi = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         state = SlowStep(t, state, (w >> (8 * k)) & 0xffu);
@@ -512,7 +527,7 @@ __device__ __forceinline__ void PrivWord(const ScanArgs& a, const SharedView& sv
 
 __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __grid_constant__ ScanArgs a)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot, a.priv_rows);
     StageTables(a, sv);
     {

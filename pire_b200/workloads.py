@@ -81,11 +81,27 @@ class SynthSpec:
                 "pire_gpu_synth_fill_device")
         return tensor
 
-    def host_sample(self, first, count):
-        """Strings [first, first+count) of the same corpus, generated on the host."""
+    def host_sample(self, first, count, threads=0):
+        """Strings [first, first+count) of the same corpus, generated on the host
+        (sliced over a few threads: the generator is pure and the C call drops the GIL)."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
         out = np.empty(count * self.string_len, np.uint8)
         s = self._c()
-        N.check(N.lib.pire_gpu_synth_fill_host(C.byref(s), out.ctypes.data, first, count), "pire_gpu_synth_fill_host")
+        if threads <= 0:
+            threads = min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
+        threads = max(1, min(threads, count // 4096 or 1))
+
+        def fill(k):
+            lo = count * k // threads
+            hi = count * (k + 1) // threads
+            N.check(N.lib.pire_gpu_synth_fill_host(C.byref(s), out.ctypes.data + lo * self.string_len, first + lo, hi - lo),
+                    "pire_gpu_synth_fill_host")
+        if threads == 1:
+            fill(0)
+        else:
+            with ThreadPoolExecutor(threads) as pool:
+                list(pool.map(fill, range(threads)))
         return out
 
     def shard(self, rank, world):

@@ -114,8 +114,8 @@ int main(int argc, char** argv)
                 if (b >= 0x20 && b < 0x7f)
                     ex += (char) b;
             }
-        std::printf("hot id 0 = state %u: %d exit bytes [%s], bitmap %08x (%d slots)\n", s0, exits, ex.c_str(),
-                    t.exit_bitmap0, __builtin_popcount(t.exit_bitmap0));
+        std::printf("hot id 0 = state %u: %d exit bytes [%s], bitmap %016llx (%d slots)\n", s0, exits, ex.c_str(),
+                    (unsigned long long) t.exit_bitmap0, __builtin_popcountll(t.exit_bitmap0));
     }
 
     // Private-row model: P most visited rows are lane-private (never conflict); a lane that
@@ -161,8 +161,12 @@ int main(int argc, char** argv)
     const int filter_mode = fm ? std::atoi(fm) : 0;      // -1 exact, k = slot (b >> k) & 31
     uint32_t bitmap = 0;
     for (uint32_t b = 0; b < 256; ++b)
-        if (t.hot8[b] != 0 && filter_mode >= 0)
+        if (t.hot8[b] != 0 && filter_mode >= 0 && filter_mode < 8)
             bitmap |= 1u << ((b >> filter_mode) & 31);
+    uint64_t bitmap64 = 0;
+    for (uint32_t b = 0; b < 256; ++b)
+        if (t.hot8[b] != 0)
+            bitmap64 |= 1ull << (b & 63);
     std::printf("filter mode %d bitmap %08x\n", filter_mode, bitmap);
     uint64_t steps = 0, wf_plain = 0, wf_pred = 0, active_pred = 0, lds_pred = 0;
     uint64_t chunks = 0, replay_lane_chunks = 0, replay_warp_chunks = 0;
@@ -199,6 +203,8 @@ int main(int argc, char** argv)
                     bool need;
                     if (filter_mode < 0)
                         need = g[l] != 0 || t.hot8[b] != 0;                       // exact
+                    else if (filter_mode == 64)
+                        need = g[l] != 0 || ((bitmap64 >> (b & 63)) & 1);
                     else
                         need = g[l] != 0 || ((bitmap >> ((b >> filter_mode) & 31)) & 1);
                     if (need) {
