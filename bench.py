@@ -31,6 +31,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 STRING_LEN = 1024
 STRINGS_PER_GPU = 9_765_632          # x 1 KiB = 10.000007 GB per GPU (multiple of 32 strings)
+MIXED_STRINGS_PER_GPU = 1_281_024    # mixed 16 B..64 KiB strings, mean 7.8 KB: ~10 GB per GPU
 FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -40,8 +41,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
-    ap.add_argument("--workload", default="glue10", choices=["glue10", "headline"])
-    ap.add_argument("--strings", type=int, default=STRINGS_PER_GPU, help="strings per GPU")
+    ap.add_argument("--workload", default="glue10", choices=["glue10", "headline", "utf8mixed"])
+    ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: 10 GB worth)")
     ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv"])
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -107,69 +108,78 @@ def cpu_reference(workload, threads, n_sample, reps, first_string=0):
     from refpire import Ref
     from pire_b200 import workloads as W
     ref = Ref()
-    patterns = W.GLUE10 if workload == "glue10" else [W.HEADLINE]
-    sc = ref.glue_all(patterns)
-    _, plants, _, _ = W.WORKLOADS[workload]
-    spec = W.SynthSpec(n_sample, STRING_LEN, plants=plants, first_string=first_string)
-    sample = spec.host_sample(0, n_sample)
+    sc, sample, offsets, n_sample, gb = reference_sample(ref, workload, n_sample, first_string)
+    kw = dict(offsets=offsets) if offsets is not None else dict(fixed_len=STRING_LEN)
     if threads <= 0:
         threads = ref.hardware_threads()
     best, matches = 1e30, 0
     for _ in range(reps):
         t0 = time.perf_counter()
-        final, mask, _ = sc.run(sample, fixed_len=STRING_LEN, n=n_sample, variant=1, threads=threads,
-                                want=("final", "mask"))
+        final, mask, _ = sc.run(sample, n=n_sample, variant=1, threads=threads, want=("final", "mask"), **kw)
         best = min(best, time.perf_counter() - t0)
         matches = int(final.sum())
     # single-thread figures on a slice, both with and without the ExitMasks fast-forward
-    k = min(n_sample, 1 << 16)
+    k = min(n_sample, 1 << 16 if offsets is None else 1 << 13)
+    kb = (k * STRING_LEN if offsets is None else int(offsets[k])) / 1e9
     t0 = time.perf_counter()
-    sc.run(sample[: k * STRING_LEN], fixed_len=STRING_LEN, n=k, variant=1, threads=1, want=("final",))
+    sc.run(sample, n=k, variant=1, threads=1, want=("final",), **kw)
     t_mask = time.perf_counter() - t0
     t0 = time.perf_counter()
-    sc.run(sample[: k * STRING_LEN], fixed_len=STRING_LEN, n=k, variant=2, threads=1, want=("final",))
+    sc.run(sample, n=k, variant=2, threads=1, want=("final",), **kw)
     t_nomask = time.perf_counter() - t0
-    gb = n_sample * STRING_LEN / 1e9
     return {
         "value": gb / best, "unit": "GB/s", "cores": threads, "kind": "reference",
-        "sample": "%d x %d B strings of the same synthetic corpus (%.2f GB), best of %d, NonrelocScanner" % (
-            n_sample, STRING_LEN, gb, reps),
+        "sample": "%d strings of the same synthetic corpus (%.2f GB), best of %d, NonrelocScanner, static partition by string count" % (
+            n_sample, gb, reps),
         "matches": matches,
-        "one_thread_GBps": k * STRING_LEN / 1e9 / t_mask,
-        "one_thread_nomask_GBps": k * STRING_LEN / 1e9 / t_nomask,
+        "one_thread_GBps": kb / t_mask,
+        "one_thread_nomask_GBps": kb / t_nomask,
     }
+
+
+def reference_sample(ref, workload, n_sample, first_string=0):
+    """The reference scanner for a workload plus a host-generated sample of its corpus."""
+    from pire_b200 import workloads as W
+    if workload == "utf8mixed":
+        sc = ref.compile(*W.HEADLINE_IU)
+        n_sample = min(n_sample, 1 << 17)          # mean string is 7.8 KB: ~1 GB
+        sample, offsets = W.MixedSpec(n_sample, first_string=first_string).host_batch(0, n_sample)
+        return sc, sample, offsets, n_sample, int(offsets[-1]) / 1e9
+    sc = ref.glue_all(W.GLUE10 if workload == "glue10" else [W.HEADLINE])
+    spec = W.SynthSpec(n_sample, STRING_LEN, plants=W.WORKLOADS[workload][1], first_string=first_string)
+    return sc, spec.host_sample(0, n_sample), None, n_sample, n_sample * STRING_LEN / 1e9
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    per_step = min(args.cpu_sample, args.strings)
+    per_step = min(args.cpu_sample, args.strings or args.cpu_sample)
     t_all = time.perf_counter()
-    cb = cpu_reference(args.workload, 0, per_step, 1)        # warm-up + the single-thread figures
+    cb = cpu_reference(args.workload, 0, min(per_step, 1 << 20), 1)        # warm-up + the single-thread figures
     times = []
     from refpire import Ref
     from pire_b200 import workloads as W
     ref = Ref()
-    sc = ref.glue_all(W.GLUE10 if args.workload == "glue10" else [W.HEADLINE])
-    spec = W.SynthSpec(per_step, STRING_LEN, plants=W.WORKLOADS[args.workload][1])
-    sample = spec.host_sample(0, per_step)
+    sc, sample, offsets, per_step, gb = reference_sample(ref, args.workload, per_step)
+    kw = dict(offsets=offsets) if offsets is not None else dict(fixed_len=STRING_LEN)
     threads = ref.hardware_threads()
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        sc.run(sample, fixed_len=STRING_LEN, n=per_step, variant=1, threads=threads, want=("final", "mask"))
+        sc.run(sample, n=per_step, variant=1, threads=threads, want=("final", "mask"), **kw)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
-    value = per_step * STRING_LEN * args.steps / 1e9 / total
-    cb.update(value=value, cores=threads)
+    value = gb * args.steps / total
+    cb.update(value=value, cores=threads,
+              sample="%d strings of the same synthetic corpus (%.2f GB) per step, NonrelocScanner" % (per_step, gb))
     line = {
         "impl": "reference", "metric": "scanned GB/s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%s: %s; each step = a bounded sample of %d x 1 KiB strings on the host" % (
-            args.workload, W.WORKLOADS[args.workload][2], per_step), "host_threads": threads},
+        "config": {"workload": "%s: %s; each step = a bounded sample of %d strings (%.2f GB) on the host" % (
+            args.workload, W.WORKLOADS[args.workload][2], per_step, gb), "host_threads": threads},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "strings_per_s": per_step * args.steps / total,
@@ -203,14 +213,32 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     image_name, plants, desc, cfg_index = W.WORKLOADS[args.workload]
-    n_local = args.strings // 32 * 32
+    mixed = args.workload == "utf8mixed"
+    n_local = (args.strings or (MIXED_STRINGS_PER_GPU if mixed else STRINGS_PER_GPU)) // 32 * 32
     n_global = n_local * world
     lo = rank * n_local
-    spec = W.SynthSpec(n_local, STRING_LEN, plants=plants, first_string=lo)
-    corpus = torch.empty(spec.total_bytes(), dtype=torch.uint8, device=dev)
-    spec.fill_device(corpus)
-    batch = P.Batch(corpus, fixed_len=STRING_LEN, n=n_local)
-    payload_local = n_local * STRING_LEN
+    if mixed:
+        # BASELINE configs[3]: CSR batch of very unequal strings; binned by length (on the device) once
+        spec = W.MixedSpec(n_local, first_string=lo)
+        corpus, offsets = spec.device_batch(dev)
+        batch = P.Batch(corpus, offsets, n=n_local)
+        payload_local = batch.payload_bytes()
+        t0 = time.perf_counter()
+        batch.bin_by_length()
+        torch.cuda.synchronize()
+        bin_ms = 1e3 * (time.perf_counter() - t0)
+    else:
+        spec = W.SynthSpec(n_local, STRING_LEN, plants=plants, first_string=lo)
+        corpus = torch.empty(spec.total_bytes(), dtype=torch.uint8, device=dev)
+        spec.fill_device(corpus)
+        batch = P.Batch(corpus, fixed_len=STRING_LEN, n=n_local)
+        payload_local = n_local * STRING_LEN
+        bin_ms = None
+    payload_global = payload_local
+    if world > 1:
+        t = torch.tensor([payload_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        payload_global = int(t.item())
 
     sc = P.Scanner(W.load_image(image_name), local)
     tune_ms = None
@@ -290,7 +318,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    value = n_global * STRING_LEN / 1e9 / (ms_per_step / 1e3)
+    value = payload_global / 1e9 / (ms_per_step / 1e3)
 
     # the scan kernel alone (CUDA events around the launches only), for the roofline
     kernel_ms = time_scan(min(args.steps, 10))
@@ -302,21 +330,28 @@ def main():
     if world > 1:
         dist.all_reduce(local_pop, op=dist.ReduceOp.SUM)
     assert int(local_pop.item()) == matches_global, (int(local_pop.item()), matches_global)
-    assert matches_local_masks == popcount_bits(bits_local) and matches_local_masks >= n_local // 8
+    assert matches_local_masks == popcount_bits(bits_local)
+    assert matches_local_masks >= (n_local // 8) * (0.9 if mixed else 1.0)      # strings < 32 B carry no plant
 
     # end to end: host buffers through the C ABI, H2D and D2H inside the timed region
     e2e = None
     if not args.no_e2e:
         try:
             host = torch.empty(payload_local, dtype=torch.uint8, pin_memory=True)
-            host.copy_(corpus)
+            host.copy_(corpus[:payload_local])
+            host_offs = None
+            if mixed:
+                host_offs = torch.empty(n_local + 1, dtype=torch.int64, pin_memory=True)
+                host_offs.copy_(batch.offsets)
             torch.cuda.synchronize()
             hb = torch.empty(words_local, dtype=torch.int32, pin_memory=True)
             hm = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
             hv = host.numpy()
 
             def e2e_step():
-                N.check(N.lib.pire_gpu_run_batch_host(sc._h, hv.ctypes.data, payload_local, None, STRING_LEN, n_local,
+                N.check(N.lib.pire_gpu_run_batch_host(sc._h, hv.ctypes.data, payload_local,
+                                                      host_offs.data_ptr() if mixed else None,
+                                                      0 if mixed else STRING_LEN, n_local,
                                                       flags, hb.data_ptr(), hm.data_ptr(), None), "run_batch_host")
             e2e_step()
             e2e_steps = max(1, min(args.steps, 3))
@@ -330,8 +365,9 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             assert torch.equal(hb, bits_local.cpu()) and torch.equal(hm, masks.cpu())
-            e2e = {"value": n_global * STRING_LEN / 1e9 / (dt / e2e_steps), "unit": "GB/s",
-                   "h2d_bytes_per_step": payload_local, "d2h_bytes_per_step": words_local * 4 + n_local * 4,
+            e2e = {"value": payload_global / 1e9 / (dt / e2e_steps), "unit": "GB/s",
+                   "h2d_bytes_per_step": payload_local + (8 * (n_local + 1) if mixed else 0),
+                   "d2h_bytes_per_step": words_local * 4 + n_local * 4,
                    "steps": e2e_steps, "api": "pire_gpu_run_batch_host (pinned host corpus in, bitmap + accept masks out)"}
             del host, hv
         except Exception as ex:          # e.g. not enough pinnable host memory
@@ -356,9 +392,11 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {
-            "workload": "BASELINE configs[%d]: %s over %d x 1 KiB synthetic printable-ASCII strings per GPU (%.2f GB/GPU), "
-                        "1/8 of the strings carry a planted match" % (cfg_index, desc, n_local, payload_local / 1e9),
-            "strings_per_gpu": n_local, "string_len": STRING_LEN, "outputs": "match bitmap + u32 accept mask per string",
+            "workload": "BASELINE configs[%d]: %s; %d synthetic strings per GPU (%.2f GB/GPU), "
+                        "1/8 of the strings carry a planted match" % (
+                            cfg_index, desc if mixed else desc + " over 1 KiB printable-ASCII strings", n_local, payload_local / 1e9),
+            "strings_per_gpu": n_local, "string_len": "16..65535 (CSR, binned by length on device)" if mixed else STRING_LEN,
+            "bin_ms": bin_ms, "outputs": "match bitmap + u32 accept mask per string",
             "kernel_variant": chosen, "variant_ms": variant_ms or None, "hot_rows": info.hot_rows, "tuned": bool(info.tuned),
             "tune_ms": tune_ms, "l2": "input (%.1f GB) is far larger than L2; no flush needed" % (payload_local / 1e9),
             "collective": (args.collective + " of the match bitmap (NCCL)") if world > 1 else "none (1 GPU)",
@@ -367,7 +405,7 @@ def main():
         "matches": matches_global, "matches_local_by_mask": matches_local_masks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "ScanUniformPrivKernel" if chosen == "priv" else "ScanUniformKernel<%s>" % chosen, "kernel_ms": kernel_ms,
+                     "traffic": traffic, "kernel": ("ScanGenericKernel<%s>" % chosen) if mixed else "ScanUniformPrivKernel" if chosen == "priv" else "ScanUniformKernel<%s>" % chosen, "kernel_ms": kernel_ms,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": payload_local},
         "clocks": clocks,

@@ -108,6 +108,19 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc,
                        uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx,
                        void* stream);
 
+/* Length-binned form of pire_gpu_run_batch for batches of very unequal strings
+ * (BASELINE config 4: 16 B .. 64 KiB).  One string per lane means a warp runs as
+ * long as its longest string; with `d_order` (a permutation of 0..n-1, longest
+ * first, from pire_gpu_length_order) warps get strings of similar length and claim
+ * them longest-first.  Results are still indexed by the original string number.
+ * CSR batches only; n < 2^32. */
+int pire_gpu_length_order(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, int device, void* stream);
+int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc,
+                               const uint8_t* d_corpus, const uint64_t* d_offsets, const uint32_t* d_order,
+                               uint64_t n, uint32_t flags,
+                               uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx,
+                               void* stream);
+
 /* Same call with HOST buffers (what a Pire user holds: const char* ranges):
  * copies corpus (+offsets) to the device, runs, copies the requested results
  * back and synchronises.  corpus_bytes = total bytes of the corpus buffer. */
@@ -172,6 +185,18 @@ typedef struct pire_gpu_synth {
 
 int pire_gpu_synth_fill_device(const pire_gpu_synth* spec, uint8_t* d_corpus, int device, void* stream);
 int pire_gpu_synth_fill_host(const pire_gpu_synth* spec, uint8_t* corpus, uint64_t first, uint64_t count);
+
+/* kind 1: mixed-length UTF-8 corpus (BASELINE config 4): lengths log-uniform in
+ * [16, 65536), multiples of 4; ASCII / 2-byte Cyrillic / 3-byte code points; every
+ * plant_every-th string (>= 32 bytes) ends with a mixed-case hit for the
+ * case-insensitive headline pattern.  *_lengths_* writes n lengths (the caller
+ * prefix-sums them into CSR offsets); *_fill_* writes the bytes for given offsets. */
+int pire_gpu_synth_mixed_lengths_device(uint64_t seed, uint64_t first_string, uint64_t n, uint64_t* d_lengths, int device, void* stream);
+int pire_gpu_synth_mixed_lengths_host(uint64_t seed, uint64_t first_string, uint64_t n, uint64_t* lengths);
+int pire_gpu_synth_mixed_fill_device(uint64_t seed, uint32_t plant_every, uint64_t first_string, uint64_t n,
+                                     const uint64_t* d_offsets, uint8_t* d_corpus, int device, void* stream);
+int pire_gpu_synth_mixed_fill_host(uint64_t seed, uint32_t plant_every, uint64_t first_string, uint64_t n,
+                                   const uint64_t* offsets, uint8_t* corpus);
 
 const char* pire_gpu_last_error(void);
 const char* pire_gpu_version(void);

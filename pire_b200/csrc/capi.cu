@@ -90,6 +90,8 @@ struct pire_gpu_scanner {
     size_t ws_offsets_bytes = 0;
     uint32_t* ws_out = nullptr;
     size_t ws_out_bytes = 0;
+    uint32_t* ws_order = nullptr;
+    size_t ws_order_bytes = 0;
     cudaStream_t ws_stream = nullptr;
 };
 
@@ -177,8 +179,8 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->letters = t.letters;
     a->wide = t.wide ? 1 : 0;
     a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
-    a->exit_bitmap0 = (uint32_t) t.exit_bitmap0;
-    a->exit_bitmap0_hi = (uint32_t) (t.exit_bitmap0 >> 32);
+    a->exit_bitmap0 = t.exit_bitmap0;
+    a->exit_shift = t.exit_shift;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
 }
@@ -246,6 +248,7 @@ void pire_gpu_scanner_destroy(pire_gpu_scanner* sc)
         cudaFree(sc->ws_corpus);
         cudaFree(sc->ws_offsets);
         cudaFree(sc->ws_out);
+        cudaFree(sc->ws_order);
         if (sc->ws_stream)
             cudaStreamDestroy(sc->ws_stream);
     }
@@ -317,6 +320,57 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     return PIRE_GPU_OK;
 }
 
+int pire_gpu_length_order(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, int device, void* stream)
+{
+    if (n && (!d_offsets || !d_order))
+        return Fail(PIRE_GPU_EINVAL, "null offsets or order");
+    if (n >= (1ull << 31))
+        return Fail(PIRE_GPU_EINVAL, "too many strings for a length order");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(LengthOrder(d_offsets, n, d_order, static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                               const uint32_t* d_order, uint64_t n, uint32_t flags,
+                               uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END))
+        return Fail(PIRE_GPU_EINVAL, "unknown run flags");
+    if (n == 0)
+        return PIRE_GPU_OK;
+    if (!d_corpus || !d_offsets || !d_order)
+        return Fail(PIRE_GPU_EINVAL, "ordered runs need corpus, CSR offsets and an order");
+    if (n >= (1ull << 31))
+        return Fail(PIRE_GPU_EINVAL, "too many strings");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScanArgs a;
+    FillArgs(sc, &a, d_corpus, d_offsets, 0, n, flags);
+    a.order = d_order;
+    a.match_bits = d_match_bits;
+    a.accept_masks = d_accept_masks;
+    a.state_idx = d_state_idx;
+    unsigned int* counter = nullptr;
+    CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned int), st));
+    cudaError_t ce = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (ce == cudaSuccess && d_match_bits)
+        ce = cudaMemsetAsync(d_match_bits, 0, (size_t) ((n + 31) / 32) * 4, st);
+    a.work_counter = counter;
+    uint32_t variant = ResolveVariant(sc, false);
+    if (variant == PIRE_GPU_VARIANT_PRIV)
+        variant = PIRE_GPU_VARIANT_PLAIN;
+    if (ce == cudaSuccess)
+        ce = LaunchScan(a, (int) variant, false, sc->plan[variant][0], st);
+    cudaFreeAsync(counter, st);
+    if (ce != cudaSuccess)
+        return FailCuda(ce, "pire_gpu_run_batch_ordered");
+    return PIRE_GPU_OK;
+}
+
 int pire_gpu_run_batch_host(const pire_gpu_scanner* csc, const uint8_t* corpus, uint64_t corpus_bytes,
                             const uint64_t* offsets, uint64_t fixed_len, uint64_t n, uint32_t flags,
                             uint32_t* match_bits, uint32_t* accept_masks, uint32_t* state_idx)
@@ -361,13 +415,27 @@ int pire_gpu_run_batch_host(const pire_gpu_scanner* csc, const uint8_t* corpus, 
     uint32_t* d_bits = match_bits ? sc->ws_out : nullptr;
     uint32_t* d_masks = accept_masks ? sc->ws_out + words : nullptr;
     uint32_t* d_states = state_idx ? sc->ws_out + words + n : nullptr;
+    const bool binned = offsets != nullptr && n >= 64 && n < (1ull << 31);
+    if (binned && sc->ws_order_bytes < (size_t) n * 4) {
+        cudaFree(sc->ws_order);
+        sc->ws_order = nullptr;
+        sc->ws_order_bytes = 0;
+        CUDA_TRY(cudaMalloc(&sc->ws_order, (size_t) n * 4));
+        sc->ws_order_bytes = (size_t) n * 4;
+    }
 
     if (corpus_bytes)
         CUDA_TRY(cudaMemcpyAsync(sc->ws_corpus, corpus, corpus_bytes, cudaMemcpyHostToDevice, st));
     if (offsets)
         CUDA_TRY(cudaMemcpyAsync(sc->ws_offsets, offsets, need_off, cudaMemcpyHostToDevice, st));
-    rc = pire_gpu_run_batch(sc, sc->ws_corpus, offsets ? sc->ws_offsets : nullptr, fixed_len, n, flags,
-                            d_bits, d_masks, d_states, st);
+    if (binned) {
+        // strings of unknown, unequal lengths: bin them so that a warp's lanes finish together
+        CUDA_TRY(LengthOrder(sc->ws_offsets, n, sc->ws_order, st));
+        rc = pire_gpu_run_batch_ordered(sc, sc->ws_corpus, sc->ws_offsets, sc->ws_order, n, flags, d_bits, d_masks, d_states, st);
+    } else {
+        rc = pire_gpu_run_batch(sc, sc->ws_corpus, offsets ? sc->ws_offsets : nullptr, fixed_len, n, flags,
+                                d_bits, d_masks, d_states, st);
+    }
     if (rc != PIRE_GPU_OK)
         return rc;
     if (match_bits)
@@ -603,6 +671,49 @@ int pire_gpu_synth_fill_host(const pire_gpu_synth* spec, uint8_t* corpus, uint64
             std::memcpy(dst + off, packed.data() + p.plant_off[id], p.plant_off[id + 1] - p.plant_off[id]);
             if (p.tail && p.plant_mode[id] == 0)
                 dst[p.string_len - 1] = (uint8_t) p.tail;
+        }
+    }
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_synth_mixed_lengths_device(uint64_t seed, uint64_t first_string, uint64_t n, uint64_t* d_lengths, int device, void* stream)
+{
+    if (!d_lengths && n)
+        return Fail(PIRE_GPU_EINVAL, "null lengths");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(LaunchSynthMixedLengths(seed, first_string, n, d_lengths, static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_synth_mixed_lengths_host(uint64_t seed, uint64_t first_string, uint64_t n, uint64_t* lengths)
+{
+    if (!lengths && n)
+        return Fail(PIRE_GPU_EINVAL, "null lengths");
+    for (uint64_t i = 0; i < n; ++i)
+        lengths[i] = SynthMixedLength(seed, first_string + i);
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_synth_mixed_fill_device(uint64_t seed, uint32_t plant_every, uint64_t first_string, uint64_t n,
+                                     const uint64_t* d_offsets, uint8_t* d_corpus, int device, void* stream)
+{
+    if (n && (!d_offsets || !d_corpus))
+        return Fail(PIRE_GPU_EINVAL, "null offsets or corpus");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(LaunchSynthMixedFill(seed, plant_every, first_string, n, d_offsets, d_corpus, static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_synth_mixed_fill_host(uint64_t seed, uint32_t plant_every, uint64_t first_string, uint64_t n,
+                                   const uint64_t* offsets, uint8_t* corpus)
+{
+    if (n && (!offsets || !corpus))
+        return Fail(PIRE_GPU_EINVAL, "null offsets or corpus");
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t len = (uint32_t) (offsets[i + 1] - offsets[i]);
+        for (uint32_t cell = 0; cell < len / 4; ++cell) {
+            uint32_t v = SynthMixedCellPlanted(seed, plant_every, first_string + i, len, cell);
+            std::memcpy(corpus + offsets[i] + (size_t) cell * 4, &v, 4);
         }
     }
     return PIRE_GPU_OK;

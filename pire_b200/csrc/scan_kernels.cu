@@ -14,7 +14,7 @@
 //     input byte k in bits 0..7 and g in bits 8..15, which is the byte address
 //     of the fused row entry.  No class lookup, no multiply, no branch.
 //   * kPred variant: the LDS is predicated off while the lane sits in hot id 0
-//     and the byte cannot leave it (64-slot bitmap probed with one 64-bit shift),
+//     and the byte cannot leave it (32-slot bitmap probed with a funnel shift),
 //     so fewer lanes hit the banks and the load costs fewer wavefronts.
 //   * Input bytes: each lane streams its own string with 32-byte (uniform
 //     kernel, LDG.256) or 16-byte (generic kernel) read-only vector loads that
@@ -29,6 +29,8 @@
 #include "scan_kernels.cuh"
 
 #include <atomic>
+
+#include <cub/device/device_radix_sort.cuh>
 
 // One dynamic shared-memory array for every kernel of this file, with an unmangled
 // PTX name so that inline PTX can address it as a link-time constant.
@@ -164,7 +166,7 @@ struct Tables {
     uint32_t H;
     uint32_t letters;
     uint32_t wide;
-    uint32_t m0, m0hi;        // 64-slot exit bitmap of hot id 0
+    uint32_t m0, mshift;      // 32-slot exit bitmap of hot id 0, slot = (byte >> mshift) & 31
 };
 
 // One byte through the complete table (hot rows first: they are in shared memory).
@@ -203,19 +205,18 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
     // idx = (g << 8) | byte_k(w): byte address of the fused row entry.
     uint32_t idx = __byte_perm(w, g, sel);
     if (kPred) {
-        // bit (byte & 63) of the 64-slot exit bitmap: may this byte leave hot id 0?
+        // bit ((byte >> mshift) & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
         // Lanes resting in id 0 on a self-looping byte skip the load (fewer bank
-        // conflicts).  Spelled in PTX so that the load stays one predicated
-        // LDS [R+UR] (LOP3, SHF.R.U64, LOP3 -> predicate, @p LDS).
+        // conflicts).  Spelled in PTX so that it stays SHF, LOP3 -> predicate,
+        // @p LDS.  (A 64-slot bitmap probed with SHF.R.U64 passes fewer lanes --
+        // 2.12 vs 2.23 modelled wavefronts -- but measured 8 % slower: the extra
+        // ALU-pipe instructions, issued at half rate, become the bound; r01 log.)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            ".reg .b32 slot, probe, addr;\n"
-            ".reg .b64 mask, shifted;\n"
-            "and.b32 slot, %1, 63;\n"
-            "mov.b64 mask, {%2, %3};\n"
-            "shr.u64 shifted, mask, slot;\n"
-            "cvt.u32.u64 probe, shifted;\n"
+            ".reg .b32 probe, addr;\n"
+            "shr.u32 probe, %1, %3;\n"
+            "shf.r.wrap.b32 probe, %2, 0, probe;\n"
             "and.b32 probe, probe, 1;\n"
             "or.b32 probe, probe, %0;\n"
             "setp.ne.u32 p, probe, 0;\n"
@@ -224,7 +225,7 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
             "@p ld.shared.u8 %0, [addr];\n"
             "}\n"
             : "+r"(g)
-            : "r"(idx), "r"(t.m0), "r"(t.m0hi));
+            : "r"(idx), "r"(t.m0), "r"(t.mshift));
     } else {
         g = t.hot[idx];
     }
@@ -254,7 +255,7 @@ __device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t*
     t.letters = letters_wide & 0x7fffffffu;
     t.wide = letters_wide >> 31;
     t.m0 = 0;
-    t.m0hi = 0;
+    t.mshift = 0;
     uint32_t s = from;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -303,6 +304,21 @@ __device__ __forceinline__ void Report(const ScanArgs& a, const Tables& t, const
     }
 }
 
+// Ordered (length-binned) launches: lane -> string is a permutation, so the match
+// bit goes to its word with an atomic OR (the caller zeroes the bitmap).
+__device__ __forceinline__ void ReportScattered(const ScanArgs& a, const Tables& t, const LaneState& s, uint64_t i, bool valid)
+{
+    if (!valid)
+        return;
+    DeviceFin f = a.fin[FullState(t, s)];
+    if (a.match_bits && (f.result >> 31))
+        atomicOr(&a.match_bits[i >> 5], 1u << (i & 31));
+    if (a.accept_masks)
+        a.accept_masks[i] = f.mask;
+    if (a.state_idx)
+        a.state_idx[i] = f.result & 0x7fffffffu;
+}
+
 // ---------------------------------------------------------------- kernels
 
 // Uniform batch: fixed length, length % 32 == 0, corpus 32-byte aligned.
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.exit_bitmap0;
-    t.m0hi = a.exit_bitmap0_hi;
+    t.mshift = a.exit_shift;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
@@ -386,25 +402,27 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.exit_bitmap0;
-    t.m0hi = a.exit_bitmap0_hi;
+    t.mshift = a.exit_shift;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
     const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
 
-    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
-        const uint64_t i = unit * 32 + lane;
-        const bool valid = i < a.n;
-        uint64_t b = 0, e = 0;
-        if (valid) {
-            if (a.offsets) {
-                b = a.offsets[i];
-                e = a.offsets[i + 1];
-            } else {
-                b = i * a.fixed_len;
-                e = b + a.fixed_len;
-            }
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);; unit += warps) {
+        if (a.work_counter) {
+            // length-binned launch: units are sorted longest first and claimed dynamically
+            // (longest-processing-time-first keeps the 64 KiB strings off the tail)
+            unsigned int claimed = 0;
+            if (lane == 0)
+                claimed = atomicAdd(a.work_counter, 1u);
+            unit = __shfl_sync(0xffffffffu, claimed, 0);
         }
+        if (unit >= units)
+            break;
+        const uint64_t slot = unit * 32 + lane;
+        const bool valid = slot < a.n;
+        const uint64_t i = valid && a.order ? a.order[slot] : slot;
+        uint64_t b = 0, e = 0;
         const uint8_t* p = a.corpus + b;
         const uint8_t* end = a.corpus + e;
 
@@ -448,7 +466,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
                 full = SlowStep(t, full, *p++);
             SetFull(t, s, full);
         }
-        Report(a, t, s, unit, i, valid);
+        if (a.order)
+            ReportScattered(a, t, s, i, valid);
+        else
+            Report(a, t, s, unit, i, valid);
     }
 }
 
@@ -496,7 +517,7 @@ __device__ __noinline__ uint2 PrivSlowWord(const uint8_t* hot, const uint16_t* c
     t.letters = letters_wide & 0x7fffffffu;
     t.wide = letters_wide >> 31;
     t.m0 = 0;
-    t.m0hi = 0;
+    t.mshift = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         state = SlowStep(t, state, (w >> (8 * k)) & 0xffu);
@@ -668,6 +689,28 @@ __global__ void __launch_bounds__(256) SynthKernel(const __grid_constant__ Synth
     }
 }
 
+__global__ void __launch_bounds__(256) SynthMixedLengthsKernel(uint64_t seed, uint64_t first, uint64_t n, uint64_t* __restrict__ lengths)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        lengths[i] = SynthMixedLength(seed, first + i);
+}
+
+// One warp per string: lanes write consecutive 4-byte cells (coalesced).
+__global__ void __launch_bounds__(256) SynthMixedFillKernel(uint64_t seed, uint32_t plant_every, uint64_t first, uint64_t n,
+                                                            const uint64_t* __restrict__ offsets, uint8_t* __restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t) gridDim.x * (blockDim.x / 32);
+    for (uint64_t i = (uint64_t) blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); i < n; i += warps) {
+        const uint64_t b = offsets[i];
+        const uint32_t len = (uint32_t) (offsets[i + 1] - b);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + b);      // offsets are multiples of 4
+        for (uint32_t cell = lane; cell < len / 4; cell += 32)
+            dst[cell] = SynthMixedCellPlanted(seed, plant_every, first + i, len, cell);
+    }
+}
+
 template <bool kPred>
 const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUniformKernel<kPred>); }
 template <bool kPred>
@@ -748,6 +791,46 @@ cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+namespace {
+__global__ void __launch_bounds__(256) LengthKeysKernel(const uint64_t* __restrict__ offsets, uint64_t n, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ ids)
+{
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint64_t len = offsets[i + 1] - offsets[i];
+        keys[i] = ~(uint32_t) (len > 0xffffffffull ? 0xffffffffull : len);     // ascending sort of ~len = descending length
+        ids[i] = (uint32_t) i;
+    }
+}
+} // namespace
+
+cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    uint32_t *keys = nullptr, *keys_out = nullptr, *ids = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t err = cudaMallocAsync(&keys, n * 4, stream);
+    if (err == cudaSuccess) err = cudaMallocAsync(&keys_out, n * 4, stream);
+    if (err == cudaSuccess) err = cudaMallocAsync(&ids, n * 4, stream);
+    if (err == cudaSuccess) {
+        LengthKeysKernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(d_offsets, n, keys, ids);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess)
+        err = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys_out, ids, d_order, (int) n, 0, 32, stream);
+    if (err == cudaSuccess) err = cudaMallocAsync(&temp, temp_bytes, stream);
+    if (err == cudaSuccess)
+        err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, ids, d_order, (int) n, 0, 32, stream);
+    if (keys) cudaFreeAsync(keys, stream);
+    if (keys_out) cudaFreeAsync(keys_out, stream);
+    if (ids) cudaFreeAsync(ids, stream);
+    if (temp) cudaFreeAsync(temp, stream);
+    return err;
+}
+
 cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream)
 {
     if (p.n_strings == 0)
@@ -756,6 +839,27 @@ cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_o
     uint64_t blocks = (total + 255) / 256;
     int grid = (int) (blocks < 148ull * 64 ? blocks : 148ull * 64);
     SynthKernel<<<grid, 256, 0, stream>>>(p, d_plants, d_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t LaunchSynthMixedLengths(uint64_t seed, uint64_t first, uint64_t n, uint64_t* d_lengths, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    SynthMixedLengthsKernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(seed, first, n, d_lengths);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t LaunchSynthMixedFill(uint64_t seed, uint32_t plant_every, uint64_t first, uint64_t n, const uint64_t* d_offsets,
+                                 uint8_t* d_out, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    uint64_t blocks = (n + 7) / 8;
+    SynthMixedFillKernel<<<(unsigned) (blocks < 148ull * 32 ? blocks : 148ull * 32), 256, 0, stream>>>(seed, plant_every, first, n,
+                                                                                                   d_offsets, d_out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

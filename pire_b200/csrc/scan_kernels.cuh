@@ -18,6 +18,8 @@ struct DeviceFin {
 struct ScanArgs {
     const uint8_t* corpus;
     const uint64_t* offsets;     // CSR (n+1) or nullptr
+    const uint32_t* order;       // generic kernel: lane i scans string order[i] (length-binned launch), or nullptr
+    unsigned int* work_counter;  // with `order`: units are claimed longest-first from this counter
     uint64_t fixed_len;          // used when offsets == nullptr
     uint64_t n;                  // strings
     const uint8_t* hot8;         // (hot+1)*256 bytes, 16-byte aligned
@@ -29,8 +31,8 @@ struct ScanArgs {
     uint32_t letters;
     uint32_t wide;               // full is u32
     uint32_t start;              // state after Initialize()[+Begin()], new numbering
-    uint32_t exit_bitmap0;       // slots 0..31 of the 64-slot exit bitmap of hot id 0 (slot = byte & 63)
-    uint32_t exit_bitmap0_hi;    // slots 32..63
+    uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = (byte >> exit_shift) & 31
+    uint32_t exit_shift;
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;
     uint32_t* match_bits;        // may be null
@@ -52,7 +54,13 @@ cudaError_t PrepareScanKernels(int device);                       // raises the 
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
+// d_order <- string indices sorted by descending length (CUB radix sort on the stream).
+cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream);
 cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream);
+
+cudaError_t LaunchSynthMixedLengths(uint64_t seed, uint64_t first, uint64_t n, uint64_t* d_lengths, cudaStream_t stream);
+cudaError_t LaunchSynthMixedFill(uint64_t seed, uint32_t plant_every, uint64_t first, uint64_t n, const uint64_t* d_offsets,
+                                 uint8_t* d_out, cudaStream_t stream);
 
 uint64_t KernelLaunchCount();
 

@@ -88,4 +88,59 @@ PIRE_HD uint8_t SynthByte(const SynthParams& p, const char* plant_bytes, uint64_
     return (uint8_t) (w >> (8 * (pos % 8)));
 }
 
+// ---- kind 1: mixed-length UTF-8 corpus (BASELINE config 4) --------------------
+// Lengths are log-uniform over octaves in [16, 65536), multiples of 4; every
+// 4-byte cell is one of: 4 printable ASCII bytes (11/16), two 2-byte Cyrillic
+// code points U+0410..U+044F (4/16), one 3-byte code point U+2000..U+2FFF plus
+// one ASCII byte (1/16) -- so any cell-aligned slice is valid UTF-8.  Every
+// plant_every-th string of at least 32 bytes ends with a mixed-case hit for the
+// case-insensitive headline pattern.
+
+PIRE_HD uint32_t SynthMixedLength(uint64_t seed, uint64_t string_index)
+{
+    uint64_t h = SynthMix(seed ^ SynthMix(string_index * 0xA24BAED4963EE407ull));
+    uint32_t k = (uint32_t) (h % 12u);
+    uint32_t frac = (uint32_t) (h >> 16) & 0xffffu;
+    uint32_t base = 16u << k;
+    uint32_t len = base + (uint32_t) (((uint64_t) base * frac) >> 16);
+    return len & ~3u;
+}
+
+
+PIRE_HD uint32_t SynthMixedCell(uint64_t seed, uint64_t string_index, uint32_t cell)
+{
+    uint64_t h = SynthMix(seed ^ SynthMix((string_index << 20) ^ cell ^ 0x5851F42D4C957F2Dull));
+    uint32_t kind = (uint32_t) (h & 15u);
+    uint32_t r = (uint32_t) (h >> 8);
+    uint32_t b[4];
+    if (kind < 11) {
+        for (int k = 0; k < 4; ++k)
+            b[k] = 0x20u + ((((r >> (8 * k)) & 0xffu) * 95u) >> 8);
+    } else if (kind < 15) {
+        for (int k = 0; k < 2; ++k) {
+            uint32_t cp = 0x410u + ((r >> (8 * k)) & 0x3fu);           // U+0410..U+044F
+            b[2 * k] = 0xC0u | (cp >> 6);
+            b[2 * k + 1] = 0x80u | (cp & 0x3fu);
+        }
+    } else {
+        uint32_t cp = 0x2000u + (r & 0xfffu);                            // U+2000..U+2FFF
+        b[0] = 0xE0u | (cp >> 12);
+        b[1] = 0x80u | ((cp >> 6) & 0x3fu);
+        b[2] = 0x80u | (cp & 0x3fu);
+        b[3] = 0x20u + ((((r >> 16) & 0xffu) * 95u) >> 8);
+    }
+    return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+}
+
+// Cell `cell` of string `string_index` whose length is `len`, plant applied.
+PIRE_HD uint32_t SynthMixedCellPlanted(uint64_t seed, uint32_t plant_every, uint64_t string_index, uint32_t len, uint32_t cell)
+{
+    if (plant_every && string_index % plant_every == 0 && len >= 32 && cell >= len / 4 - 4) {
+        // "HeLLo   WoRRRRLD" as four little-endian cells
+        const uint32_t plant[4] = {0x4C4C6548u /* HeLL */, 0x2020206Fu /* o    */, 0x52526F57u /* WoRR */, 0x444C5252u /* RRLD */};
+        return plant[cell - (len / 4 - 4)];
+    }
+    return SynthMixedCell(seed, string_index, cell);
+}
+
 } // namespace pire_b200

@@ -50,6 +50,20 @@ class Batch:
             if self.n * self.fixed_len > corpus.numel():
                 raise ValueError("corpus shorter than n * fixed_len")
         self.device = corpus.device
+        self.order = None          # set by bin_by_length()
+
+    def bin_by_length(self):
+        """Sort the strings by descending length (on the device) so that the lanes of a warp
+        scan strings of similar length; results stay indexed by the original string number."""
+        torch = _torch()
+        if self.offsets is None or self.n == 0:
+            return self
+        order = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(N.lib.pire_gpu_length_order(self.offsets.data_ptr(), self.n, order.data_ptr(), self.device.index or 0, stream),
+                "pire_gpu_length_order")
+        self.order = order
+        return self
 
     @classmethod
     def from_strings(cls, strings, device="cuda:0"):
@@ -164,6 +178,12 @@ class Scanner:
         if stream is None:
             stream = torch.cuda.current_stream(batch.device).cuda_stream
         ptr = lambda t: None if t is None else t.data_ptr()
+        if getattr(batch, "order", None) is not None:
+            N.check(N.lib.pire_gpu_run_batch_ordered(self._h, batch.corpus.data_ptr(), ptr(batch.offsets),
+                                                     batch.order.data_ptr(), batch.n, flags, ptr(match_bits),
+                                                     ptr(accept_masks), ptr(state_idx), stream),
+                    "pire_gpu_run_batch_ordered")
+            return
         N.check(N.lib.pire_gpu_run_batch(self._h, batch.corpus.data_ptr(), ptr(batch.offsets), batch.fixed_len,
                                          batch.n, flags, ptr(match_bits), ptr(accept_masks), ptr(state_idx), stream),
                 "pire_gpu_run_batch")

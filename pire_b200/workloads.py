@@ -113,6 +113,47 @@ class SynthSpec:
         return SynthSpec(hi - lo, self.string_len, self.seed, self.plant_every, self.plants, self.first_string + lo), lo
 
 
+class MixedSpec:
+    """BASELINE config 4: mixed-length (16 B .. 64 KiB) UTF-8 strings, CSR offsets."""
+
+    def __init__(self, n_strings, seed=42, plant_every=8, first_string=0):
+        self.n_strings, self.seed, self.plant_every, self.first_string = int(n_strings), int(seed), int(plant_every), int(first_string)
+
+    def device_batch(self, device):
+        """(corpus uint8, offsets int64) CUDA tensors, generated on the device."""
+        import torch
+        dev = torch.device(device)
+        idx = dev.index or 0
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lengths = torch.empty(self.n_strings, dtype=torch.int64, device=dev)
+        N.check(N.lib.pire_gpu_synth_mixed_lengths_device(self.seed, self.first_string, self.n_strings, lengths.data_ptr(), idx, stream),
+                "pire_gpu_synth_mixed_lengths_device")
+        offsets = torch.zeros(self.n_strings + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lengths, 0, out=offsets[1:])
+        total = int(offsets[-1].item())
+        corpus = torch.empty(total + 32, dtype=torch.uint8, device=dev)
+        N.check(N.lib.pire_gpu_synth_mixed_fill_device(self.seed, self.plant_every, self.first_string, self.n_strings,
+                                                       offsets.data_ptr(), corpus.data_ptr(), idx, stream),
+                "pire_gpu_synth_mixed_fill_device")
+        return corpus, offsets
+
+    def host_batch(self, first, count):
+        """Strings [first, first+count) on the host: (corpus uint8, offsets uint64[count+1])."""
+        lengths = np.zeros(count, np.uint64)
+        N.check(N.lib.pire_gpu_synth_mixed_lengths_host(self.seed, self.first_string + first, count, lengths.ctypes.data),
+                "pire_gpu_synth_mixed_lengths_host")
+        offsets = np.zeros(count + 1, np.uint64)
+        np.cumsum(lengths, out=offsets[1:])
+        corpus = np.zeros(int(offsets[-1]) + 32, np.uint8)
+        N.check(N.lib.pire_gpu_synth_mixed_fill_host(self.seed, self.plant_every, self.first_string + first, count,
+                                                     offsets.ctypes.data, corpus.ctypes.data),
+                "pire_gpu_synth_mixed_fill_host")
+        return corpus, offsets
+
+
+HEADLINE_IU = (rb"hello\s+w.+d$", "iu")      # README:35-47: CaseInsensitive + UTF-8
+
+
 def load_image(name):
     """Scanner::Save() image of a BASELINE pattern set ('headline' or 'glue10'),
     precompiled by tools/compile_patterns.py with the reference's front end."""
@@ -127,4 +168,5 @@ WORKLOADS = {
     # name: (image, plants, description, BASELINE.json config index)
     "headline": ("headline", HEADLINE_PLANTS, r"single regex hello\s+w.+d$ (NonrelocScanner DFA: 11 states)", 1),
     "glue10": ("glue10", GLUE10_PLANTS, "10 regexes glued into one multi-Scanner (29664 states x 54 letters)", 2),
+    "utf8mixed": ("headline_iu", None, r"hello\s+w.+d$ with UTF-8 + CaseInsensitive, mixed-length (16 B-64 KiB) UTF-8 strings", 3),
 }

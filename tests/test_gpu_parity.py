@@ -288,3 +288,58 @@ def test_full_size_properties(cuda_device, ref):
         sub = P.Batch(dev[lo * 1024: hi * 1024], fixed_len=1024, n=hi - lo)
         parts.append(P.Runner(sc).Begin().Run(sub).End().MatchBits().cpu().numpy())
     assert (np.concatenate(parts) == whole).all()
+
+
+def test_length_binned_launch_mixed_utf8(cuda_device, ref):
+    """BASELINE config 4 through the length-binned (ordered) launch: device- and host-generated
+    corpora agree; match bits / masks / StateIndex, indexed by ORIGINAL string number, are
+    bit-exact against the reference, with and without binning."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    sc_ref = ref.compile(*W.HEADLINE_IU)
+    sc = P.Scanner(W.load_image("headline_iu"), cuda_device)
+    assert sc.Size() == sc_ref.size
+    n = 6000
+    spec = W.MixedSpec(n)
+    corpus, offsets = spec.device_batch("cuda:0")
+    h_corpus, h_offsets = spec.host_batch(0, n)
+    assert (offsets.cpu().numpy().astype(np.uint64) == h_offsets).all()
+    assert (corpus.cpu().numpy()[: int(h_offsets[-1])] == h_corpus[: int(h_offsets[-1])]).all()
+    f_ref, m_ref, s_ref = sc_ref.run(h_corpus, h_offsets, variant=1, threads=8)
+    assert int(f_ref.sum()) >= n // 8 * 0.9
+    for binned in (False, True):
+        batch = P.Batch(corpus, offsets, n=n)
+        if binned:
+            batch.bin_by_length()
+            order = batch.order.cpu().numpy()
+            lens = np.diff(h_offsets.astype(np.int64))
+            assert sorted(order.tolist()) == list(range(n)) and (np.diff(lens[order]) <= 0).all()
+        for variant in (1, 2):
+            sc.set_variant(variant)
+            r = P.Runner(sc).Begin().Run(batch).End()
+            assert (r.Matches().astype(np.uint8) == f_ref).all(), (binned, variant)
+            assert (r.AcceptMasks() == m_ref).all() and (r.States() == s_ref).all(), (binned, variant)
+    # the host-buffer entry point bins CSR batches itself
+    bits, masks, states = sc.run_batch_host(h_corpus, offsets=h_offsets, want_masks=True, want_states=True)
+    assert (np.unpackbits(bits.view(np.uint8), bitorder="little")[:n] == f_ref).all() and (states == s_ref).all()
+
+
+def test_autoselect_keeps_results(cuda_device, ref):
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    sc_ref = ref.glue_all(W.GLUE10)
+    sc = P.Scanner(W.load_image("glue10"), cuda_device)
+    n = 32768
+    spec = W.SynthSpec(n, 1024, plants=W.GLUE10_PLANTS)
+    dev = torch.empty(spec.total_bytes(), dtype=torch.uint8, device="cuda:0")
+    spec.fill_device(dev)
+    batch = P.Batch(dev, fixed_len=1024, n=n)
+    sc.Tune(batch, 4096)
+    ms = sc.AutoSelect(batch)
+    assert set(ms) >= {"plain", "pred"} and all(v > 0 for v in ms.values())
+    assert sc.info().variant in (1, 2, 3)
+    r = P.Runner(sc).Begin().Run(batch).End()
+    f_ref, m_ref, _ = sc_ref.run(spec.host_sample(0, n), fixed_len=1024, n=n, variant=1, threads=8)
+    assert (r.Matches().astype(np.uint8) == f_ref).all() and (r.AcceptMasks() == m_ref).all()

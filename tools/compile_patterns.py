@@ -27,7 +27,7 @@ def main():
     ref = Ref()
     out = os.path.join(ROOT, "pire_b200", "data")
     os.makedirs(out, exist_ok=True)
-    for name, pats in (("headline", [ns["HEADLINE"]]), ("glue10", ns["GLUE10"])):
+    for name, pats in (("headline", [ns["HEADLINE"]]), ("glue10", ns["GLUE10"]), ("headline_iu", [ns["HEADLINE_IU"]])):
         sc = ref.glue_all(pats)
         img = sc.save()
         path = os.path.join(out, name + ".pire.xz")

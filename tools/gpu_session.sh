@@ -35,6 +35,7 @@ except Exception as e:
 PY
     done
   done
+  timeout 900 python bench.py --workload utf8mixed --no-cpu > $OUT/bench_utf8mixed.json 2> $OUT/bench_utf8mixed.err; cat $OUT/bench_utf8mixed.json; tail -3 $OUT/bench_utf8mixed.err
   timeout 900 python bench.py > $OUT/bench_default.json 2> $OUT/bench_default.err; cat $OUT/bench_default.json
   timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json
   ;;
