@@ -423,6 +423,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
         const bool valid = slot < a.n;
         const uint64_t i = valid && a.order ? a.order[slot] : slot;
         uint64_t b = 0, e = 0;
+        if (valid) {
+            if (a.offsets) {
+                b = a.offsets[i];
+                e = a.offsets[i + 1];
+            } else {
+                b = i * a.fixed_len;
+                e = b + a.fixed_len;
+            }
+        }
         const uint8_t* p = a.corpus + b;
         const uint8_t* end = a.corpus + e;
 
