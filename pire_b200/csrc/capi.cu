@@ -180,7 +180,6 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->wide = t.wide ? 1 : 0;
     a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
     a->exit_bitmap0 = t.exit_bitmap0;
-    a->exit_shift = t.exit_shift;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
 }

@@ -112,27 +112,11 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
         t.noexit[h] = stays ? 1 : 0;    // same predicate as BuildShortcuts' NoExit, multi.h:477-514
     }
 
-    // 32-slot filter of the kPred variant: slot = (byte >> shift) & 31.  Pick the shift
-    // under which the fewest bytes alias an exit byte of hot id 0 (printable ASCII counts
-    // four-fold: it is what text corpora are made of).
-    {
-        uint64_t best_cost = ~0ull;
-        for (uint32_t shift = 0; shift < 4; ++shift) {
-            uint32_t bm = 0;
-            for (uint32_t b = 0; b < 256; ++b)
-                if (t.hot8[b] != 0)
-                    bm |= 1u << ((b >> shift) & 31);
-            uint64_t cost = 0;
-            for (uint32_t b = 0; b < 256; ++b)
-                if ((bm >> ((b >> shift) & 31)) & 1)
-                    cost += (b >= 0x20 && b < 0x7f) ? 4 : 1;
-            if (cost < best_cost) {
-                best_cost = cost;
-                t.exit_bitmap0 = bm;
-                t.exit_shift = shift;
-            }
-        }
-    }
+    // 32-slot filter of the kPred variant: slot = byte & 31.
+    t.exit_bitmap0 = 0;
+    for (uint32_t b = 0; b < 256; ++b)
+        if (t.hot8[b] != 0)
+            t.exit_bitmap0 |= 1u << (b & 31);
 
     // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,
     // the last id being the sink.

@@ -51,8 +51,7 @@ struct ScanTables {
     std::vector<uint32_t> full32;
     std::vector<FinEntry> fin[2];            // [with_end][new id]
     uint32_t start[2] = {0, 0};              // [with_begin] -> new id
-    uint32_t exit_bitmap0 = ~0u;             // bit ((b >> exit_shift) & 31) set if byte b may leave hot id 0
-    uint32_t exit_shift = 0;                 // chosen to let the fewest bytes through (kPred filter)
+    uint32_t exit_bitmap0 = ~0u;             // bit (b & 31) set if byte b may leave hot id 0 (kPred filter)
 
     // Lane-private rows (kernel variant PRIV): the first priv_rows-1 hot ids, plus a sink
     // row (id priv_rows-1) that absorbs every transition into a non-private state.  Only

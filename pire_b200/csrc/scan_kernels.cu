@@ -166,7 +166,7 @@ struct Tables {
     uint32_t H;
     uint32_t letters;
     uint32_t wide;
-    uint32_t m0, mshift;      // 32-slot exit bitmap of hot id 0, slot = (byte >> mshift) & 31
+    uint32_t m0;              // 32-slot exit bitmap of hot id 0, slot = byte & 31
 };
 
 // One byte through the complete table (hot rows first: they are in shared memory).
@@ -205,18 +205,18 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
     // idx = (g << 8) | byte_k(w): byte address of the fused row entry.
     uint32_t idx = __byte_perm(w, g, sel);
     if (kPred) {
-        // bit ((byte >> mshift) & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
+        // bit (byte & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
         // Lanes resting in id 0 on a self-looping byte skip the load (fewer bank
         // conflicts).  Spelled in PTX so that it stays SHF, LOP3 -> predicate,
-        // @p LDS.  (A 64-slot bitmap probed with SHF.R.U64 passes fewer lanes --
-        // 2.12 vs 2.23 modelled wavefronts -- but measured 8 % slower: the extra
-        // ALU-pipe instructions, issued at half rate, become the bound; r01 log.)
+        // @p LDS.  (Sharper filters -- a 64-slot bitmap probed with SHF.R.U64, or a
+        // slot of (byte >> 2) & 31 -- pass fewer lanes (2.12 / 2.14 vs 2.23 modelled
+        // wavefronts) but measured 8 % slower: a fourth ALU-pipe instruction per byte,
+        // issued at half rate, becomes the bound; DESIGN.md results log.)
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
             ".reg .b32 probe, addr;\n"
-            "shr.u32 probe, %1, %3;\n"
-            "shf.r.wrap.b32 probe, %2, 0, probe;\n"
+            "shf.r.wrap.b32 probe, %2, 0, %1;\n"
             "and.b32 probe, probe, 1;\n"
             "or.b32 probe, probe, %0;\n"
             "setp.ne.u32 p, probe, 0;\n"
@@ -225,7 +225,7 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
             "@p ld.shared.u8 %0, [addr];\n"
             "}\n"
             : "+r"(g)
-            : "r"(idx), "r"(t.m0), "r"(t.mshift));
+            : "r"(idx), "r"(t.m0));
     } else {
         g = t.hot[idx];
     }
@@ -255,7 +255,6 @@ __device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t*
     t.letters = letters_wide & 0x7fffffffu;
     t.wide = letters_wide >> 31;
     t.m0 = 0;
-    t.mshift = 0;
     uint32_t s = from;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -338,7 +337,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.exit_bitmap0;
-    t.mshift = a.exit_shift;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
@@ -402,7 +400,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.exit_bitmap0;
-    t.mshift = a.exit_shift;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
@@ -489,33 +486,20 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
 // are replicated into all 32 banks: lane l reads only bank l, so every load is one
 // wavefront whatever the states and bytes are.  Layout (byte address inside the
 // private region):   [19:14] quad q   [13:7] byte b (< 128)   [6:2] lane   [1:0] row-in-quad s
-// A lane's state is S = (q << 14) | (lane << 2) | s; one step is
-//     e = LDS.U8 [priv + S + (b << 7)];   S = ((e * 0x1001) & 0xFC003) | (lane << 2)
-// (e = 4q' + s'; the multiply drops s' into bits 1:0 and q' into bits 19:14).  Rows
-// that are not private map to the sink row; a lane found in the sink after a 4-byte
-// word (or a word holding a byte >= 128) re-walks that word through the shared
-// hot rows / the complete table and re-enters a private row when it can.
+// A lane's state is its private row id e = 4q + s; one step is
+//     e = LDS.U8 [priv + (((e * 0x1001) & 0xFC003) | (b << 7) | (lane << 2))]
+// (the multiply drops s into bits 1:0 and q into bits 19:14; the other fields are
+// disjoint, so one LOP3 assembles the address).  Rows that are not private map to the
+// sink row; a lane found in the sink after a 4-byte word (or a word holding a byte
+// >= 128) re-walks that word through the shared hot rows / the complete table and
+// re-enters a private row when it can.
 
 constexpr int kPrivBlock = 1024;
 constexpr uint32_t kPrivMask = 0x000FC003u;
 
-struct PrivLane {
-    uint32_t S;         // private row address (relative to the private region) or the lane's sink
-    uint32_t other;     // complete state while S == sink
-};
-
-__device__ __forceinline__ uint32_t PrivAddrOf(uint32_t id, uint32_t lane4) { return ((id >> 2) << 14) | lane4 | (id & 3u); }
-__device__ __forceinline__ uint32_t PrivIdOf(uint32_t S) { return ((S >> 14) << 2) | (S & 3u); }
-
-__device__ __forceinline__ void PrivStep(const uint8_t* priv, uint32_t& S, uint32_t b, uint32_t lane4)
-{
-    uint32_t e = priv[S + (b << 7)];
-    S = ((e * 0x1001u) & kPrivMask) | lane4;
-}
-
-// Re-walk of one word for a lane that is (or fell) outside the private rows.
-__device__ __noinline__ uint2 PrivSlowWord(const uint8_t* hot, const uint16_t* cls, const void* full, uint32_t H,
-                                           uint32_t letters_wide, uint32_t real_rows, uint32_t state, uint32_t w)
+// Re-walk of one word through the complete table, for a lane that left even the shared hot rows.
+__device__ __noinline__ uint32_t PrivColdWord(const uint8_t* hot, const uint16_t* cls, const void* full, uint32_t H,
+                                              uint32_t letters_wide, uint32_t state, uint32_t w)
 {
     Tables t;
     t.hot_saddr = 0;
@@ -526,33 +510,53 @@ __device__ __noinline__ uint2 PrivSlowWord(const uint8_t* hot, const uint16_t* c
     t.letters = letters_wide & 0x7fffffffu;
     t.wide = letters_wide >> 31;
     t.m0 = 0;
-    t.mshift = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         state = SlowStep(t, state, (w >> (8 * k)) & 0xffu);
-    return make_uint2(state, state < real_rows ? 1u : 0u);
+    return state;
 }
 
-__device__ __forceinline__ void PrivWord(const ScanArgs& a, const SharedView& sv, PrivLane& s, uint32_t w, uint32_t lane4,
-                                         uint32_t sink, uint32_t real_rows)
+// Four input bytes.  `e` is the lane's private row id (sink = not in a private row, the
+// complete state then lives in `other`).  One step costs two ALU-pipe instructions (PRMT,
+// LOP3), two FMA-pipe ones (IMAD, IMAD) and one conflict-free LDS.
+__device__ __forceinline__ uint32_t LoadSharedU8(uint32_t shared_addr)
 {
-    const uint32_t before = s.S;
-    uint32_t S = s.S;
-    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4440), lane4);
-    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4441), lane4);
-    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4442), lane4);
-    PrivStep(sv.priv, S, __byte_perm(w, 0, 0x4443), lane4);
-    if (S == sink || (w & 0x80808080u) != 0) {
-        uint32_t from = before == sink ? s.other : PrivIdOf(before);
-        uint2 r = PrivSlowWord(sv.hot, sv.cls, a.full, a.hot, a.letters | (a.wide << 31), real_rows, from, w);
-        if (r.y) {
-            S = PrivAddrOf(r.x, lane4);
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+
+__device__ __forceinline__ void PrivWord(const Tables& t, uint32_t& e, uint32_t& other, uint32_t w, uint32_t lane_base,
+                                         uint32_t sink_id, uint32_t real_rows)
+{
+    const uint32_t before = e;
+    // lane_base = shared-window address of the private region + lane * 4.  The byte term
+    // and the final add go to the FMA pipe (IMAD), leaving PRMT and LOP3 on the ALU pipe.
+    const uint32_t k0 = __byte_perm(w, 0, 0x4440) * 128u + lane_base;
+    const uint32_t k1 = __byte_perm(w, 0, 0x4441) * 128u + lane_base;
+    const uint32_t k2 = __byte_perm(w, 0, 0x4442) * 128u + lane_base;
+    const uint32_t k3 = __umulhi(w, 256u) * 128u + lane_base;           // w >> 24 without the ALU pipe
+    e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k0);
+    e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k1);
+    e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k2);
+    e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k3);
+    if (e == sink_id || (w & 0x80808080u) != 0) {
+        // left the private rows (or a byte >= 128): re-walk the word through the shared hot
+        // rows, PRMT + LDS per byte as in the plain kernel; the complete table only if that
+        // fails too
+        const uint32_t from = before == sink_id ? other : before;
+        uint32_t g = from < t.H ? from : t.H;
+        FastWord<false>(t, g, w);
+        uint32_t full = g;
+        if (g == t.H)
+            full = PrivColdWord(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, w);
+        if (full < real_rows) {
+            e = full;
         } else {
-            S = sink;
-            s.other = r.x;
+            e = sink_id;
+            other = full;
         }
     }
-    s.S = S;
 }
 
 __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __grid_constant__ ScanArgs a)
@@ -569,10 +573,20 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
         __syncthreads();
     }
 
+    Tables t;
+    t.hot_saddr = SmemAddr(sv.hot);
+    t.hot = sv.hot;
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = 0;
+
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lane4 = lane << 2;
+    const uint32_t lane_base = SmemAddr(sv.priv) + (lane << 2);
     const uint32_t real_rows = a.priv_rows - 1 < a.hot ? a.priv_rows - 1 : a.hot;
-    const uint32_t sink = PrivAddrOf(a.priv_rows - 1, lane4);
+    const uint32_t sink_id = a.priv_rows - 1;
     const uint64_t units = (a.n + 31) / 32;
     const uint64_t warps = (uint64_t) gridDim.x * (kPrivBlock / 32);
     const uint32_t len = (uint32_t) a.fixed_len;
@@ -582,9 +596,8 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
         const bool valid = i < a.n;
         const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
 
-        PrivLane s;
-        s.other = a.start;
-        s.S = a.start < real_rows ? PrivAddrOf(a.start, lane4) : sink;
+        uint32_t other = a.start;
+        uint32_t e = a.start < real_rows ? a.start : sink_id;
 
         uint4 c0, c1, d0, d1;
         LoadStream32(p, c0, c1);
@@ -593,37 +606,35 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
             const bool more_d = off < len;
             if (more_d)
                 LoadStream32(p + off, d0, d1);
-            PrivWord(a, sv, s, c0.x, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c0.y, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c0.z, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c0.w, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c1.x, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c1.y, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c1.z, lane4, sink, real_rows);
-            PrivWord(a, sv, s, c1.w, lane4, sink, real_rows);
+            PrivWord(t, e, other, c0.x, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c0.y, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c0.z, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c0.w, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c1.x, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c1.y, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c1.z, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, c1.w, lane_base, sink_id, real_rows);
             if (!more_d)
                 break;
             off += 32;
             const bool more_c = off < len;
             if (more_c)
                 LoadStream32(p + off, c0, c1);
-            PrivWord(a, sv, s, d0.x, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d0.y, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d0.z, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d0.w, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d1.x, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d1.y, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d1.z, lane4, sink, real_rows);
-            PrivWord(a, sv, s, d1.w, lane4, sink, real_rows);
+            PrivWord(t, e, other, d0.x, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d0.y, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d0.z, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d0.w, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d1.x, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d1.y, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d1.z, lane_base, sink_id, real_rows);
+            PrivWord(t, e, other, d1.w, lane_base, sink_id, real_rows);
             if (!more_c)
                 break;
         }
 
-        Tables t;
-        t.H = a.hot;
         LaneState fs;
         fs.g = a.hot;
-        fs.cold = s.S == sink ? s.other : PrivIdOf(s.S);
+        fs.cold = e == sink_id ? other : e;
         Report(a, t, fs, unit, i, valid);
     }
 }

@@ -31,8 +31,7 @@ struct ScanArgs {
     uint32_t letters;
     uint32_t wide;               // full is u32
     uint32_t start;              // state after Initialize()[+Begin()], new numbering
-    uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = (byte >> exit_shift) & 31
-    uint32_t exit_shift;
+    uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;
     uint32_t* match_bits;        // may be null

@@ -114,8 +114,8 @@ int main(int argc, char** argv)
                 if (b >= 0x20 && b < 0x7f)
                     ex += (char) b;
             }
-        std::printf("hot id 0 = state %u: %d exit bytes [%s], bitmap %08x shift %u (%d slots)\n", s0, exits, ex.c_str(),
-                    t.exit_bitmap0, t.exit_shift, __builtin_popcount(t.exit_bitmap0));
+        std::printf("hot id 0 = state %u: %d exit bytes [%s], bitmap %08x (%d slots)\n", s0, exits, ex.c_str(),
+                    t.exit_bitmap0, __builtin_popcount(t.exit_bitmap0));
     }
 
     // Private-row model: P most visited rows are lane-private (never conflict); a lane that

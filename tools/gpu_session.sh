@@ -46,6 +46,14 @@ ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniform -s 3 -c 1 -f -o $OUT/prof_glue10_$v \
         python bench.py --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant $v > $OUT/ncu_full_$v.log 2>&1
   done
+  if [ -n "${NCU_MIXED:-}" ]; then
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanGeneric -s 4 -c 1 -f -o $OUT/prof_utf8mixed \
+        python bench.py --workload utf8mixed --strings 320000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant plain > $OUT/ncu_full_mixed.log 2>&1
+  fi
+  if [ -n "${NCU_HEADLINE:-}" ]; then
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniform -s 3 -c 1 -f -o $OUT/prof_headline_plain \
+        python bench.py --workload headline --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant plain > $OUT/ncu_full_headline.log 2>&1
+  fi
   ls -la $OUT/*.ncu-rep
   ;;
 esac
