@@ -52,6 +52,7 @@ struct DeviceTables {
     void* full = nullptr;
     DeviceFin* fin[2] = {nullptr, nullptr};
     uint32_t* priv_packed = nullptr;
+    uint8_t* hot8_small = nullptr;
     size_t full_bytes = 0;
 
     void Free()
@@ -63,6 +64,7 @@ struct DeviceTables {
         cudaFree(fin[0]);
         cudaFree(fin[1]);
         cudaFree(priv_packed);
+        cudaFree(hot8_small);
         *this = DeviceTables();
     }
 };
@@ -134,10 +136,12 @@ int Upload(pire_gpu_scanner* sc)
     }
     CUDA_TRY(cudaMalloc(&d.priv_packed, t.priv_packed.size() * 4));
     CUDA_TRY(cudaMemcpy(d.priv_packed, t.priv_packed.data(), t.priv_packed.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.hot8_small, t.hot8_small.size()));
+    CUDA_TRY(cudaMemcpy(d.hot8_small, t.hot8_small.data(), t.hot8_small.size(), cudaMemcpyHostToDevice));
     sc->priv_ok = false;
     for (int v = kVariantPlain; v <= kVariantPriv; ++v)
         for (int u = 0; u < 2; ++u) {
-            cudaError_t pe = PlanScan(sc->device, t.hot, t.priv_rows, v, u != 0, &sc->plan[v][u]);
+            cudaError_t pe = PlanScan(sc->device, t.hot, t.hot_small, t.priv_rows, v, u != 0, &sc->plan[v][u]);
             if (v == kVariantPriv && u == 1) {
                 sc->priv_ok = pe == cudaSuccess;     // needs ~225 KB of shared memory per CTA
                 if (pe != cudaSuccess)
@@ -182,6 +186,8 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->exit_bitmap0 = t.exit_bitmap0;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
+    a->hot8_small = sc->dev.hot8_small;
+    a->hot_small = t.hot_small;
 }
 
 int CheckRunnable(const pire_gpu_scanner* sc)
@@ -268,7 +274,8 @@ int pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out)
     out->variant = ResolveVariant(sc);
     out->tuned = sc->tuned ? 1 : 0;
     out->table_bytes = sc->tab.wide ? sc->tab.full32.size() * 4 : sc->tab.full16.size() * 2;
-    out->shared_bytes = ScanSharedBytes(sc->tab.hot, ResolveVariant(sc) == PIRE_GPU_VARIANT_PRIV ? sc->tab.priv_rows : 0);
+    out->shared_bytes = ResolveVariant(sc) == PIRE_GPU_VARIANT_PRIV ? ScanSharedBytes(sc->tab.hot_small, sc->tab.priv_rows)
+                                                                    : ScanSharedBytes(sc->tab.hot, 0);
     out->device = sc->device;
     return PIRE_GPU_OK;
 }

@@ -139,6 +139,17 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
             }
     }
 
+    {
+        const uint32_t Hs = std::min<uint32_t>(H, kPrivHotRows);
+        t.hot_small = Hs;
+        t.hot8_small.assign((size_t) (Hs + 1) * 256, (uint8_t) Hs);
+        for (uint32_t h = 0; h < Hs; ++h)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint32_t to = t.hot8[(size_t) h * 256 + b];
+                t.hot8_small[(size_t) h * 256 + b] = (uint8_t) (to < Hs ? to : Hs);
+            }
+    }
+
     // What a string that stops in state s reports.
     for (int with_end = 0; with_end < 2; ++with_end) {
         t.fin[with_end].resize(dfa.states);

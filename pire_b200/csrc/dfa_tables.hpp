@@ -33,7 +33,8 @@
 namespace pire_b200 {
 
 constexpr uint32_t kMaxHot = 255;
-constexpr uint32_t kMaxPrivRows = 40;     // lane-private rows incl. the sink (10 quads x 16 KB of shared memory)
+constexpr uint32_t kMaxPrivRows = 48;     // lane-private rows incl. the sink (12 quads x 16 KB of shared memory)
+constexpr uint32_t kPrivHotRows = 135;    // shared second-tier rows that still fit beside them
 
 struct FinEntry {
     uint32_t result;   // bit31 = Final(), bits 0..30 = StateIndex() in the reference's numbering
@@ -60,6 +61,10 @@ struct ScanTables {
     // lane l only ever touches bank l: one wavefront per load, no conflicts by construction.
     uint32_t priv_rows = 0;                  // multiple of 4
     std::vector<uint32_t> priv_packed;       // (priv_rows / 4) * 128
+    // The PRIV kernel's second tier: the same fused rows as hot8, cut to the first
+    // hot_small ids (what fits in shared memory next to the private region).
+    uint32_t hot_small = 0;
+    std::vector<uint8_t> hot8_small;         // (hot_small + 1) * 256
 };
 
 // Default hot order: breadth-first from the start states (states near the start

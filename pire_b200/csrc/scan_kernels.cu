@@ -29,6 +29,7 @@
 #include "scan_kernels.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -44,6 +45,10 @@ namespace {
 
 constexpr int kBlock = 512;
 constexpr int kMinBlocksPerSM = 3;
+// The generic kernel keeps 64 + 64 bytes of input per lane in registers and runs at two
+// CTAs per SM: ragged batches are bound by the latency of their longest strings (one
+// dependent LDS chain per string), which fewer co-resident warps shorten.
+constexpr int kGenericBlocksPerSM = 2;
 constexpr int kWarpsPerBlock = kBlock / 32;
 
 std::atomic<uint64_t> g_launches{0};
@@ -132,9 +137,9 @@ __device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot, u
 }
 
 // Stage the tables: hot rows by TMA bulk copy, the two small tables by plain loads.
-__device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView& sv)
+__device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView& sv, const uint8_t* hot8, uint32_t hot)
 {
-    const uint32_t total = (uint32_t) HotBytes(a.hot);
+    const uint32_t total = (uint32_t) HotBytes(hot);
     if (threadIdx.x == 0) {
         MbarInit(sv.bar, 1);
         FenceBarrierInit();
@@ -145,12 +150,12 @@ __device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView&
         constexpr uint32_t kPiece = 16384;
         for (uint32_t off = 0; off < total; off += kPiece) {
             uint32_t n = total - off < kPiece ? total - off : kPiece;
-            BulkCopyG2S(sv.hot + off, a.hot8 + off, n, sv.bar);
+            BulkCopyG2S(sv.hot + off, hot8 + off, n, sv.bar);
         }
     }
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         sv.cls[i] = a.cls[i];
-        sv.noexit[i] = i <= a.hot ? a.noexit[i] : 0;
+        sv.noexit[i] = i <= hot ? a.noexit[i] : 0;
     }
     MbarWait(sv.bar, 0);
     __syncthreads();
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
-    StageTables(a, sv);
+    StageTables(a, sv, a.hot8, a.hot);
 
     Tables t;
     t.hot_saddr = SmemAddr(sv.hot);
@@ -385,11 +390,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 // tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
 // with its word-aligned body.
 template <bool kPred>
-__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
-    StageTables(a, sv);
+    StageTables(a, sv, a.hot8, a.hot);
 
     Tables t;
     t.hot_saddr = SmemAddr(sv.hot);
@@ -442,26 +447,37 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
                 full = SlowStep(t, full, *p++);
             SetFull(t, s, full);
         }
-        // body: 16-byte chunks, prefetched one ahead; the warp iterates until its
-        // longest lane is done, shorter lanes idle (length binning is the caller's job).
+        // body: 64 bytes (four 16-byte chunks) per iteration, the next 64 bytes in flight
+        // while these are walked; the warp iterates until its longest lane is done, shorter
+        // lanes idle (length binning keeps them few).
         const uint32_t chunks = (uint32_t) ((end - p) >> 4);
         bool parked = false;       // lane sits in a NoExit state: its remaining bytes are irrelevant
-        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-        if (chunks > 0)
-            cur = LoadStream16(p);
-        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); ++k) {
-            const bool live = k < chunks;
-            if (k + 1 < chunks)
-                nxt = LoadStream16(p + 16 * (size_t) (k + 1));
-            if (live)
-                Chunk16<kPred>(t, s, cur);
-            cur = nxt;
+        uint4 cur[4], nxt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cur[j] = make_uint4(0, 0, 0, 0);
+            nxt[j] = make_uint4(0, 0, 0, 0);
+            if ((uint32_t) j < chunks)
+                cur[j] = LoadStream16(p + 16 * j);
+        }
+        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + 4 + j < chunks)
+                    nxt[j] = LoadStream16(p + 16 * (size_t) (k + 4 + j));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + j < chunks)
+                    Chunk16<kPred>(t, s, cur[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                cur[j] = nxt[j];
             // multi.h:955-958,:979-982: a NoExit state cannot be left by any byte.
+            const bool live = k + 4 < chunks;
             const bool stuck = sv.noexit[s.g] != 0;
             if (__all_sync(0xffffffffu, !live || stuck)) {
                 parked = live && stuck;
-                if (__all_sync(0xffffffffu, k + 1 >= chunks || parked))
-                    break;
+                break;
             }
         }
         // tail
@@ -497,28 +513,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanGenericKernel(con
 constexpr int kPrivBlock = 1024;
 constexpr uint32_t kPrivMask = 0x000FC003u;
 
-// Re-walk of one word through the complete table, for a lane that left even the shared hot rows.
-__device__ __noinline__ uint32_t PrivColdWord(const uint8_t* hot, const uint16_t* cls, const void* full, uint32_t H,
-                                              uint32_t letters_wide, uint32_t state, uint32_t w)
-{
-    Tables t;
-    t.hot_saddr = 0;
-    t.hot = hot;
-    t.cls = cls;
-    t.full = full;
-    t.H = H;
-    t.letters = letters_wide & 0x7fffffffu;
-    t.wide = letters_wide >> 31;
-    t.m0 = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        state = SlowStep(t, state, (w >> (8 * k)) & 0xffu);
-    return state;
-}
-
-// Four input bytes.  `e` is the lane's private row id (sink = not in a private row, the
-// complete state then lives in `other`).  One step costs two ALU-pipe instructions (PRMT,
-// LOP3), two FMA-pipe ones (IMAD, IMAD) and one conflict-free LDS.
 __device__ __forceinline__ uint32_t LoadSharedU8(uint32_t shared_addr)
 {
     uint32_t v;
@@ -526,12 +520,11 @@ __device__ __forceinline__ uint32_t LoadSharedU8(uint32_t shared_addr)
     return v;
 }
 
-__device__ __forceinline__ void PrivWord(const Tables& t, uint32_t& e, uint32_t& other, uint32_t w, uint32_t lane_base,
-                                         uint32_t sink_id, uint32_t real_rows)
+// Four steps.  `e` is the lane's private row id.  One step costs two ALU-pipe
+// instructions (PRMT, LOP3), three FMA-pipe ones (IMAD x3) and one conflict-free LDS.
+// lane_base = shared-window address of the private region + lane * 4.
+__device__ __forceinline__ void PrivWord(uint32_t& e, uint32_t w, uint32_t lane_base)
 {
-    const uint32_t before = e;
-    // lane_base = shared-window address of the private region + lane * 4.  The byte term
-    // and the final add go to the FMA pipe (IMAD), leaving PRMT and LOP3 on the ALU pipe.
     const uint32_t k0 = __byte_perm(w, 0, 0x4440) * 128u + lane_base;
     const uint32_t k1 = __byte_perm(w, 0, 0x4441) * 128u + lane_base;
     const uint32_t k2 = __byte_perm(w, 0, 0x4442) * 128u + lane_base;
@@ -540,16 +533,30 @@ __device__ __forceinline__ void PrivWord(const Tables& t, uint32_t& e, uint32_t&
     e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k1);
     e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k2);
     e = LoadSharedU8(((e * 0x1001u) & kPrivMask) + k3);
-    if (e == sink_id || (w & 0x80808080u) != 0) {
-        // left the private rows (or a byte >= 128): re-walk the word through the shared hot
-        // rows, PRMT + LDS per byte as in the plain kernel; the complete table only if that
-        // fails too
+}
+
+// Sixteen input bytes.  The sink row is absorbing, so one test per chunk finds every lane
+// that left the private rows (or met a byte >= 128, which the private rows do not cover);
+// such a lane re-walks the chunk through the shared hot rows (PRMT + LDS per byte, as in the
+// plain kernel) and through the complete table only if that fails too.
+__device__ __forceinline__ void PrivChunk(const Tables& t, uint32_t& e, uint32_t& other, uint4 v, uint32_t lane_base,
+                                          uint32_t sink_id, uint32_t real_rows)
+{
+    const uint32_t before = e;
+    PrivWord(e, v.x, lane_base);
+    PrivWord(e, v.y, lane_base);
+    PrivWord(e, v.z, lane_base);
+    PrivWord(e, v.w, lane_base);
+    if (e == sink_id || ((v.x | v.y | v.z | v.w) & 0x80808080u) != 0) {
         const uint32_t from = before == sink_id ? other : before;
         uint32_t g = from < t.H ? from : t.H;
-        FastWord<false>(t, g, w);
+        FastWord<false>(t, g, v.x);
+        FastWord<false>(t, g, v.y);
+        FastWord<false>(t, g, v.z);
+        FastWord<false>(t, g, v.w);
         uint32_t full = g;
         if (g == t.H)
-            full = PrivColdWord(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, w);
+            full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, v);
         if (full < real_rows) {
             e = full;
         } else {
@@ -562,8 +569,8 @@ __device__ __forceinline__ void PrivWord(const Tables& t, uint32_t& e, uint32_t&
 __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
-    SharedView sv = CarveShared(smem, a.hot, a.priv_rows);
-    StageTables(a, sv);
+    SharedView sv = CarveShared(smem, a.hot_small, a.priv_rows);
+    StageTables(a, sv, a.hot8_small, a.hot_small);
     {
         // replicate every packed word into the 32 banks
         const uint32_t words = (a.priv_rows / 4) * 128 * 32;
@@ -578,14 +585,14 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
     t.hot = sv.hot;
     t.cls = sv.cls;
     t.full = a.full;
-    t.H = a.hot;
+    t.H = a.hot_small;          // the second tier seen by this kernel
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = 0;
 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lane_base = SmemAddr(sv.priv) + (lane << 2);
-    const uint32_t real_rows = a.priv_rows - 1 < a.hot ? a.priv_rows - 1 : a.hot;
+    const uint32_t real_rows = a.priv_rows - 1 < a.hot_small ? a.priv_rows - 1 : a.hot_small;
     const uint32_t sink_id = a.priv_rows - 1;
     const uint64_t units = (a.n + 31) / 32;
     const uint64_t warps = (uint64_t) gridDim.x * (kPrivBlock / 32);
@@ -606,34 +613,22 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
             const bool more_d = off < len;
             if (more_d)
                 LoadStream32(p + off, d0, d1);
-            PrivWord(t, e, other, c0.x, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c0.y, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c0.z, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c0.w, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c1.x, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c1.y, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c1.z, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, c1.w, lane_base, sink_id, real_rows);
+            PrivChunk(t, e, other, c0, lane_base, sink_id, real_rows);
+            PrivChunk(t, e, other, c1, lane_base, sink_id, real_rows);
             if (!more_d)
                 break;
             off += 32;
             const bool more_c = off < len;
             if (more_c)
                 LoadStream32(p + off, c0, c1);
-            PrivWord(t, e, other, d0.x, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d0.y, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d0.z, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d0.w, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d1.x, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d1.y, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d1.z, lane_base, sink_id, real_rows);
-            PrivWord(t, e, other, d1.w, lane_base, sink_id, real_rows);
+            PrivChunk(t, e, other, d0, lane_base, sink_id, real_rows);
+            PrivChunk(t, e, other, d1, lane_base, sink_id, real_rows);
             if (!more_c)
                 break;
         }
 
         LaneState fs;
-        fs.g = a.hot;
+        fs.g = t.H;
         fs.cold = e == sink_id ? other : e;
         Report(a, t, fs, unit, i, valid);
     }
@@ -768,11 +763,11 @@ cudaError_t PrepareScanKernels(int device)
     return cudaSuccess;
 }
 
-cudaError_t PlanScan(int device, uint32_t hot, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
+cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
 {
     const bool priv = variant == kVariantPriv && uniform;
     plan->block = priv ? kPrivBlock : kBlock;
-    plan->shared = ScanSharedBytes(hot, priv ? priv_rows : 0);
+    plan->shared = priv ? ScanSharedBytes(hot_small, priv_rows) : ScanSharedBytes(hot, 0);
     int sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess)
@@ -782,6 +777,12 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t priv_rows, int variant, 
         return err;
     if (per_sm < 1)
         return cudaErrorLaunchOutOfResources;
+    if (!uniform) {
+        int cap = kGenericBlocksPerSM;
+        if (const char* env = getenv("PIRE_B200_GENERIC_CTAS"))       // experiments: resident CTAs per SM
+            cap = atoi(env) > 0 ? atoi(env) : cap;
+        per_sm = per_sm < cap ? per_sm : cap;
+    }
     plan->grid = sms * per_sm;     // persistent: every SM holds its full share of CTAs
     return cudaSuccess;
 }

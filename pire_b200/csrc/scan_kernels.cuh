@@ -34,6 +34,8 @@ struct ScanArgs {
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;
+    const uint8_t* hot8_small;   // PRIV variant's second tier: (hot_small+1)*256
+    uint32_t hot_small;
     uint32_t* match_bits;        // may be null
     uint32_t* accept_masks;      // may be null
     uint32_t* state_idx;         // may be null
@@ -50,7 +52,7 @@ enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3 };
 
 size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows);
 cudaError_t PrepareScanKernels(int device);                       // raises the dynamic smem limit
-cudaError_t PlanScan(int device, uint32_t hot, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
+cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
 // d_order <- string indices sorted by descending length (CUB radix sort on the stream).
