@@ -104,6 +104,18 @@ __device__ __forceinline__ uint4 LoadStream16(const uint8_t* p)
     return v;
 }
 
+// Same, for the generic kernel: there every lane follows its own, far-away string, so each
+// request opens a DRAM row of its own; asking L2 to fetch the whole 256-byte block on the
+// first touch turns 16 row activations into one (ragged batches were DRAM-row bound, r01).
+__device__ __forceinline__ uint4 LoadStream16Far(const uint8_t* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& b)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -458,13 +470,13 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             cur[j] = make_uint4(0, 0, 0, 0);
             nxt[j] = make_uint4(0, 0, 0, 0);
             if ((uint32_t) j < chunks)
-                cur[j] = LoadStream16(p + 16 * j);
+                cur[j] = LoadStream16Far(p + 16 * j);
         }
         for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (k + 4 + j < chunks)
-                    nxt[j] = LoadStream16(p + 16 * (size_t) (k + 4 + j));
+                    nxt[j] = LoadStream16Far(p + 16 * (size_t) (k + 4 + j));
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (k + j < chunks)
