@@ -116,6 +116,25 @@ __device__ __forceinline__ uint4 LoadStream16Far(const uint8_t* p)
     return v;
 }
 
+// Asynchronous 16-byte copy global -> shared (LDGSTS).  Completion is tracked by
+// commit/wait groups, not by the register scoreboard, so a pending copy never makes an
+// unrelated shared-memory load wait for DRAM (which is what register prefetch did in the
+// generic kernel: one exposed DRAM round trip per iteration, r01 experiments).
+__device__ __forceinline__ void CopyAsync16(uint32_t dst_shared, const uint8_t* src)
+{
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void CopyAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void CopyAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+__device__ __forceinline__ uint4 LoadShared16(uint32_t shared_addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shared_addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& b)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -125,12 +144,16 @@ __device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& 
 
 // ---------------------------------------------------------------- shared layout
 
+constexpr int kStageSlots = 4;                                      // 16-byte chunks in flight per lane
+constexpr size_t kStageBytes = (size_t) 512 * kStageSlots * 16;      // generic kernel: 32 KB per CTA
+
 struct SharedView {
     uint8_t* priv;       // (priv_rows/4) * 16 KB, PRIV variant only (else empty)
     uint8_t* hot;        // (H+1)*256
     uint16_t* cls;       // 256
     uint8_t* noexit;     // 256 (H+1 used)
     uint64_t* bar;
+    uint8_t* stage;      // generic kernel only: cp.async ring, kStageBytes
 };
 
 __host__ __device__ inline size_t HotBytes(uint32_t hot) { return (size_t) (hot + 1) * 256; }
@@ -145,6 +168,7 @@ __device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot, u
     v.cls = reinterpret_cast<uint16_t*>(smem + HotBytes(hot));
     v.noexit = smem + HotBytes(hot) + 512;
     v.bar = reinterpret_cast<uint64_t*>(smem + HotBytes(hot) + 512 + 256);
+    v.stage = smem + HotBytes(hot) + 512 + 256 + 16;
     return v;
 }
 
@@ -421,6 +445,9 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t units = (a.n + 31) / 32;
     const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    // staging ring: slot j of (warp w, lane l) at ((w * kStageSlots + j) * 32 + l) * 16 -- the 32
+    // lanes of a warp read 512 contiguous bytes with one LDS.128 (conflict-free)
+    const uint32_t stage = SmemAddr(sv.stage) + (((threadIdx.x >> 5) * kStageSlots) * 32 + lane) * 16;
 
     for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);; unit += warps) {
         if (a.work_counter) {
@@ -459,39 +486,37 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
                 full = SlowStep(t, full, *p++);
             SetFull(t, s, full);
         }
-        // body: 64 bytes (four 16-byte chunks) per iteration, the next 64 bytes in flight
-        // while these are walked; the warp iterates until its longest lane is done, shorter
-        // lanes idle (length binning keeps them few).
+        // body: 16-byte chunks through a four-deep cp.async ring in shared memory (slot
+        // c % 4 of this lane holds chunk c); the warp iterates until its longest lane is
+        // done, shorter lanes idle (length binning keeps them few).
         const uint32_t chunks = (uint32_t) ((end - p) >> 4);
         bool parked = false;       // lane sits in a NoExit state: its remaining bytes are irrelevant
-        uint4 cur[4], nxt[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cur[j] = make_uint4(0, 0, 0, 0);
-            nxt[j] = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < kStageSlots; ++j) {
             if ((uint32_t) j < chunks)
-                cur[j] = LoadStream16Far(p + 16 * j);
+                CopyAsync16(stage + j * 512, p + 16 * j);
+            CopyAsyncCommit();
         }
-        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += 4) {
+        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += kStageSlots) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (k + 4 + j < chunks)
-                    nxt[j] = LoadStream16Far(p + 16 * (size_t) (k + 4 + j));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < kStageSlots; ++j) {
+                CopyAsyncWait<kStageSlots - 1>();                 // chunk k + j has landed
+                const uint4 v = LoadShared16(stage + j * 512);
+                if (k + kStageSlots + j < chunks)
+                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
+                CopyAsyncCommit();
                 if (k + j < chunks)
-                    Chunk16<kPred>(t, s, cur[j]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                cur[j] = nxt[j];
+                    Chunk16<kPred>(t, s, v);
+            }
             // multi.h:955-958,:979-982: a NoExit state cannot be left by any byte.
-            const bool live = k + 4 < chunks;
+            const bool live = k + kStageSlots < chunks;
             const bool stuck = sv.noexit[s.g] != 0;
             if (__all_sync(0xffffffffu, !live || stuck)) {
                 parked = live && stuck;
                 break;
             }
         }
+        CopyAsyncWait<0>();
         // tail
         if (!parked) {
             p += 16 * (size_t) chunks;
@@ -756,6 +781,7 @@ const void* KernelFor(int variant, bool uniform)
 } // namespace
 
 size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows) { return PrivBytes(priv_rows) + HotBytes(hot) + 512 + 256 + 16; }
+size_t GenericSharedBytes(uint32_t hot) { return ScanSharedBytes(hot, 0) + kStageBytes; }
 
 cudaError_t PrepareScanKernels(int device)
 {
@@ -779,7 +805,7 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
 {
     const bool priv = variant == kVariantPriv && uniform;
     plan->block = priv ? kPrivBlock : kBlock;
-    plan->shared = priv ? ScanSharedBytes(hot_small, priv_rows) : ScanSharedBytes(hot, 0);
+    plan->shared = priv ? ScanSharedBytes(hot_small, priv_rows) : uniform ? ScanSharedBytes(hot, 0) : GenericSharedBytes(hot);
     int sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess)

@@ -99,6 +99,54 @@ __global__ void __launch_bounds__(512) LoadKernel(const uint8_t* corpus, uint64_
         out[0] = acc;
 }
 
+// Do warp shuffles share the shared-memory data pipe?  kWhat: 1 = LDS.U8 chain only,
+// 2 = SHFL chain only, 3 = both interleaved (two independent chains per thread).
+// If the pipes were separate, mode 3 would take max(mode 1, mode 2); if shared, the sum.
+template <int kWhat>
+__global__ void __launch_bounds__(512) PipeKernel(uint32_t iters, uint32_t* out)
+{
+    __shared__ uint8_t table[8192];
+    for (uint32_t i = threadIdx.x; i < 8192; i += blockDim.x)
+        table[i] = (uint8_t) (i * 7 + 3);
+    __syncthreads();
+    uint32_t a = threadIdx.x & 255, b = threadIdx.x * 5 + 1, v = threadIdx.x;
+    for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (kWhat & 1)
+                a = table[(a << 5) | (threadIdx.x & 31)];          // conflict-free: bank = lane
+            if (kWhat & 2)
+                v = __shfl_sync(0xffffffffu, v + b, (v ^ k) & 31);
+        }
+    }
+    if ((a ^ v) == 0xdeadbeefu)
+        out[0] = a;
+}
+
+template <int kWhat>
+void RunPipe(const char* name, uint32_t* out)
+{
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const uint32_t iters = 20000;
+    PipeKernel<kWhat><<<sms * 3, 512>>>(iters, out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    PipeKernel<kWhat><<<sms * 3, 512>>>(iters, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    // warp-level ops of each kind per clock per SM, assuming 1965 MHz
+    double ops = (double) iters * 8 * 48;        // per SM: 48 warps
+    std::printf("{\"bench\": \"pipe\", \"mode\": \"%s\", \"ms\": %.3f, \"warp_ops_per_clk_per_sm_each\": %.3f}\n", name, ms,
+                ops / (ms * 1e-3 * 1.965e9));
+    std::fflush(stdout);
+}
+
 template <int kMode>
 void Run(const char* name, const uint8_t* d, uint64_t n, uint32_t len, uint32_t* out, int threads_per_sm)
 {
@@ -137,6 +185,11 @@ int main(int argc, char** argv)
     CK(cudaMalloc(&d, n * len));
     CK(cudaMalloc(&out, 64));
     CK(cudaMemset(d, 0x5a, n * len));
+    RunPipe<1>("lds_only", out);
+    RunPipe<2>("shfl_only", out);
+    RunPipe<3>("lds_and_shfl", out);
+    if (argc > 3)
+        return 0;
     for (int tps : {1024, 1536, 2048}) {
         Run<5>("coalesced_ldg128", d, n, len, out, tps);
         Run<0>("lane_ldg128_noalloc", d, n, len, out, tps);
