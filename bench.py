@@ -70,7 +70,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -86,7 +86,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        if not rows:          # timed region shorter than the sampling period: nearest samples around it
+            rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for _, r in self.rows[-3:]]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -295,10 +297,10 @@ def main():
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local) if rank == 0 else None        # started early: nvidia-smi needs ~100 ms to begin
     for _ in range(max(args.warmup, 3)):
         step()
     launches0 = N.lib.pire_gpu_launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
