@@ -110,9 +110,11 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc,
 
 /* Length-binned form of pire_gpu_run_batch for batches of very unequal strings
  * (BASELINE config 4: 16 B .. 64 KiB).  One string per lane means a warp runs as
- * long as its longest string; with `d_order` (a permutation of 0..n-1, longest
- * first, from pire_gpu_length_order) warps get strings of similar length and claim
- * them longest-first.  Results are still indexed by the original string number.
+ * long as its longest string; with `d_order` (a permutation of 0..n-1 from
+ * pire_gpu_length_order: longest half-octave length bucket first, corpus order
+ * inside a bucket so that a warp's lanes read neighbouring addresses) warps get
+ * strings of similar length and claim them longest-first.  Results are still
+ * indexed by the original string number.
  * CSR batches only; n < 2^32. */
 int pire_gpu_length_order(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, int device, void* stream);
 int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc,

@@ -55,7 +55,7 @@ cudaError_t PrepareScanKernels(int device);                       // raises the 
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
-// d_order <- string indices sorted by descending length (CUB radix sort on the stream).
+// d_order <- string indices, longest half-octave length bucket first, corpus order inside a bucket (stable CUB radix sort).
 cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream);
 cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream);
 

@@ -314,7 +314,11 @@ def test_length_binned_launch_mixed_utf8(cuda_device, ref):
             batch.bin_by_length()
             order = batch.order.cpu().numpy()
             lens = np.diff(h_offsets.astype(np.int64))
-            assert sorted(order.tolist()) == list(range(n)) and (np.diff(lens[order]) <= 0).all()
+            assert sorted(order.tolist()) == list(range(n))
+            bucket = np.floor(2 * np.log2(lens[order])).astype(int)      # half-octave buckets, longest first,
+            assert (np.diff(bucket) <= 0).all()                          # corpus order inside a bucket
+            same = np.diff(bucket) == 0
+            assert (np.diff(order)[same] > 0).all()
         for variant in (1, 2):
             sc.set_variant(variant)
             r = P.Runner(sc).Begin().Run(batch).End()
