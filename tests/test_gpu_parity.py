@@ -315,8 +315,10 @@ def test_length_binned_launch_mixed_utf8(cuda_device, ref):
             order = batch.order.cpu().numpy()
             lens = np.diff(h_offsets.astype(np.int64))
             assert sorted(order.tolist()) == list(range(n))
-            bucket = np.floor(2 * np.log2(lens[order])).astype(int)      # half-octave buckets, longest first,
-            assert (np.diff(bucket) <= 0).all()                          # corpus order inside a bucket
+            sorted_lens = lens[order]
+            msb = np.floor(np.log2(sorted_lens)).astype(int)
+            bucket = 2 * msb + ((sorted_lens >> np.maximum(msb - 1, 0)) & 1)   # [2^k, 1.5*2^k) and [1.5*2^k, 2^(k+1))
+            assert (np.diff(bucket) <= 0).all()                          # longest bucket first, corpus order inside
             same = np.diff(bucket) == 0
             assert (np.diff(order)[same] > 0).all()
         for variant in (1, 2):
