@@ -1,0 +1,71 @@
+"""A small pass through every kernel of the library, for compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_run.py
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+Checks results against the oracle on the way (bit-exact)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+import pire_b200 as P
+from pire_b200 import _native as N
+from pire_b200 import workloads as W
+from refpire import Oracle
+
+dev = "cuda:0"
+
+
+def check(sc, orc, batch, corpus_host, offsets_host, fixed_len, n, tag):
+    f, m, s = orc.run(corpus_host, offsets_host, fixed_len=fixed_len, n=n, shortcuts=True)
+    for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED, N.VARIANT_PRIV):
+        sc.set_variant(variant)
+        r = P.Runner(sc).Begin().Run(batch).End()
+        assert (r.Matches().astype(np.uint8) == f).all() and (r.AcceptMasks() == m).all() and (r.States() == s).all(), (tag, variant)
+    print("ok", tag, "n=%d matches=%d" % (n, int(f.sum())), flush=True)
+
+
+# glued 10-pattern scanner, fixed-length strings: uniform kernels incl. PRIV, tune, tiny hot sets (replay/cold paths)
+img = W.load_image("glue10")
+orc = Oracle(img)
+sc = P.Scanner(img, 0)
+n = 2048 + 3
+spec = W.SynthSpec(n, 256, plants=W.GLUE10_PLANTS)
+d = torch.empty(spec.total_bytes(), dtype=torch.uint8, device=dev)
+spec.fill_device(d)
+host = spec.host_sample(0, n)
+batch = P.Batch(d, fixed_len=256, n=n)
+check(sc, orc, batch, host, None, 256, n, "glue10 static")
+sc.Tune(batch, 512)
+check(sc, orc, batch, host, None, 256, n, "glue10 tuned")
+sc.set_max_hot(3)
+check(sc, orc, batch, host, None, 256, n, "glue10 hot=3")
+print(sc.AutoSelect(batch))
+
+# UTF-8 scanner, ragged CSR batch: generic kernels, ordered launch, host entry point
+img = W.load_image("headline_iu")
+orc = Oracle(img)
+sc = P.Scanner(img, 0)
+mspec = W.MixedSpec(1500)
+mc, mo = mspec.device_batch(dev)
+hc, ho = mspec.host_batch(0, 1500)
+b = P.Batch(mc, mo, n=1500)
+check(sc, orc, b, hc, ho, 0, 1500, "mixed unordered")
+b.bin_by_length()
+check(sc, orc, b, hc, ho, 0, 1500, "mixed binned")
+bits, masks, states = sc.run_batch_host(hc, offsets=ho, want_masks=True, want_states=True)
+f, m, s = orc.run(hc, ho)
+assert (np.unpackbits(bits.view(np.uint8), bitorder="little")[:1500] == f).all() and (states == s).all()
+print("ok host entry")
+# odd shapes: empty strings, unaligned starts
+strings = [b"", b"x", b"hello world", b"\xd0\xbf" * 7 + b"HeLLo  World", b"a" * 33, b""] * 20
+bb = P.Batch.from_strings(strings)
+r = P.Runner(sc).Begin().Run(bb).End()
+from refpire import csr
+c, o = csr(strings)
+f, m, s = orc.run(c, o)
+assert (r.Matches().astype(np.uint8) == f).all() and (r.States() == s).all()
+print("ok ragged")
+torch.cuda.synchronize()
+print("sanitize_run done, launches:", N.lib.pire_gpu_launch_count())
