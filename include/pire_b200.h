@@ -123,6 +123,23 @@ int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc,
                                uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx,
                                void* stream);
 
+/* Replaces, per string of a batch,
+ *     Pire::LongestPrefix (sc, begin, end, throughBeginMark, throughEndMark)   run.h:277-292
+ *     Pire::ShortestPrefix(sc, begin, end, throughBeginMark, throughEndMark)   run.h:294-311
+ * d_prefix_len[i] = length of the longest / shortest prefix of string i that the
+ * scanner accepts, or PIRE_GPU_NO_PREFIX when there is none (the reference returns a
+ * null pointer).  flags: PIRE_GPU_RUN_BEGIN = throughBeginMark, PIRE_GPU_RUN_END =
+ * throughEndMark.  The scan stops in a dead state (pire_ut.cpp ScanTermination).
+ * Semantics are those of the byte-by-byte predicates (run.h:69-100), i.e. of the
+ * NoMask scanner variants: the ExitMasks fast-forward of the reference skips the
+ * predicate for the bytes it jumps over, which can leave LongestPrefix short when a
+ * string ends exactly on a 16-byte boundary of the host address space. */
+#define PIRE_GPU_NO_PREFIX 0xFFFFFFFFu
+int pire_gpu_prefix_batch(const pire_gpu_scanner* sc,
+                          const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest,
+                          uint32_t* d_prefix_len, void* stream);
+
 /* Same call with HOST buffers (what a Pire user holds: const char* ranges):
  * copies corpus (+offsets) to the device, runs, copies the requested results
  * back and synchronises.  corpus_bytes = total bytes of the corpus buffer. */

@@ -182,6 +182,24 @@ private:
 
 inline BatchRunner Runner(const Scanner& sc) { return BatchRunner(sc); }     // run.h:388-389
 
+// Batch counterparts of Pire::LongestPrefix / Pire::ShortestPrefix (run.h:277-311): one prefix
+// length per string into d_prefix_len (PIRE_GPU_NO_PREFIX where the reference returns null).
+inline void LongestPrefix(const Scanner& sc, const Batch& b, uint32_t* d_prefix_len, bool throughBeginMark = false,
+                          bool throughEndMark = false, void* stream = nullptr)
+{
+    unsigned flags = (throughBeginMark ? PIRE_GPU_RUN_BEGIN : 0u) | (throughEndMark ? PIRE_GPU_RUN_END : 0u);
+    Check(pire_gpu_prefix_batch(sc.Raw(), b.Corpus, b.Offsets, b.FixedLen, b.Count, flags, 0, d_prefix_len, stream),
+          "pire_gpu_prefix_batch");
+}
+
+inline void ShortestPrefix(const Scanner& sc, const Batch& b, uint32_t* d_prefix_len, bool throughBeginMark = false,
+                           bool throughEndMark = false, void* stream = nullptr)
+{
+    unsigned flags = (throughBeginMark ? PIRE_GPU_RUN_BEGIN : 0u) | (throughEndMark ? PIRE_GPU_RUN_END : 0u);
+    Check(pire_gpu_prefix_batch(sc.Raw(), b.Corpus, b.Offsets, b.FixedLen, b.Count, flags, 1, d_prefix_len, stream),
+          "pire_gpu_prefix_batch");
+}
+
 // Host-buffer counterpart of `bool Pire::Runner(sc).Begin().Run(p, n).End()` for many
 // strings at once (CSR): fills `matched[i]`.
 inline void MatchesHost(const Scanner& sc, const uint8_t* corpus, const uint64_t* offsets, uint64_t n,

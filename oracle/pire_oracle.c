@@ -229,3 +229,40 @@ void pire_oracle_run_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
             state_out[i] = (uint32_t) pire_oracle_state_index(sc, st);
     }
 }
+
+void pire_oracle_prefix_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
+                              const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
+                              int through_begin, int through_end, int shortest, int64_t* out)
+{
+    uint64_t i;
+    for (i = 0; i < n; ++i) {
+        const uint8_t* b = offsets ? corpus + offsets[i] : corpus + i * fixed_len;
+        const uint8_t* e = offsets ? corpus + offsets[i + 1] : b + fixed_len;
+        const uint8_t* p;
+        uint64_t st = pire_oracle_initial(sc);                          /* run.h:280-281 / :297-298 */
+        int64_t pos = -1;
+        int stop = 0;
+        if (through_begin)
+            st = pire_oracle_step(sc, st, PIRE_ORACLE_BEGIN_MARK);      /* run.h:282-283 / :299-300 */
+        if (pire_oracle_final(sc, st)) {                                /* run.h:284 / :301-302 */
+            pos = 0;
+            stop = shortest;
+        }
+        for (p = b; p != e && !stop; ++p) {
+            st = pire_oracle_step(sc, st, *p);
+            if (pire_oracle_final(sc, st)) {                            /* LongestPrefixPred run.h:92-93, Shortest :76-79 */
+                pos = (int64_t) (p + 1 - b);
+                if (shortest)
+                    stop = 1;
+            }
+            if (!stop && pire_oracle_dead(sc, st))                      /* run.h:82 / :94 */
+                stop = 1;
+        }
+        if (through_end) {                                              /* run.h:286-290 / :305-309 */
+            st = pire_oracle_step(sc, st, PIRE_ORACLE_END_MARK);
+            if (pire_oracle_final(sc, st) && (!shortest || pos < 0))
+                pos = (int64_t) (e - b);
+        }
+        out[i] = pos;
+    }
+}

@@ -67,6 +67,12 @@ void pire_oracle_run_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
                            int with_begin, int with_end, int use_shortcuts,
                            uint8_t* final_out, uint32_t* mask_out, uint32_t* state_out);
 
+/* LongestPrefix / ShortestPrefix (run.h:277-311 with the predicates of run.h:69-100) per
+ * string: out[i] = prefix length, or -1 where the reference returns a null pointer. */
+void pire_oracle_prefix_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
+                              const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
+                              int through_begin, int through_end, int shortest, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

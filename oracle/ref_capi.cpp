@@ -268,6 +268,28 @@ int pref_dead(void* h, uint64_t stateIndex)
 	return p.Dead(p.ToState(stateIndex)) ? 1 : 0;
 }
 
+// Pire::LongestPrefix / ShortestPrefix (run.h:277-311) per string.
+// variant: 0 = Scanner (ExitMasks), 2 = NonrelocScannerNoMask (byte-by-byte predicates).
+// out[i] = prefix length or -1 (the reference returns a null pointer).
+int pref_prefix_batch(void* h, int variant, int shortest, const uint8_t* corpus, const uint64_t* offsets,
+                      uint64_t fixedLen, uint64_t n, int throughBegin, int throughEnd, int64_t* out)
+{
+	RefScanner* s = (RefScanner*) h;
+	for (uint64_t i = 0; i < n; ++i) {
+		const char* b = (const char*) corpus + (offsets ? offsets[i] : i * fixedLen);
+		const char* e = offsets ? (const char*) corpus + offsets[i + 1] : b + fixedLen;
+		const char* p;
+		if (variant == 0)
+			p = shortest ? Pire::ShortestPrefix(s->reloc, b, e, throughBegin != 0, throughEnd != 0)
+			             : Pire::LongestPrefix(s->reloc, b, e, throughBegin != 0, throughEnd != 0);
+		else
+			p = shortest ? Pire::ShortestPrefix(s->nonrelocNoMask, b, e, throughBegin != 0, throughEnd != 0)
+			             : Pire::LongestPrefix(s->nonrelocNoMask, b, e, throughBegin != 0, throughEnd != 0);
+		out[i] = p ? (int64_t) (p - b) : -1;
+	}
+	return 0;
+}
+
 unsigned pref_hardware_threads() { return std::thread::hardware_concurrency(); }
 
 } // extern "C"

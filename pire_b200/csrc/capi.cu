@@ -53,6 +53,7 @@ struct DeviceTables {
     DeviceFin* fin[2] = {nullptr, nullptr};
     uint32_t* priv_packed = nullptr;
     uint8_t* hot8_small = nullptr;
+    uint8_t* flags = nullptr;
     size_t full_bytes = 0;
 
     void Free()
@@ -65,6 +66,7 @@ struct DeviceTables {
         cudaFree(fin[1]);
         cudaFree(priv_packed);
         cudaFree(hot8_small);
+        cudaFree(flags);
         *this = DeviceTables();
     }
 };
@@ -138,6 +140,8 @@ int Upload(pire_gpu_scanner* sc)
     CUDA_TRY(cudaMemcpy(d.priv_packed, t.priv_packed.data(), t.priv_packed.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&d.hot8_small, t.hot8_small.size()));
     CUDA_TRY(cudaMemcpy(d.hot8_small, t.hot8_small.data(), t.hot8_small.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.flags, t.flags_new.size()));
+    CUDA_TRY(cudaMemcpy(d.flags, t.flags_new.data(), t.flags_new.size(), cudaMemcpyHostToDevice));
     sc->priv_ok = false;
     for (int v = kVariantPlain; v <= kVariantPriv; ++v)
         for (int u = 0; u < 2; ++u) {
@@ -323,6 +327,31 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     if (variant == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
         variant = PIRE_GPU_VARIANT_PLAIN;       // the private-row kernel exists for uniform batches only
     CUDA_TRY(LaunchScan(a, (int) variant, uniform, sc->plan[variant][uniform ? 1 : 0], static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest, uint32_t* d_prefix_len, void* stream)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END))
+        return Fail(PIRE_GPU_EINVAL, "unknown run flags");
+    if (n == 0)
+        return PIRE_GPU_OK;
+    if (!d_prefix_len || (!d_corpus && (d_offsets || fixed_len != 0)))
+        return Fail(PIRE_GPU_EINVAL, "null corpus or output");
+    if (!d_offsets && fixed_len > 0xfffffffeull)
+        return Fail(PIRE_GPU_EINVAL, "strings longer than 4 GiB");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    ScanArgs a;
+    FillArgs(sc, &a, d_corpus, d_offsets, fixed_len, n, flags);
+    a.flags = sc->dev.flags;
+    a.end_class = sc->tab.end_class;
+    a.through_end = (flags & PIRE_GPU_RUN_END) ? 1 : 0;
+    a.prefix_len = d_prefix_len;
+    CUDA_TRY(LaunchPrefix(a, shortest != 0, sc->device, static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
 }
 

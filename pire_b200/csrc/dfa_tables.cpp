@@ -166,6 +166,11 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
         }
     }
 
+    t.flags_new.resize(dfa.states);
+    for (uint32_t ns = 0; ns < dfa.states; ++ns)
+        t.flags_new[ns] = dfa.flags[t.old_of_new[ns]];
+    t.end_class = dfa.class_of[kEndMark];
+
     t.start[0] = t.new_of_old[dfa.initial];                              // Initialize(), multi.h:161
     t.start[1] = t.new_of_old[dfa.Next(dfa.initial, kBeginMark)];        // Begin(), run.h:375
 }

@@ -52,6 +52,8 @@ struct ScanTables {
     std::vector<uint32_t> full32;
     std::vector<FinEntry> fin[2];            // [with_end][new id]
     uint32_t start[2] = {0, 0};              // [with_begin] -> new id
+    std::vector<uint8_t> flags_new;          // [new id]: bit0 Final, bit1 Dead (prefix scans test them per byte)
+    uint32_t end_class = 0;                  // letter class of EndMark (prefix scans step it explicitly)
     uint32_t exit_bitmap0 = ~0u;             // bit (b & 31) set if byte b may leave hot id 0 (kPred filter)
 
     // Lane-private rows (kernel variant PRIV): the first priv_rows-1 hot ids, plus a sink

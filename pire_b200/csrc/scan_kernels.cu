@@ -96,26 +96,6 @@ __device__ __forceinline__ void BulkCopyG2S(void* dst, const void* src, uint32_t
                  : "memory");
 }
 
-// Streaming read-only loads of the corpus: never re-used by this SM.
-__device__ __forceinline__ uint4 LoadStream16(const uint8_t* p)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-// Same, for the generic kernel: there every lane follows its own, far-away string, so each
-// request opens a DRAM row of its own; asking L2 to fetch the whole 256-byte block on the
-// first touch turns 16 row activations into one (ragged batches were DRAM-row bound, r01).
-__device__ __forceinline__ uint4 LoadStream16Far(const uint8_t* p)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-    return v;
-}
-
 // Asynchronous 16-byte copy global -> shared (LDGSTS).  Completion is tracked by
 // commit/wait groups, not by the register scoreboard, so a pending copy never makes an
 // unrelated shared-memory load wait for DRAM (which is what register prefetch did in the
@@ -135,6 +115,8 @@ __device__ __forceinline__ uint4 LoadShared16(uint32_t shared_addr)
     return v;
 }
 
+// Streaming read-only load of the corpus (uniform kernels): 32 bytes = one full sector per
+// lane per request, never re-used by this SM.
 __device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& b)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -200,7 +182,6 @@ __device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView&
 // ---------------------------------------------------------------- the walk
 
 struct Tables {
-    uint32_t hot_saddr;       // shared-window address of hot (for PTX loads)
     const uint8_t* hot;
     const uint16_t* cls;
     const void* full;
@@ -288,7 +269,6 @@ __device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t*
                                              uint32_t letters_wide, uint32_t from, uint4 v)
 {
     Tables t;
-    t.hot_saddr = 0;
     t.hot = hot;
     t.cls = cls;
     t.full = full;
@@ -370,7 +350,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     StageTables(a, sv, a.hot8, a.hot);
 
     Tables t;
-    t.hot_saddr = SmemAddr(sv.hot);
     t.hot = sv.hot;
     t.cls = sv.cls;
     t.full = a.full;
@@ -433,7 +412,6 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     StageTables(a, sv, a.hot8, a.hot);
 
     Tables t;
-    t.hot_saddr = SmemAddr(sv.hot);
     t.hot = sv.hot;
     t.cls = sv.cls;
     t.full = a.full;
@@ -618,7 +596,6 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
     }
 
     Tables t;
-    t.hot_saddr = SmemAddr(sv.hot);
     t.hot = sv.hot;
     t.cls = sv.cls;
     t.full = a.full;
@@ -668,6 +645,72 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
         fs.g = t.H;
         fs.cold = e == sink_id ? other : e;
         Report(a, t, fs, unit, i, valid);
+    }
+}
+
+// ---------------------------------------------------------------- prefix scans
+//
+// Pire::LongestPrefix / ShortestPrefix (run.h:277-311, predicates run.h:69-100) for a batch:
+// the same walk, but Final() and Dead() are looked at after every byte -- the longest scan
+// remembers the last position whose state is final, the shortest stops at the first, both
+// stop in a dead state (pire_ut.cpp ScanTermination@475).  One string per lane; hot rows and
+// the flags of hot states come from shared memory, the rest from the complete table.
+template <bool kShortest>
+__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+    uint8_t* hot_flags = sv.stage;                       // reuse the (unused here) staging area: H+1 bytes
+    for (uint32_t i = threadIdx.x; i <= a.hot; i += blockDim.x)
+        hot_flags[i] = i < a.hot ? a.flags[i] : 0;
+    __syncthreads();
+
+    Tables t;
+    t.hot = sv.hot;
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = 0;
+
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        uint64_t b, e;
+        if (a.offsets) {
+            b = a.offsets[i];
+            e = a.offsets[i + 1];
+        } else {
+            b = i * a.fixed_len;
+            e = b + a.fixed_len;
+        }
+        const uint8_t* p = a.corpus + b;
+        const uint32_t len = (uint32_t) (e - b);
+        uint32_t st = a.start;                                           // Initialize() [+ Step(BeginMark)]
+        uint32_t fl = st < t.H ? hot_flags[st] : a.flags[st];
+        uint32_t pos = (fl & 1u) ? 0u : kNone;                           // run.h:284 / :301-302
+        bool stop = kShortest && (fl & 1u);
+        uint32_t k = 0;
+        for (; k < len && !stop; ++k) {
+            st = SlowStep(t, st, p[k]);
+            fl = st < t.H ? hot_flags[st] : a.flags[st];
+            if (fl & 1u) {                                               // Final: run.h:76-79 / :92-93
+                pos = k + 1;
+                stop = kShortest;
+            }
+            if (fl & 2u)                                                 // Dead: run.h:82 / :94
+                stop = true;
+        }
+        if (a.through_end) {                                             // run.h:286-290 / :305-309
+            size_t at = (size_t) st * t.letters + a.end_class;
+            uint32_t last = t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at)
+                                   : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
+            if ((a.flags[last] & 1u) && (!kShortest || pos == kNone))
+                pos = len;
+        }
+        a.prefix_len[i] = pos;
     }
 }
 
@@ -835,6 +878,29 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
     void* args[] = {const_cast<ScanArgs*>(&a)};
     cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
+    if (err == cudaSuccess)
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    return err;
+}
+
+cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream)
+{
+    if (a.n == 0)
+        return cudaSuccess;
+    const void* fn = shortest ? reinterpret_cast<const void*>(&PrefixKernel<true>) : reinterpret_cast<const void*>(&PrefixKernel<false>);
+    int optin = 0, sms = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err == cudaSuccess)
+        err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err != cudaSuccess)
+        return err;
+    const size_t shared = GenericSharedBytes(a.hot);
+    uint64_t want = (a.n + kBlock - 1) / kBlock;
+    int grid = (int) (want < (uint64_t) sms * kGenericBlocksPerSM ? want : (uint64_t) sms * kGenericBlocksPerSM);
+    void* args[] = {const_cast<ScanArgs*>(&a)};
+    err = cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);
     return err;

@@ -40,6 +40,10 @@ struct ScanArgs {
     uint32_t* accept_masks;      // may be null
     uint32_t* state_idx;         // may be null
     unsigned long long* visits;  // tune kernel only: per-state visit counters (new numbering)
+    const uint8_t* flags;        // prefix kernels: [states] bit0 Final, bit1 Dead (new numbering)
+    uint32_t end_class;          // prefix kernels: letter class of EndMark
+    uint32_t through_end;        // prefix kernels: step EndMark after the bytes
+    uint32_t* prefix_len;        // prefix kernels: n words, 0xFFFFFFFF = no accepted prefix
 };
 
 struct LaunchPlan {
@@ -55,6 +59,7 @@ cudaError_t PrepareScanKernels(int device);                       // raises the 
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
+cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream);
 // d_order <- string indices, longest half-octave length bucket first, corpus order inside a bucket (stable CUB radix sort).
 cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream);
 cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream);

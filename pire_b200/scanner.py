@@ -284,3 +284,27 @@ def Runner(sc):
 def Matches(sc, batch):
     """Pire::Matches(scanner, begin, end) (run.h:396-400): Run without Begin/End marks."""
     return Runner(sc).Run(batch).Matches()
+
+
+def _prefix(sc, batch, shortest, throughBeginMark, throughEndMark):
+    torch = _torch()
+    out = torch.empty(batch.n, dtype=torch.int32, device=batch.device)
+    flags = (N.RUN_BEGIN if throughBeginMark else 0) | (N.RUN_END if throughEndMark else 0)
+    stream = torch.cuda.current_stream(batch.device).cuda_stream
+    N.check(N.lib.pire_gpu_prefix_batch(sc._h, batch.corpus.data_ptr(),
+                                        batch.offsets.data_ptr() if batch.offsets is not None else None,
+                                        batch.fixed_len, batch.n, flags, int(shortest), out.data_ptr(), stream),
+            "pire_gpu_prefix_batch")
+    res = out.cpu().numpy().view(np.uint32).astype(np.int64)
+    res[res == 0xFFFFFFFF] = -1
+    return res
+
+
+def LongestPrefix(sc, batch, throughBeginMark=False, throughEndMark=False):
+    """Pire::LongestPrefix (run.h:277-292) per string: prefix length, or -1 where the reference returns null."""
+    return _prefix(sc, batch, False, throughBeginMark, throughEndMark)
+
+
+def ShortestPrefix(sc, batch, throughBeginMark=False, throughEndMark=False):
+    """Pire::ShortestPrefix (run.h:294-311) per string: prefix length, or -1 where the reference returns null."""
+    return _prefix(sc, batch, True, throughBeginMark, throughEndMark)

@@ -41,7 +41,14 @@ def load_golden():
         return [GoldenCase(c) for c in json.load(f)["cases"]]
 
 
+def load_golden_prefix():
+    with open(os.path.join(HERE, "golden", "pire_golden.json")) as f:
+        return [(bytes.fromhex(c["pattern"]), base64.b64decode(c["image"]), bytes.fromhex(c["text"]), c["shortest"], c["longest"])
+                for c in json.load(f)["prefix_cases"]]
+
+
 GOLDEN = load_golden()
+GOLDEN_PREFIX = load_golden_prefix()
 
 
 @pytest.fixture(scope="session")

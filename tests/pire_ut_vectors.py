@@ -76,3 +76,30 @@ GLUE_CASES = [
     ([(b"a", "n"), (b"c", "n")],
      [(b"ac", [])]),
 ]
+
+# ScanBoundaries@343 (pire_ut.cpp:351-464): (pattern, text, ShortestPrefix length, LongestPrefix length),
+# -1 = null.  Patterns are compiled WITHOUT Surround() (pire_ut.cpp:313-325: Lexer(p).Parse().Compile<Scanner>()),
+# no Begin/End marks.
+_D = b"123456789-" * 8
+PREFIX_CASES = [
+    (b"a*", b"", 0, 0),
+    (b"a", b"", -1, -1),
+    (b"fixed", b"fixed prefix", 5, 5),
+    (b"fixed", b"a fixed nonexistent prefix", -1, -1),
+    (b"a*", b"aaabbb", 0, 3),
+    (b"a*", b"bbbbbb", 0, 0),
+    (b"a*", b"aaaaaa", 0, 6),
+    (b"aa*", b"aaabbb", 1, 3),
+    (b"a*a", b"aaaaaa", 1, 6),
+    (b".*a", b"bbbba", 5, 5),
+    (b".*", _D, 0, 80),
+    (b".*a", _D + b"a", 81, 81),
+    (b".*a", _D + b"a" + _D + b"a", 81, 162),
+    (b".*b", _D, -1, -1),
+    (b".*a.*", _D + b"a" + _D + b"b", 81, 162),
+    (b".*a.*b", _D + b"a" + _D + b"b", 162, 162),
+    (b"1.*a.*", _D + b"a" + _D + b"b", 81, 162),
+    (b"a+", b"bbbbbb", -1, -1),
+    # ScanTermination@475: "aaa" over "aaab\0": the scan must stop in the dead state; longest prefix = 3
+    (b"aaa", b"aaab\0", 3, 3),
+]

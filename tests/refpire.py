@@ -66,6 +66,20 @@ class RefScanner:
         self._lib.pref_save(self._h, buf, n)
         return bytes(buf)
 
+    def prefix(self, corpus, offsets=None, fixed_len=0, n=None, shortest=False, through_begin=False, through_end=False,
+               variant=2):
+        """Pire::LongestPrefix / ShortestPrefix per string: length or -1.  variant 0 = Scanner
+        (ExitMasks), 2 = NonrelocScannerNoMask."""
+        corpus = np.ascontiguousarray(corpus, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            n = len(offsets) - 1 if n is None else n
+        out = np.zeros(n, np.int64)
+        rc = self._lib.pref_prefix_batch(self._h, variant, int(shortest), _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n,
+                                         int(through_begin), int(through_end), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert rc == 0
+        return out
+
     def run(self, corpus, offsets=None, fixed_len=0, n=None, begin=True, end=True, variant=1, threads=1,
             want=("final", "mask", "state")):
         """Runner(sc).[Begin()].Run(str).[End()] per string (run.h:365-392)."""
@@ -110,6 +124,8 @@ class Ref:
         lib.pref_save.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         lib.pref_run_batch.argtypes = [C.c_void_p, C.c_int, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                        C.c_int, u8p, u32p, u32p]
+        lib.pref_prefix_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int64)]
         lib.pref_hardware_threads.restype = C.c_uint
         self.lib = lib
 
@@ -167,6 +183,9 @@ class Oracle:
             lib.pire_oracle_run_batch.restype = None
             lib.pire_oracle_run_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64,
                                                   C.c_int, C.c_int, C.c_int, u8p, u32p, u32p]
+            lib.pire_oracle_prefix_batch.restype = None
+            lib.pire_oracle_prefix_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64, C.c_int,
+                                                     C.c_int, C.c_int, C.POINTER(C.c_int64)]
             Oracle._lib = lib
         # keep an 8-byte aligned private copy alive for the views
         self._buf = np.frombuffer(bytes(image) + b"\0" * 8, dtype=np.uint8).copy()
@@ -193,6 +212,18 @@ class Oracle:
                                           int(begin), int(end), int(shortcuts), _ptr(final, u8p), _ptr(mask, u32p),
                                           _ptr(state, u32p))
         return final, mask, state
+
+
+def oracle_prefix(orc, corpus, offsets=None, fixed_len=0, n=None, shortest=False, through_begin=False, through_end=False):
+    corpus = np.ascontiguousarray(corpus, dtype=np.uint8)
+    if offsets is not None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1 if n is None else n
+    out = np.zeros(n, np.int64)
+    Oracle._lib.pire_oracle_prefix_batch(C.byref(orc._sc), _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n,
+                                         int(through_begin), int(through_end), int(shortest),
+                                         out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out
 
 
 def csr(strings):

@@ -349,3 +349,51 @@ def test_autoselect_keeps_results(cuda_device, ref):
     r = P.Runner(sc).Begin().Run(batch).End()
     f_ref, m_ref, _ = sc_ref.run(spec.host_sample(0, n), fixed_len=1024, n=n, variant=1, threads=8)
     assert (r.Matches().astype(np.uint8) == f_ref).all() and (r.AcceptMasks() == m_ref).all()
+
+
+def test_prefix_scans_golden(cuda_device):
+    """Pire::LongestPrefix / ShortestPrefix on the device against the reference's own
+    ScanBoundaries@343 / ScanTermination@475 table."""
+    import pire_b200 as P
+    from conftest import GOLDEN_PREFIX
+    for pat, image, text, shortest, longest in GOLDEN_PREFIX:
+        sc = P.Scanner(image, cuda_device)
+        batch = P.Batch.from_strings([b"junk", text, b"", text + b"tail"])
+        s = P.ShortestPrefix(sc, batch)
+        l = P.LongestPrefix(sc, batch)
+        assert s[1] == shortest and l[1] == longest, (pat, s.tolist(), l.tolist())
+
+
+def test_prefix_scans_vs_reference(cuda_device, ref):
+    """Random text, all four mark combinations, hot sets small enough to force cold states;
+    checker = the reference's byte-by-byte (NoMask) scanner and the oracle."""
+    import pire_b200 as P
+    from refpire import oracle_prefix
+    rng = np.random.default_rng(33)
+    for pat, opts in [(b"a+b", ""), (b"foo.*bar", "n"), (rb"[0-9]+\.[0-9]+", ""), (b"x*", "n"), (b"(ab)*c", "n"), (b".*z", "n"),
+                      (b"^ab", ""), (b"[^x]*", "n")]:
+        sc_ref = ref.compile(pat, opts)
+        image = sc_ref.save()
+        orc = Oracle(image)
+        strs = [bytes(rng.choice(np.frombuffer(b"abfoxz019. r", np.uint8), size=int(n))) for n in rng.integers(0, 400, size=700)]
+        strs += [b"a" * n for n in (15, 16, 17, 31, 32, 33, 64)]        # the 16-byte-boundary cases of the ExitMasks quirk
+        corpus, offs = csr(strs)
+        for max_hot in (255, 2):
+            sc = P.Scanner(image, cuda_device)
+            sc.set_max_hot(max_hot)
+            batch = P.Batch.from_strings(strs)
+            for tb in (False, True):
+                for te in (False, True):
+                    for shortest in (False, True):
+                        fn = P.ShortestPrefix if shortest else P.LongestPrefix
+                        got = fn(sc, batch, throughBeginMark=tb, throughEndMark=te)
+                        want = sc_ref.prefix(corpus, offs, shortest=shortest, through_begin=tb, through_end=te, variant=2)
+                        assert (got == want).all(), (pat, max_hot, tb, te, shortest, np.nonzero(got != want)[0][:5])
+                        assert (got == oracle_prefix(orc, corpus, offs, shortest=shortest, through_begin=tb, through_end=te)).all()
+    # fixed-length batch through the same entry point
+    sc_ref = ref.compile(b"ab+c", "")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    host = rng.choice(np.frombuffer(b"abc ", np.uint8), size=(5000, 64)).reshape(-1)
+    import torch
+    got = P.LongestPrefix(sc, P.Batch(torch.from_numpy(host).to("cuda:0"), fixed_len=64, n=5000))
+    assert (got == sc_ref.prefix(host, fixed_len=64, n=5000, variant=2)).all()

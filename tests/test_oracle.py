@@ -73,3 +73,31 @@ def test_reference_variants_agree(ref):
     orc = Oracle(sc.save())
     f, _, s = orc.run(corpus, fixed_len=1024, shortcuts=True)
     assert (f == f0).all() and (s == s0).all()
+
+
+def test_oracle_prefix_scans_match_golden():
+    """ScanBoundaries@343 / ScanTermination@475 (pire_ut.cpp): LongestPrefix / ShortestPrefix lengths."""
+    from conftest import GOLDEN_PREFIX
+    from refpire import oracle_prefix
+    for pat, image, text, shortest, longest in GOLDEN_PREFIX:
+        orc = Oracle(image)
+        corpus, offs = csr([b"junk", text, b""])
+        assert oracle_prefix(orc, corpus, offs, shortest=True)[1] == shortest, pat
+        assert oracle_prefix(orc, corpus, offs, shortest=False)[1] == longest, pat
+
+
+def test_oracle_prefix_scans_vs_reference_live(ref):
+    from refpire import oracle_prefix
+    rng = np.random.default_rng(21)
+    for pat, opts in [(b"a+b", ""), (b"foo.*bar", "n"), (rb"[0-9]+\.[0-9]+", ""), (b"x*", "n"), (b"(ab)*c", "n"), (b".*z", "n"),
+                      (b"^ab", "")]:
+        sc = ref.compile(pat, opts)
+        orc = Oracle(sc.save())
+        strs = [bytes(rng.choice(np.frombuffer(b"abfoxz019. r", np.uint8), size=int(n))) for n in rng.integers(0, 90, size=300)]
+        corpus, offs = csr(strs)
+        for tb in (False, True):
+            for te in (False, True):
+                for shortest in (False, True):
+                    want = sc.prefix(corpus, offs, shortest=shortest, through_begin=tb, through_end=te, variant=2)
+                    got = oracle_prefix(orc, corpus, offs, shortest=shortest, through_begin=tb, through_end=te)
+                    assert (got == want).all(), (pat, tb, te, shortest)
