@@ -14,9 +14,8 @@
 // (pire/scanners/multi.h:137-194,:281-284) on the HOST in index space, so the
 // reference's own templates -- Pire::Step, Pire::Run, Pire::Runner, LongestPrefix,
 // ShortestPrefix (pire/run.h) -- compile against it unchanged; the parity tests use
-// that to prove the ingest is lossless.  The host concept is for verification and
-// for the prefix/suffix scans that have not moved to the device yet; the batch
-// path never falls back to it.
+// that to prove the ingest is lossless.  The host concept is for verification; the
+// batch path never falls back to it.
 //
 // This header does not include any Pire header: the templated constructor only
 // needs `sc.Save(std::ostream*)`.
