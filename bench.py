@@ -104,12 +104,61 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows)}
 
 
+class PortScanner:
+    """Stand-in with RefScanner.run's signature over the oracle port (oracle/pire_oracle.c), used
+    only when oracle/_ref (the compiled reference) is not on this box.  Python threads over slices:
+    the C call drops the GIL."""
+
+    def __init__(self, image):
+        from refpire import Oracle
+        self.orc = Oracle(image)
+
+    def run(self, corpus, offsets=None, fixed_len=0, n=None, variant=1, threads=1, want=("final", "mask")):
+        import numpy as np
+        from concurrent.futures import ThreadPoolExecutor
+        threads = max(1, min(threads, n // 1024 or 1))
+        final = np.zeros(n, np.uint8)
+        mask = np.zeros(n, np.uint32)
+
+        def part(k):
+            lo, hi = n * k // threads, n * (k + 1) // threads
+            if offsets is not None:
+                f, m, _ = self.orc.run(corpus, offsets[lo:hi + 1], n=hi - lo, shortcuts=variant != 2)
+            else:
+                f, m, _ = self.orc.run(corpus[lo * fixed_len:hi * fixed_len], fixed_len=fixed_len, n=hi - lo, shortcuts=variant != 2)
+            final[lo:hi] = f
+            mask[lo:hi] = m
+        with ThreadPoolExecutor(threads) as pool:
+            list(pool.map(part, range(threads)))
+        return final, mask, None
+
+
+class PortRef:
+    kind = "port"
+
+    def hardware_threads(self):
+        return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+    def scanner(self, workload):
+        from pire_b200 import workloads as W
+        return PortScanner(W.load_image(W.WORKLOADS[workload][0]))
+
+
+def get_reference():
+    """The compiled reference (oracle/_ref) when it is on this box, else the oracle port."""
+    from refpire import Ref, have_ref
+    if have_ref():
+        ref = Ref()
+        ref.kind = "reference"
+        return ref
+    return PortRef()
+
+
 def cpu_reference(workload, threads, n_sample, reps, first_string=0):
     """The reference's own scan, Runner(sc).Begin().Run().End() per string with NonrelocScanner
     (its fastest variant, multi.h:1119-1123), statically partitioned over `threads` host threads."""
-    from refpire import Ref
     from pire_b200 import workloads as W
-    ref = Ref()
+    ref = get_reference()
     sc, sample, offsets, n_sample, gb = reference_sample(ref, workload, n_sample, first_string)
     kw = dict(offsets=offsets) if offsets is not None else dict(fixed_len=STRING_LEN)
     if threads <= 0:
@@ -130,9 +179,9 @@ def cpu_reference(workload, threads, n_sample, reps, first_string=0):
     sc.run(sample, n=k, variant=2, threads=1, want=("final",), **kw)
     t_nomask = time.perf_counter() - t0
     return {
-        "value": gb / best, "unit": "GB/s", "cores": threads, "kind": "reference",
-        "sample": "%d strings of the same synthetic corpus (%.2f GB), best of %d, NonrelocScanner, static partition by string count" % (
-            n_sample, gb, reps),
+        "value": gb / best, "unit": "GB/s", "cores": threads, "kind": ref.kind,
+        "sample": "%d strings of the same synthetic corpus (%.2f GB), best of %d, %s, static partition by string count" % (
+            n_sample, gb, reps, "NonrelocScanner" if ref.kind == "reference" else "oracle port (oracle/_ref absent)"),
         "matches": matches,
         "one_thread_GBps": kb / t_mask,
         "one_thread_nomask_GBps": kb / t_nomask,
@@ -142,12 +191,13 @@ def cpu_reference(workload, threads, n_sample, reps, first_string=0):
 def reference_sample(ref, workload, n_sample, first_string=0):
     """The reference scanner for a workload plus a host-generated sample of its corpus."""
     from pire_b200 import workloads as W
+    port = getattr(ref, "kind", "reference") == "port"
     if workload == "utf8mixed":
-        sc = ref.compile(*W.HEADLINE_IU)
+        sc = ref.scanner(workload) if port else ref.compile(*W.HEADLINE_IU)
         n_sample = min(n_sample, 1 << 17)          # mean string is 7.8 KB: ~1 GB
         sample, offsets = W.MixedSpec(n_sample, first_string=first_string).host_batch(0, n_sample)
         return sc, sample, offsets, n_sample, int(offsets[-1]) / 1e9
-    sc = ref.glue_all(W.GLUE10 if workload == "glue10" else [W.HEADLINE])
+    sc = ref.scanner(workload) if port else ref.glue_all(W.GLUE10 if workload == "glue10" else [W.HEADLINE])
     spec = W.SynthSpec(n_sample, STRING_LEN, plants=W.WORKLOADS[workload][1], first_string=first_string)
     return sc, spec.host_sample(0, n_sample), None, n_sample, n_sample * STRING_LEN / 1e9
 
@@ -160,9 +210,8 @@ def reference_arm(args):
     t_all = time.perf_counter()
     cb = cpu_reference(args.workload, 0, min(per_step, 1 << 20), 1)        # warm-up + the single-thread figures
     times = []
-    from refpire import Ref
     from pire_b200 import workloads as W
-    ref = Ref()
+    ref = get_reference()
     sc, sample, offsets, per_step, gb = reference_sample(ref, args.workload, per_step)
     kw = dict(offsets=offsets) if offsets is not None else dict(fixed_len=STRING_LEN)
     threads = ref.hardware_threads()
@@ -174,8 +223,9 @@ def reference_arm(args):
             times.append(dt)
     total = sum(times)
     value = gb * args.steps / total
-    cb.update(value=value, cores=threads,
-              sample="%d strings of the same synthetic corpus (%.2f GB) per step, NonrelocScanner" % (per_step, gb))
+    cb.update(value=value, cores=threads, kind=ref.kind,
+              sample="%d strings of the same synthetic corpus (%.2f GB) per step, %s" % (
+                  per_step, gb, "NonrelocScanner" if ref.kind == "reference" else "oracle port"))
     line = {
         "impl": "reference", "metric": "scanned GB/s", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -377,12 +427,39 @@ def main():
         except Exception as ex:          # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": "GB/s", "error": repr(ex)}
 
+    # the other fixed-length BASELINE configuration on the same resident bytes (a few launches)
+    also = None
+    if not mixed:
+        try:
+            other = "headline" if args.workload == "glue10" else "glue10"
+            sc2 = P.Scanner(W.load_image(W.WORKLOADS[other][0]), local)
+            sc2.Tune(batch, min(n_local, 16384))
+            ms2 = sc2.AutoSelect(batch)
+            best2 = min(ms2, key=ms2.get)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                sc2.run_batch(batch, flags, bits_local, masks, None)
+            e1.record()
+            torch.cuda.synchronize()
+            gbps2 = payload_local / 1e9 / (e0.elapsed_time(e1) / 5 / 1e3)
+            also = {"workload": "BASELINE configs[%d]: %s (same resident corpus, this GPU only)" % (W.WORKLOADS[other][3], W.WORKLOADS[other][2]),
+                    "value": gbps2, "unit": "GB/s", "kernel_variant": best2}
+            scan()           # restore this workload's outputs in bits_local / masks
+            torch.cuda.synchronize()
+            del sc2
+        except Exception as ex:      # noqa: BLE001
+            also = {"error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = measured_peak()
+    if also and "value" in also:
+        also["frac_of_hbm_peak"] = also["value"] / peak
     achieved = payload_local / 1e9 / (kernel_ms / 1e3)
     traffic = None
     try:
@@ -414,6 +491,7 @@ def main():
                      "algorithmic_bytes_per_launch": payload_local},
         "clocks": clocks,
         "e2e": e2e,
+        "also": also,
     }
     if not args.no_cpu and world == 1:
         try:

@@ -168,6 +168,8 @@ int main(int argc, char** argv)
         if (t.hot8[b] != 0)
             bitmap64 |= 1ull << (b & 63);
     std::printf("filter mode %d bitmap %08x\n", filter_mode, bitmap);
+    const char* rotenv = std::getenv("ROT");
+    const int rot = rotenv ? std::atoi(rotenv) : -1;      // >= 0: lanes 16..31 use a second table copy rotated by `rot` banks
     uint64_t steps = 0, wf_plain = 0, wf_pred = 0, active_pred = 0, lds_pred = 0;
     uint64_t chunks = 0, replay_lane_chunks = 0, replay_warp_chunks = 0;
     uint64_t hist_plain[8] = {0}, hist_pred[8] = {0};
@@ -189,6 +191,10 @@ int main(int argc, char** argv)
                     uint8_t b = corpus[(base + l) * len + c + k];
                     uint32_t idx = (g[l] << 8) | b;
                     uint32_t word = idx >> 2, bank = word & 31;
+                    if (rot >= 0 && l >= 16) {
+                        bank = (bank + rot) & 31;
+                        word |= 0x40000000u;            // a different copy: never the same word as copy A
+                    }
                     auto add = [&](uint32_t (*words)[4], int* cnt) {
                         bool seen = false;
                         for (int q = 0; q < cnt[bank] && q < 4; ++q)
