@@ -140,6 +140,22 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc,
                           uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest,
                           uint32_t* d_prefix_len, void* stream);
 
+/* The step before the path for line-oriented input (samples/pigrep/pigrep.cpp:38-45 calls
+ * std::getline and then Runner(sc).Begin().Run(line).End() per line).
+ * pire_gpu_split_lines finds the lines of a newline-delimited text resident in HBM:
+ *   d_line_offsets[0..*n_lines] (capacity + 1 entries available), line i =
+ *   d_text[off[i] .. off[i+1] - 1) -- the newline itself is excluded, a last line without
+ *   newline is kept, an empty text has no lines (std::getline semantics).
+ *   If capacity is too small (or d_line_offsets is NULL) nothing is written, *n_lines
+ *   receives a sufficient capacity and PIRE_GPU_EINVAL is returned.  Synchronises `stream`.
+ * pire_gpu_run_lines scans those lines (optionally length-binned via d_order, see
+ * pire_gpu_length_order; may be NULL); outputs as in pire_gpu_run_batch. */
+int pire_gpu_split_lines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_line_offsets, uint64_t capacity,
+                         uint64_t* n_lines, int device, void* stream);
+int pire_gpu_run_lines(const pire_gpu_scanner* sc, const uint8_t* d_text, const uint64_t* d_line_offsets,
+                       const uint32_t* d_order, uint64_t n_lines, uint32_t flags,
+                       uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream);
+
 /* Same call with HOST buffers (what a Pire user holds: const char* ranges):
  * copies corpus (+offsets) to the device, runs, copies the requested results
  * back and synchronises.  corpus_bytes = total bytes of the corpus buffer. */

@@ -71,6 +71,10 @@ $CXX $CXXFLAGS $INC -I"$REF/tools" -I"$REF/tools/common" \
     "$REF/tools/bench/bench.cpp" $OBJS -o "$OUT/pire_bench" &
 wait
 
+# the reference's own benchmark text (tools/bench/test_file, 20 KB of prose) beside the binary, for
+# continuity runs of tools/bench on the GPU box's host (run-bench doubles it to >= 300 MB)
+cp "$REF/tools/bench/test_file" "$OUT/test_file"
+
 if [ "${1:-}" != "--no-check" ]; then
     "$OUT/pire_ut" > "$OUT/pire_ut.log" 2>&1 || { tail -20 "$OUT/pire_ut.log"; echo "reference unit tests FAILED" >&2; exit 1; }
     tail -1 "$OUT/pire_ut.log"

@@ -366,9 +366,45 @@ int pire_gpu_length_order(const uint64_t* d_offsets, uint64_t n, uint32_t* d_ord
     return PIRE_GPU_OK;
 }
 
+static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets, const uint32_t* d_order,
+                  uint32_t trim, uint64_t n, uint32_t flags, uint32_t* d_match_bits, uint32_t* d_accept_masks,
+                  uint32_t* d_state_idx, void* stream);
+
 int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
                                const uint32_t* d_order, uint64_t n, uint32_t flags,
                                uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)
+{
+    if (n != 0 && !d_order)
+        return Fail(PIRE_GPU_EINVAL, "ordered runs need corpus, CSR offsets and an order");
+    return RunCsr(sc, d_corpus, d_offsets, d_order, 0, n, flags, d_match_bits, d_accept_masks, d_state_idx, stream);
+}
+
+int pire_gpu_split_lines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_line_offsets, uint64_t capacity,
+                         uint64_t* n_lines, int device, void* stream)
+{
+    if (!n_lines || (n_bytes && !d_text))
+        return Fail(PIRE_GPU_EINVAL, "null text or n_lines");
+    CUDA_TRY(cudaSetDevice(device));
+    uint64_t lines = 0;
+    cudaError_t ce = SplitLines(d_text, n_bytes, d_line_offsets, capacity, &lines, static_cast<cudaStream_t>(stream));
+    *n_lines = lines;
+    if (ce == cudaErrorInvalidValue)
+        return Fail(PIRE_GPU_EINVAL, "line offset buffer too small; *n_lines holds a sufficient capacity");
+    if (ce != cudaSuccess)
+        return FailCuda(ce, "pire_gpu_split_lines");
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_run_lines(const pire_gpu_scanner* sc, const uint8_t* d_text, const uint64_t* d_line_offsets,
+                       const uint32_t* d_order, uint64_t n_lines, uint32_t flags,
+                       uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)
+{
+    return RunCsr(sc, d_text, d_line_offsets, d_order, 1, n_lines, flags, d_match_bits, d_accept_masks, d_state_idx, stream);
+}
+
+static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets, const uint32_t* d_order,
+                  uint32_t trim, uint64_t n, uint32_t flags, uint32_t* d_match_bits, uint32_t* d_accept_masks,
+                  uint32_t* d_state_idx, void* stream)
 {
     int rc = CheckRunnable(sc);
     if (rc != PIRE_GPU_OK)
@@ -377,32 +413,38 @@ int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc, const uint8_t* d_corp
         return Fail(PIRE_GPU_EINVAL, "unknown run flags");
     if (n == 0)
         return PIRE_GPU_OK;
-    if (!d_corpus || !d_offsets || !d_order)
-        return Fail(PIRE_GPU_EINVAL, "ordered runs need corpus, CSR offsets and an order");
+    if (!d_corpus || !d_offsets)
+        return Fail(PIRE_GPU_EINVAL, "CSR runs need a corpus and offsets");
     if (n >= (1ull << 31))
         return Fail(PIRE_GPU_EINVAL, "too many strings");
     CUDA_TRY(cudaSetDevice(sc->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ScanArgs a;
     FillArgs(sc, &a, d_corpus, d_offsets, 0, n, flags);
+    a.trim = trim;
     a.order = d_order;
     a.match_bits = d_match_bits;
     a.accept_masks = d_accept_masks;
     a.state_idx = d_state_idx;
     unsigned int* counter = nullptr;
-    CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned int), st));
-    cudaError_t ce = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
-    if (ce == cudaSuccess && d_match_bits)
-        ce = cudaMemsetAsync(d_match_bits, 0, (size_t) ((n + 31) / 32) * 4, st);
-    a.work_counter = counter;
+    cudaError_t ce = cudaSuccess;
+    if (d_order) {
+        // length-binned: units are claimed longest-first, match bits are OR-ed into a zeroed bitmap
+        CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned int), st));
+        ce = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+        if (ce == cudaSuccess && d_match_bits)
+            ce = cudaMemsetAsync(d_match_bits, 0, (size_t) ((n + 31) / 32) * 4, st);
+        a.work_counter = counter;
+    }
     uint32_t variant = ResolveVariant(sc, false);
     if (variant == PIRE_GPU_VARIANT_PRIV)
         variant = PIRE_GPU_VARIANT_PLAIN;
     if (ce == cudaSuccess)
         ce = LaunchScan(a, (int) variant, false, sc->plan[variant][0], st);
-    cudaFreeAsync(counter, st);
+    if (counter)
+        cudaFreeAsync(counter, st);
     if (ce != cudaSuccess)
-        return FailCuda(ce, "pire_gpu_run_batch_ordered");
+        return FailCuda(ce, "pire_gpu_run_batch (CSR)");
     return PIRE_GPU_OK;
 }
 

@@ -32,6 +32,8 @@
 #include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 // One dynamic shared-memory array for every kernel of this file, with an unmangled
 // PTX name so that inline PTX can address it as a link-time constant.
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
         if (valid) {
             if (a.offsets) {
                 b = a.offsets[i];
-                e = a.offsets[i + 1];
+                e = a.offsets[i + 1] - a.trim;
             } else {
                 b = i * a.fixed_len;
                 e = b + a.fixed_len;
@@ -960,6 +962,108 @@ cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order
     if (keys_out) cudaFreeAsync(keys_out, stream);
     if (ids) cudaFreeAsync(ids, stream);
     if (temp) cudaFreeAsync(temp, stream);
+    return err;
+}
+
+namespace {
+struct IsNewline {
+    const uint8_t* text;
+    __host__ __device__ bool operator()(const unsigned long long& i) const { return text[i] == '\n'; }
+};
+
+__global__ void __launch_bounds__(256) CountNewlinesKernel(const uint8_t* __restrict__ text, uint64_t n_bytes, unsigned long long* __restrict__ count)
+{
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += (uint64_t) gridDim.x * blockDim.x)
+        local += text[i] == '\n';
+    for (int d = 16; d; d >>= 1)
+        local += __shfl_down_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local)
+        atomicAdd(count, local);
+}
+
+__global__ void FinishLineOffsetsKernel(const uint8_t* __restrict__ text, uint64_t n_bytes, uint64_t* __restrict__ offsets,
+                                        const unsigned long long* __restrict__ n_newlines, uint64_t capacity,
+                                        unsigned long long* __restrict__ n_lines_out)
+{
+    // offsets[1..k] hold newline positions; turn them into the starts of the following lines
+    const unsigned long long k = *n_newlines;
+    const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < k && idx + 1 <= capacity)
+        offsets[idx + 1] += 1;
+    if (idx == 0) {
+        offsets[0] = 0;
+        unsigned long long lines = k;
+        if (n_bytes != 0 && text[n_bytes - 1] != '\n') {     // last line has no newline: a virtual one after the end
+            if (k + 1 <= capacity)
+                offsets[k + 1] = n_bytes + 1;
+            lines = k + 1;
+        }
+        *n_lines_out = lines;
+    }
+}
+} // namespace
+
+cudaError_t SplitLines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_offsets, uint64_t capacity, uint64_t* n_lines,
+                       cudaStream_t stream)
+{
+    *n_lines = 0;
+    if (n_bytes == 0)
+        return cudaSuccess;
+    unsigned long long* d_counts = nullptr;       // [0] newlines, [1] lines
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t err = cudaMallocAsync(&d_counts, 2 * sizeof(unsigned long long), stream);
+    cub::CountingInputIterator<unsigned long long> positions(0);
+    IsNewline pred{d_text};
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(d_offsets + 1);
+    // capacity guards: the select writes at most min(newlines, n_bytes) entries; the caller sizes d_offsets for the
+    // worst case it accepts (capacity + 1 entries) and we verify after the fact.
+    // first pass: how many lines?  (the select below writes every newline position, so the
+    // caller's buffer must be known to be large enough before it runs)
+    unsigned long long precount = 0;
+    if (err == cudaSuccess)
+        err = cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), stream);
+    if (err == cudaSuccess) {
+        uint64_t blocks = (n_bytes + 256 * 64 - 1) / (256 * 64);
+        CountNewlinesKernel<<<(unsigned) (blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(d_text, n_bytes, d_counts);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(&precount, d_counts, sizeof(precount), cudaMemcpyDeviceToHost, stream);
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(stream);
+    if (err == cudaSuccess && (!d_offsets || precount + 1 > capacity)) {
+        cudaFreeAsync(d_counts, stream);
+        *n_lines = precount + 1;                       // upper bound of lines; caller retries with this capacity
+        return cudaErrorInvalidValue;
+    }
+    if (err == cudaSuccess)
+        err = cub::DeviceSelect::If(nullptr, temp_bytes, positions, out, d_counts, (long long) n_bytes, pred, stream);
+    if (err == cudaSuccess)
+        err = cudaMallocAsync(&temp, temp_bytes, stream);
+    if (err == cudaSuccess)
+        err = cub::DeviceSelect::If(temp, temp_bytes, positions, out, d_counts, (long long) n_bytes, pred, stream);
+    unsigned long long newlines = 0;
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(&newlines, d_counts, sizeof(newlines), cudaMemcpyDeviceToHost, stream);
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(stream);
+    if (err == cudaSuccess) {
+        unsigned blocks = (unsigned) ((newlines + 255) / 256);
+        FinishLineOffsetsKernel<<<blocks ? blocks : 1, 256, 0, stream>>>(d_text, n_bytes, d_offsets, d_counts, capacity, d_counts + 1);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        err = cudaGetLastError();
+    }
+    unsigned long long lines = 0;
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(&lines, d_counts + 1, sizeof(lines), cudaMemcpyDeviceToHost, stream);
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(stream);
+    if (d_counts) cudaFreeAsync(d_counts, stream);
+    if (temp) cudaFreeAsync(temp, stream);
+    *n_lines = lines;
     return err;
 }
 

@@ -18,6 +18,7 @@ struct DeviceFin {
 struct ScanArgs {
     const uint8_t* corpus;
     const uint64_t* offsets;     // CSR (n+1) or nullptr
+    uint32_t trim;               // CSR only: bytes dropped from the end of every string (1 = the newline of a line)
     const uint32_t* order;       // generic kernel: lane i scans string order[i] (length-binned launch), or nullptr
     unsigned int* work_counter;  // with `order`: units are claimed longest-first from this counter
     uint64_t fixed_len;          // used when offsets == nullptr
@@ -62,6 +63,10 @@ cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
 cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream);
 // d_order <- string indices, longest half-octave length bucket first, corpus order inside a bucket (stable CUB radix sort).
 cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream);
+// Line starts of a newline-delimited text (std::getline semantics): d_offsets[0..n_lines], line i =
+// text[off[i] .. off[i+1] - 1).  *n_lines is written on the host after a stream synchronise.
+cudaError_t SplitLines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_offsets, uint64_t capacity, uint64_t* n_lines,
+                       cudaStream_t stream);
 cudaError_t LaunchSynth(const SynthParams& p, const char* d_plants, uint8_t* d_out, cudaStream_t stream);
 
 cudaError_t LaunchSynthMixedLengths(uint64_t seed, uint64_t first, uint64_t n, uint64_t* d_lengths, cudaStream_t stream);

@@ -51,6 +51,7 @@ class Batch:
                 raise ValueError("corpus shorter than n * fixed_len")
         self.device = corpus.device
         self.order = None          # set by bin_by_length()
+        self.trim = 0              # 1 for line batches (from_text): the newline ending a line is not part of it
 
     def bin_by_length(self):
         """Sort the strings by descending length (on the device) so that the lanes of a warp
@@ -66,6 +67,31 @@ class Batch:
         return self
 
     @classmethod
+    def from_text(cls, text):
+        """Lines of a newline-delimited text (uint8 CUDA tensor), found on the device with
+        std::getline semantics -- what samples/pigrep/pigrep.cpp:38-45 feeds to Runner per line."""
+        torch = _torch()
+        if text.dtype != torch.uint8 or not text.is_cuda or not text.is_contiguous():
+            raise ValueError("text must be a contiguous uint8 CUDA tensor")
+        dev = text.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n_lines = C.c_uint64(0)
+        cap = max(1024, text.numel() // 64)
+        while True:
+            offsets = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+            rc = N.lib.pire_gpu_split_lines(text.data_ptr(), text.numel(), offsets.data_ptr(), cap, C.byref(n_lines),
+                                            dev.index or 0, stream)
+            if rc == 0:
+                break
+            if rc == -1 and n_lines.value > cap:         # buffer too small: retry with the reported capacity
+                cap = int(n_lines.value)
+                continue
+            N.check(rc, "pire_gpu_split_lines")
+        b = cls(text, offsets[: n_lines.value + 1].contiguous(), n=int(n_lines.value))
+        b.trim = 1
+        return b
+
+    @classmethod
     def from_strings(cls, strings, device="cuda:0"):
         """Host convenience: pack Python byte strings (CSR) and upload."""
         torch = _torch()
@@ -78,7 +104,7 @@ class Batch:
         if self.offsets is None:
             return self.n * self.fixed_len
         o = self.offsets
-        return int(o[self.n].item() - o[0].item())
+        return int(o[self.n].item() - o[0].item()) - self.trim * self.n
 
 
 class Scanner:
@@ -178,6 +204,12 @@ class Scanner:
         if stream is None:
             stream = torch.cuda.current_stream(batch.device).cuda_stream
         ptr = lambda t: None if t is None else t.data_ptr()
+        if getattr(batch, "trim", 0):
+            order = batch.order.data_ptr() if batch.order is not None else None
+            N.check(N.lib.pire_gpu_run_lines(self._h, batch.corpus.data_ptr(), ptr(batch.offsets), order, batch.n, flags,
+                                             ptr(match_bits), ptr(accept_masks), ptr(state_idx), stream),
+                    "pire_gpu_run_lines")
+            return
         if getattr(batch, "order", None) is not None:
             N.check(N.lib.pire_gpu_run_batch_ordered(self._h, batch.corpus.data_ptr(), ptr(batch.offsets),
                                                      batch.order.data_ptr(), batch.n, flags, ptr(match_bits),

@@ -397,3 +397,109 @@ def test_prefix_scans_vs_reference(cuda_device, ref):
     import torch
     got = P.LongestPrefix(sc, P.Batch(torch.from_numpy(host).to("cuda:0"), fixed_len=64, n=5000))
     assert (got == sc_ref.prefix(host, fixed_len=64, n=5000, variant=2)).all()
+
+
+def _random_pattern(rng, depth=0):
+    atoms = [b"a", b"b", b"c", b"x", b"0", b"\\d", b"\\s", b"\\w", b".", b"[a-c]", b"[^a]", b"ab", b"hello", b"\xd0\xb0", b" "]
+    r = rng.random()
+    if depth > 2 or r < 0.45:
+        a = atoms[int(rng.integers(len(atoms)))]
+    elif r < 0.65:
+        a = b"(" + _random_pattern(rng, depth + 1) + b"|" + _random_pattern(rng, depth + 1) + b")"
+    else:
+        a = _random_pattern(rng, depth + 1) + _random_pattern(rng, depth + 1)
+    q = rng.random()
+    if q < 0.15:
+        a = (b"(" + a + b")" if len(a) > 1 and not a.startswith(b"(") and not a.startswith(b"[") and not a.startswith(b"\\") else a) + b"*"
+    elif q < 0.25:
+        a = (b"(" + a + b")" if len(a) > 1 and not a.startswith(b"(") and not a.startswith(b"[") and not a.startswith(b"\\") else a) + b"+"
+    elif q < 0.32:
+        a = (b"(" + a + b")" if len(a) > 1 and not a.startswith(b"(") and not a.startswith(b"[") and not a.startswith(b"\\") else a) + b"{1,3}"
+    return a
+
+
+def test_fuzz_random_patterns(cuda_device, ref):
+    """Differential fuzz: random patterns (alternation, classes, repetition, anchors, UTF-8,
+    case-insensitive), singly and glued in threes, over random strings; every output of every
+    kernel variant must equal the reference's."""
+    import pire_b200 as P
+    rng = np.random.default_rng(2024)
+    alphabet = b"abcxABX 019\t." + "аб".encode()
+    compiled = []
+    while len(compiled) < 36:
+        pat = _random_pattern(rng)
+        if rng.random() < 0.2:
+            pat = b"^" + pat
+        if rng.random() < 0.2:
+            pat = pat + b"$"
+        opts = "".join(o for o in "iu" if rng.random() < 0.3)
+        try:
+            compiled.append((pat, opts, ref.compile(pat, opts)))
+        except ValueError:
+            continue
+    scanners = [(p, o, sc) for p, o, sc in compiled]
+    for k in range(0, 12, 3):                                    # glued triples
+        try:
+            g = ref.glue(ref.glue(compiled[k][2], compiled[k + 1][2]), compiled[k + 2][2])
+        except ValueError:
+            continue
+        if not g.empty:
+            scanners.append((b"glue", "", g))
+    strings = [bytes(rng.choice(np.frombuffer(alphabet, np.uint8), size=int(n))) for n in rng.integers(0, 120, size=1500)]
+    corpus, offs = csr(strings)
+    batch = P.Batch.from_strings(strings)
+    fixed = rng.choice(np.frombuffer(alphabet, np.uint8), size=(2048, 64)).reshape(-1)
+    import torch
+    fixed_batch = P.Batch(torch.from_numpy(fixed).to("cuda:0"), fixed_len=64, n=2048)
+    for pat, opts, sc_ref in scanners:
+        sc = P.Scanner(sc_ref.save(), cuda_device)
+        sc.Tune(batch, 512)
+        want = sc_ref.run(corpus, offs, variant=0)
+        want_fixed = sc_ref.run(fixed, fixed_len=64, n=2048, variant=0)
+        for variant in (1, 2, 3):
+            sc.set_variant(variant)
+            r = P.Runner(sc).Begin().Run(batch).End()
+            ok = (r.Matches().astype(np.uint8) == want[0]).all() and (r.AcceptMasks() == want[1]).all()
+            assert ok and (r.States() == want[2]).all(), (pat, opts, variant)
+            r = P.Runner(sc).Begin().Run(fixed_batch).End()
+            assert (r.Matches().astype(np.uint8) == want_fixed[0]).all() and (r.States() == want_fixed[2]).all(), (pat, opts, variant)
+        for shortest in (False, True):
+            fn = P.ShortestPrefix if shortest else P.LongestPrefix
+            got = fn(sc, batch, throughBeginMark=True)
+            assert (got == sc_ref.prefix(corpus, offs, shortest=shortest, through_begin=True, variant=2)).all(), (pat, opts, shortest)
+
+
+def test_lines_front_end(cuda_device, ref):
+    """samples/pigrep/pigrep.cpp:38-45: std::getline per line, then Runner(sc).Begin().Run(line).End().
+    Lines are found on the device; the newline is not part of a line ('$' must see the line end);
+    empty lines, a last line without newline and an empty text follow getline."""
+    import torch
+    import pire_b200 as P
+    sc_ref = ref.compile(rb"timeout$|^GET |error", "")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    rng = np.random.default_rng(9)
+    words = [b"GET /index", b"timeout", b"error 42", b"ok", b"", b"a timeout", b"timeout ", b"x" * 300, b"the error"]
+    for ending in (b"\n", b""):
+        lines = [words[int(k)] + bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(0, 40)), dtype=np.uint8)) * int(rng.integers(0, 2))
+                 for k in rng.integers(0, len(words), size=5000)]
+        lines = [l.replace(b"\n", b" ") for l in lines]
+        text = b"\n".join(lines) + ending
+        expect_lines = text.split(b"\n")
+        if text.endswith(b"\n") or text == b"":
+            expect_lines = expect_lines[:-1]                      # std::getline: no empty line after a final newline
+        batch = P.Batch.from_text(torch.from_numpy(np.frombuffer(text, np.uint8).copy()).to("cuda:0"))
+        assert batch.n == len(expect_lines)
+        offs = batch.offsets.cpu().numpy()
+        for i in (0, 1, batch.n // 2, batch.n - 1):
+            assert text[offs[i]: offs[i + 1] - 1] == expect_lines[i]
+        corpus, o = csr(expect_lines)
+        want = sc_ref.run(corpus, o, variant=0)
+        for binned in (False, True):
+            if binned:
+                batch.bin_by_length()
+            r = P.Runner(sc).Begin().Run(batch).End()
+            assert (r.Matches().astype(np.uint8) == want[0]).all() and (r.AcceptMasks() == want[1]).all() and (r.States() == want[2]).all()
+    empty = P.Batch.from_text(torch.zeros(0, dtype=torch.uint8, device="cuda:0"))
+    assert empty.n == 0
+    one = P.Batch.from_text(torch.from_numpy(np.frombuffer(b"\n", np.uint8).copy()).to("cuda:0"))
+    assert one.n == 1 and P.Runner(sc).Begin().Run(one).End().Matches().tolist() == [False]
