@@ -542,6 +542,10 @@ __device__ __forceinline__ uint32_t LoadSharedU8(uint32_t shared_addr)
 // lane_base = shared-window address of the private region + lane * 4.
 __device__ __forceinline__ void PrivWord(uint32_t& e, uint32_t w, uint32_t lane_base)
 {
+    // The private rows cover bytes 0..127 only.  A byte >= 128 sends the whole chunk to the
+    // re-walk anyway (PrivChunk), but its speculative step must not index past the table:
+    // clear bit 7 of every byte first (one LOP3 per word).
+    w &= 0x7F7F7F7Fu;
     const uint32_t k0 = __byte_perm(w, 0, 0x4440) * 128u + lane_base;
     const uint32_t k1 = __byte_perm(w, 0, 0x4441) * 128u + lane_base;
     const uint32_t k2 = __byte_perm(w, 0, 0x4442) * 128u + lane_base;

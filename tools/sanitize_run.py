@@ -67,5 +67,14 @@ c, o = csr(strings)
 f, m, s = orc.run(c, o)
 assert (r.Matches().astype(np.uint8) == f).all() and (r.States() == s).all()
 print("ok ragged")
+# tiny automaton (one private quad) over bytes >= 128, fixed length: the PRIV kernel's speculative steps
+from conftest import GOLDEN
+case = next(c for c in GOLDEN if c.name == "UTF8@181b")
+sc = P.Scanner(case.image, 0)
+orc = Oracle(case.image)
+rng = np.random.default_rng(5)
+fx = rng.choice(np.frombuffer("x\u0424y ab".encode() + bytes(range(120, 256)), np.uint8), size=(1024, 64)).reshape(-1)
+fb = P.Batch(torch.from_numpy(fx).to(dev), fixed_len=64, n=1024)
+check(sc, orc, fb, fx, None, 64, 1024, "tiny DFA, high bytes, PRIV")
 torch.cuda.synchronize()
 print("sanitize_run done, launches:", N.lib.pire_gpu_launch_count())
