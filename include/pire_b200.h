@@ -44,7 +44,10 @@ typedef enum pire_gpu_status {
  * Pire::Matches(sc,b,e) (run.h:396-400) steps neither mark == 0. */
 enum {
     PIRE_GPU_RUN_BEGIN = 1u,
-    PIRE_GPU_RUN_END = 2u
+    PIRE_GPU_RUN_END = 2u,
+    /* CSR offsets come from pire_gpu_split_lines: string i ends one byte before offsets[i+1]
+     * (its newline).  Accepted by every entry point that takes CSR offsets. */
+    PIRE_GPU_RUN_LINES = 4u
 };
 
 /* Kernel variants (pire_gpu_scanner_set_variant). */

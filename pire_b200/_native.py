@@ -16,6 +16,7 @@ u64p = C.POINTER(C.c_uint64)
 
 RUN_BEGIN = 1
 RUN_END = 2
+RUN_LINES = 4
 VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV = 0, 1, 2, 3
 
 # every symbol include/pire_b200.h declares

@@ -187,6 +187,7 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->letters = t.letters;
     a->wide = t.wide ? 1 : 0;
     a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
+    a->trim = (offsets && (flags & PIRE_GPU_RUN_LINES)) ? 1 : 0;
     a->exit_bitmap0 = t.exit_bitmap0;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
@@ -308,7 +309,7 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     int rc = CheckRunnable(sc);
     if (rc != PIRE_GPU_OK)
         return rc;
-    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END))
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END | PIRE_GPU_RUN_LINES))
         return Fail(PIRE_GPU_EINVAL, "unknown run flags");
     if (n == 0)
         return PIRE_GPU_OK;
@@ -336,7 +337,7 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     int rc = CheckRunnable(sc);
     if (rc != PIRE_GPU_OK)
         return rc;
-    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END))
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END | PIRE_GPU_RUN_LINES))
         return Fail(PIRE_GPU_EINVAL, "unknown run flags");
     if (n == 0)
         return PIRE_GPU_OK;
@@ -367,8 +368,8 @@ int pire_gpu_length_order(const uint64_t* d_offsets, uint64_t n, uint32_t* d_ord
 }
 
 static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets, const uint32_t* d_order,
-                  uint32_t trim, uint64_t n, uint32_t flags, uint32_t* d_match_bits, uint32_t* d_accept_masks,
-                  uint32_t* d_state_idx, void* stream);
+                  uint64_t n, uint32_t flags, uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx,
+                  void* stream);
 
 int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
                                const uint32_t* d_order, uint64_t n, uint32_t flags,
@@ -376,7 +377,7 @@ int pire_gpu_run_batch_ordered(const pire_gpu_scanner* sc, const uint8_t* d_corp
 {
     if (n != 0 && !d_order)
         return Fail(PIRE_GPU_EINVAL, "ordered runs need corpus, CSR offsets and an order");
-    return RunCsr(sc, d_corpus, d_offsets, d_order, 0, n, flags, d_match_bits, d_accept_masks, d_state_idx, stream);
+    return RunCsr(sc, d_corpus, d_offsets, d_order, n, flags, d_match_bits, d_accept_masks, d_state_idx, stream);
 }
 
 int pire_gpu_split_lines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_line_offsets, uint64_t capacity,
@@ -399,17 +400,18 @@ int pire_gpu_run_lines(const pire_gpu_scanner* sc, const uint8_t* d_text, const 
                        const uint32_t* d_order, uint64_t n_lines, uint32_t flags,
                        uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)
 {
-    return RunCsr(sc, d_text, d_line_offsets, d_order, 1, n_lines, flags, d_match_bits, d_accept_masks, d_state_idx, stream);
+    return RunCsr(sc, d_text, d_line_offsets, d_order, n_lines, flags | PIRE_GPU_RUN_LINES, d_match_bits, d_accept_masks,
+                  d_state_idx, stream);
 }
 
 static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets, const uint32_t* d_order,
-                  uint32_t trim, uint64_t n, uint32_t flags, uint32_t* d_match_bits, uint32_t* d_accept_masks,
-                  uint32_t* d_state_idx, void* stream)
+                  uint64_t n, uint32_t flags, uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx,
+                  void* stream)
 {
     int rc = CheckRunnable(sc);
     if (rc != PIRE_GPU_OK)
         return rc;
-    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END))
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END | PIRE_GPU_RUN_LINES))
         return Fail(PIRE_GPU_EINVAL, "unknown run flags");
     if (n == 0)
         return PIRE_GPU_OK;
@@ -421,7 +423,6 @@ static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uin
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ScanArgs a;
     FillArgs(sc, &a, d_corpus, d_offsets, 0, n, flags);
-    a.trim = trim;
     a.order = d_order;
     a.match_bits = d_match_bits;
     a.accept_masks = d_accept_masks;

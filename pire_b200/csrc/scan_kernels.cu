@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
         uint64_t b, e;
         if (a.offsets) {
             b = a.offsets[i];
-            e = a.offsets[i + 1];
+            e = a.offsets[i + 1] - a.trim;
         } else {
             b = i * a.fixed_len;
             e = b + a.fixed_len;
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(256) VisitCountKernel(const __grid_constant__ 
     uint64_t b, e;
     if (a.offsets) {
         b = a.offsets[i];
-        e = a.offsets[i + 1];
+        e = a.offsets[i + 1] - a.trim;
     } else {
         b = i * a.fixed_len;
         e = b + a.fixed_len;

@@ -178,7 +178,7 @@ class Scanner:
     def Tune(self, batch, n_sample=None, begin=True, end=True):
         """Pick the shared-memory rows from the states a sample of `batch` visits."""
         n_sample = batch.n if n_sample is None else min(int(n_sample), batch.n)
-        flags = (N.RUN_BEGIN if begin else 0) | (N.RUN_END if end else 0)
+        flags = (N.RUN_BEGIN if begin else 0) | (N.RUN_END if end else 0) | (N.RUN_LINES if batch.trim else 0)
         torch = _torch()
         stream = torch.cuda.current_stream(batch.device).cuda_stream
         N.check(N.lib.pire_gpu_scanner_tune(self._h, batch.corpus.data_ptr(),
@@ -188,7 +188,7 @@ class Scanner:
     def AutoSelect(self, batch, begin=True, end=True):
         """Time the kernel variants on `batch` and keep the fastest as the AUTO choice.
         Returns {variant name: ms}."""
-        flags = (N.RUN_BEGIN if begin else 0) | (N.RUN_END if end else 0)
+        flags = (N.RUN_BEGIN if begin else 0) | (N.RUN_END if end else 0) | (N.RUN_LINES if batch.trim else 0)
         torch = _torch()
         stream = torch.cuda.current_stream(batch.device).cuda_stream
         ms = (C.c_float * 4)()
@@ -321,7 +321,7 @@ def Matches(sc, batch):
 def _prefix(sc, batch, shortest, throughBeginMark, throughEndMark):
     torch = _torch()
     out = torch.empty(batch.n, dtype=torch.int32, device=batch.device)
-    flags = (N.RUN_BEGIN if throughBeginMark else 0) | (N.RUN_END if throughEndMark else 0)
+    flags = (N.RUN_BEGIN if throughBeginMark else 0) | (N.RUN_END if throughEndMark else 0) | (N.RUN_LINES if batch.trim else 0)
     stream = torch.cuda.current_stream(batch.device).cuda_stream
     N.check(N.lib.pire_gpu_prefix_batch(sc._h, batch.corpus.data_ptr(),
                                         batch.offsets.data_ptr() if batch.offsets is not None else None,

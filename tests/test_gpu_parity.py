@@ -499,6 +499,11 @@ def test_lines_front_end(cuda_device, ref):
                 batch.bin_by_length()
             r = P.Runner(sc).Begin().Run(batch).End()
             assert (r.Matches().astype(np.uint8) == want[0]).all() and (r.AcceptMasks() == want[1]).all() and (r.States() == want[2]).all()
+        # the other CSR entry points honour the line flag too (tune reads no byte past a line's end)
+        sc.Tune(batch, 2048)
+        assert (P.Runner(sc).Begin().Run(batch).End().AcceptMasks() == want[1]).all()
+        got = P.LongestPrefix(sc, batch, throughBeginMark=True, throughEndMark=True)
+        assert (got == sc_ref.prefix(corpus, o, through_begin=True, through_end=True, variant=2)).all()
     empty = P.Batch.from_text(torch.zeros(0, dtype=torch.uint8, device="cuda:0"))
     assert empty.n == 0
     one = P.Batch.from_text(torch.from_numpy(np.frombuffer(b"\n", np.uint8).copy()).to("cuda:0"))
