@@ -312,45 +312,6 @@ __device__ __forceinline__ void Chunk16(const Tables& t, LaneState& s, uint4 v)
     }
 }
 
-// The first and the last 16-byte chunk of a string that does not start / end on a 16-byte
-// boundary: bytes [lo, hi) of the aligned chunk belong to the string (the reference does the
-// same with its head and tail words, run.h:129-151 RunChunk(p, pos, size)).
-__device__ __noinline__ uint32_t ReplayChunkMasked(const uint8_t* hot, const uint16_t* cls, const void* full, uint32_t H,
-                                                   uint32_t letters_wide, uint32_t from, uint4 v, uint32_t lo_hi)
-{
-    Tables t;
-    t.hot = hot;
-    t.cls = cls;
-    t.full = full;
-    t.H = H;
-    t.letters = letters_wide & 0x7fffffffu;
-    t.wide = letters_wide >> 31;
-    t.m0 = 0;
-    const uint32_t lo = lo_hi & 0xffu, hi = lo_hi >> 8;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t s = from;
-    for (uint32_t k = lo; k < hi; ++k)
-        s = SlowStep(t, s, (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-    return s;
-}
-
-__device__ __forceinline__ void Chunk16Masked(const Tables& t, LaneState& s, uint4 v, uint32_t lo, uint32_t hi)
-{
-    const uint32_t before = s.g;
-    uint32_t g = s.g;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (uint32_t k = 0; k < 16; ++k)
-        if (k >= lo && k < hi)
-            FastStep<false>(t, g, w[k >> 2], 0x5540u + (k & 3u));
-    s.g = g;
-    if (g == t.H && lo < hi) {
-        uint32_t from = before == t.H ? s.cold : before;
-        uint32_t full = ReplayChunkMasked(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, v, lo | (hi << 8));
-        SetFull(t, s, full);
-    }
-}
-
 __device__ __forceinline__ void Report(const ScanArgs& a, const Tables& t, const LaneState& s, uint64_t unit, uint64_t i, bool valid)
 {
     DeviceFin f = a.fin[FullState(t, s)];
@@ -467,9 +428,6 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     // staging ring: slot j of (warp w, lane l) at ((w * kStageSlots + j) * 32 + l) * 16 -- the 32
     // lanes of a warp read 512 contiguous bytes with one LDS.128 (conflict-free)
     const uint32_t stage = SmemAddr(sv.stage) + (((threadIdx.x >> 5) * kStageSlots) * 32 + lane) * 16;
-    // [buf_lo, buf_hi): the bytes of the caller's corpus buffer that may be read in whole aligned chunks
-    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
-    const uintptr_t buf_hi = buf_lo + (a.offsets ? a.offsets[a.n] - a.trim : a.n * a.fixed_len);
 
     for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);; unit += warps) {
         if (a.work_counter) {
@@ -501,54 +459,34 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
         LaneState s;
         SetFull(t, s, a.start);
 
-        // A string is walked as whole aligned 16-byte chunks; in its first and last chunk only
-        // the bytes [lo0, 16) and [0, hiN) are its own.  Reading a whole aligned chunk is only
-        // allowed inside the corpus buffer; a string whose first or last chunk would stick out
-        // of it (at most the first and the last string of the corpus) walks those bytes one
-        // at a time instead.
-        const uintptr_t pa = reinterpret_cast<uintptr_t>(p), ea = reinterpret_cast<uintptr_t>(end);
-        uintptr_t first = pa & ~(uintptr_t) 15, last = (ea + 15) & ~(uintptr_t) 15;
-        uint32_t lo0 = (uint32_t) (pa - first), hiN = 16u - (uint32_t) (last - ea);
-        const bool whole = first >= buf_lo && last <= buf_hi;
-        if (!whole && pa < ea) {
-            uint32_t full = FullState(t, s);                   // head bytes up to the first boundary
+        // head: up to the first 16-byte boundary
+        {
+            uint32_t full = FullState(t, s);
             while (p < end && (reinterpret_cast<uintptr_t>(p) & 15) != 0)
                 full = SlowStep(t, full, *p++);
             SetFull(t, s, full);
-            first = reinterpret_cast<uintptr_t>(p);
-            last = first + ((ea - first) & ~(uintptr_t) 15);   // full chunks only; the tail follows below
-            lo0 = 0;
-            hiN = 16;
         }
-        const uint8_t* q = reinterpret_cast<const uint8_t*>(first);
-        const uint32_t chunks = pa < ea ? (uint32_t) ((last - first) >> 4) : 0u;
+        // body: 16-byte chunks through a four-deep cp.async ring in shared memory (slot
+        // c % 4 of this lane holds chunk c); the warp iterates until its longest lane is
+        // done, shorter lanes idle (length binning keeps them few).
+        const uint32_t chunks = (uint32_t) ((end - p) >> 4);
         bool parked = false;       // lane sits in a NoExit state: its remaining bytes are irrelevant
 #pragma unroll
         for (int j = 0; j < kStageSlots; ++j) {
             if ((uint32_t) j < chunks)
-                CopyAsync16(stage + j * 512, q + 16 * j);
+                CopyAsync16(stage + j * 512, p + 16 * j);
             CopyAsyncCommit();
         }
-        // chunks go through a four-deep cp.async ring in shared memory (slot c % 4 of this lane
-        // holds chunk c); the warp iterates until its longest lane is done, shorter lanes idle
-        // (length binning keeps them few).
         for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += kStageSlots) {
 #pragma unroll
             for (int j = 0; j < kStageSlots; ++j) {
                 CopyAsyncWait<kStageSlots - 1>();                 // chunk k + j has landed
                 const uint4 v = LoadShared16(stage + j * 512);
                 if (k + kStageSlots + j < chunks)
-                    CopyAsync16(stage + j * 512, q + 16 * (size_t) (k + kStageSlots + j));
+                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
                 CopyAsyncCommit();
-                const uint32_t c = k + j;
-                if (c < chunks) {
-                    const uint32_t lo = c == 0 ? lo0 : 0u;
-                    const uint32_t hi = c + 1 == chunks ? hiN : 16u;
-                    if (lo == 0 && hi == 16)
-                        Chunk16<kPred>(t, s, v);
-                    else
-                        Chunk16Masked(t, s, v, lo, hi);
-                }
+                if (k + j < chunks)
+                    Chunk16<kPred>(t, s, v);
             }
             // multi.h:955-958,:979-982: a NoExit state cannot be left by any byte.
             const bool live = k + kStageSlots < chunks;
@@ -559,8 +497,9 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             }
         }
         CopyAsyncWait<0>();
-        if (!whole && !parked && pa < ea) {                    // tail bytes of a string at the buffer's edge
-            p = q + 16 * (size_t) chunks;
+        // tail
+        if (!parked) {
+            p += 16 * (size_t) chunks;
             uint32_t full = FullState(t, s);
             while (p < end)
                 full = SlowStep(t, full, *p++);
