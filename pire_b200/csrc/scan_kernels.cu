@@ -403,6 +403,40 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     }
 }
 
+// Edge chunk of a string (its first or last, partially owned 16 bytes): loaded once, then
+// handed out byte by byte from registers.
+__device__ __forceinline__ uint4 LoadEdge16(const uint8_t* aligned)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(aligned));
+    return v;
+}
+
+struct EdgeBytes {
+    uint64_t lo, hi;
+    __device__ __forceinline__ EdgeBytes(uint4 v, uint32_t skip)
+    {
+        lo = (uint64_t) v.x | ((uint64_t) v.y << 32);
+        hi = (uint64_t) v.z | ((uint64_t) v.w << 32);
+        if (skip >= 8) {
+            lo = hi;
+            hi = 0;
+            skip -= 8;
+        }
+        if (skip) {
+            lo = (lo >> (8 * skip)) | (hi << (64 - 8 * skip));
+            hi >>= 8 * skip;
+        }
+    }
+    __device__ __forceinline__ uint32_t Next()
+    {
+        uint32_t b = (uint32_t) lo & 0xffu;
+        lo = (lo >> 8) | (hi << 56);
+        hi >>= 8;
+        return b;
+    }
+};
+
 // Generic batch: CSR offsets or arbitrary fixed length / alignment.  Head and
 // tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
 // with its word-aligned body.
@@ -428,6 +462,9 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     // staging ring: slot j of (warp w, lane l) at ((w * kStageSlots + j) * 32 + l) * 16 -- the 32
     // lanes of a warp read 512 contiguous bytes with one LDS.128 (conflict-free)
     const uint32_t stage = SmemAddr(sv.stage) + (((threadIdx.x >> 5) * kStageSlots) * 32 + lane) * 16;
+    // [buf_lo, buf_hi): the caller's corpus buffer; whole aligned chunks may be read inside it only
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
+    const uintptr_t buf_hi = buf_lo + (a.offsets ? a.offsets[a.n] - a.trim : a.n * a.fixed_len);
 
     for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);; unit += warps) {
         if (a.work_counter) {
@@ -459,12 +496,28 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
         LaneState s;
         SetFull(t, s, a.start);
 
-        // head: up to the first 16-byte boundary
+        // head: up to the first 16-byte boundary.  The bytes come from ONE load of the aligned
+        // chunk that holds them (the reference's RunChunk does the same with its head word,
+        // run.h:129-151) instead of one dependent global load per byte; only a string whose edge
+        // chunk would stick out of the corpus buffer reads its edge bytes one by one.
         {
-            uint32_t full = FullState(t, s);
-            while (p < end && (reinterpret_cast<uintptr_t>(p) & 15) != 0)
-                full = SlowStep(t, full, *p++);
-            SetFull(t, s, full);
+            const uint32_t misalign = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
+            if (p < end && misalign != 0) {
+                const uint64_t room = (uint64_t) (end - p);
+                const uint32_t nhead = room < 16 - misalign ? (uint32_t) room : 16 - misalign;
+                uint32_t full = FullState(t, s);
+                const uint8_t* chunk = p - misalign;
+                if (reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi) {
+                    EdgeBytes eb(LoadEdge16(chunk), misalign);
+                    for (uint32_t k = 0; k < nhead; ++k)
+                        full = SlowStep(t, full, eb.Next());
+                } else {
+                    for (uint32_t k = 0; k < nhead; ++k)
+                        full = SlowStep(t, full, p[k]);
+                }
+                p += nhead;
+                SetFull(t, s, full);
+            }
         }
         // body: 16-byte chunks through a four-deep cp.async ring in shared memory (slot
         // c % 4 of this lane holds chunk c); the warp iterates until its longest lane is
@@ -497,13 +550,22 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             }
         }
         CopyAsyncWait<0>();
-        // tail
+        // tail: fewer than 16 bytes, at an aligned address
         if (!parked) {
             p += 16 * (size_t) chunks;
-            uint32_t full = FullState(t, s);
-            while (p < end)
-                full = SlowStep(t, full, *p++);
-            SetFull(t, s, full);
+            if (p < end) {
+                const uint32_t ntail = (uint32_t) (end - p);
+                uint32_t full = FullState(t, s);
+                if (reinterpret_cast<uintptr_t>(p) + 16 <= buf_hi) {
+                    EdgeBytes eb(LoadEdge16(p), 0);
+                    for (uint32_t k = 0; k < ntail; ++k)
+                        full = SlowStep(t, full, eb.Next());
+                } else {
+                    for (uint32_t k = 0; k < ntail; ++k)
+                        full = SlowStep(t, full, p[k]);
+                }
+                SetFull(t, s, full);
+            }
         }
         if (a.order)
             ReportScattered(a, t, s, i, valid);
