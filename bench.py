@@ -349,7 +349,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    sampler = ClockSampler(local) if rank == 0 else None        # started early: nvidia-smi needs ~100 ms to begin
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("PIRE_B200_NO_CLOCKS") else None        # started early: nvidia-smi needs ~100 ms to begin
     for _ in range(max(args.warmup, 3)):
         step()
     launches0 = N.lib.pire_gpu_launch_count()
@@ -357,14 +357,19 @@ def main():
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step()
-    e1.record()
+        marks[i].record()
+    e1 = marks[-1] if marks else e1
+    if not marks:
+        e1.record()
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    per_step = sorted((marks[i - 1] if i else e0).elapsed_time(marks[i]) for i in range(args.steps))
     launches = N.lib.pire_gpu_launch_count() - launches0
     clocks = sampler.stop(t_begin, t_end) if sampler else None
     if world > 1:
@@ -471,6 +476,7 @@ def main():
     line = {
         "metric": "scanned GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]} if per_step else None,
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {
             "workload": "BASELINE configs[%d]: %s; %d synthetic strings per GPU (%.2f GB/GPU), "

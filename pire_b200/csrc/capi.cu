@@ -431,7 +431,7 @@ static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uin
     cudaError_t ce = cudaSuccess;
     if (d_order) {
         // length-binned: units are claimed longest-first, match bits are OR-ed into a zeroed bitmap
-        CUDA_TRY(cudaMallocAsync(&counter, sizeof(unsigned int), st));
+        CUDA_TRY(ScratchAlloc(reinterpret_cast<void**>(&counter), sizeof(unsigned int), st));
         ce = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
         if (ce == cudaSuccess && d_match_bits)
             ce = cudaMemsetAsync(d_match_bits, 0, (size_t) ((n + 31) / 32) * 4, st);

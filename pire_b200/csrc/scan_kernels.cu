@@ -29,6 +29,7 @@
 #include "scan_kernels.cuh"
 
 #include <atomic>
+#include <mutex>
 #include <cstdlib>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -1004,6 +1005,42 @@ __global__ void __launch_bounds__(256) LengthKeysKernel(const uint64_t* __restri
 }
 } // namespace
 
+// Stream-ordered scratch (work counters, sort/select temporaries) comes from a private per-device pool
+// that keeps up to 64 MiB cached.  The device's default pool returns everything to the driver at each
+// synchronisation, after which the next 4-byte counter allocation costs a 10-40 ms mapping stall -- seen as
+// one slow step in twenty on the length-binned path.
+cudaError_t ScratchAlloc(void** out, size_t bytes, cudaStream_t stream)
+{
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int device = 0;
+    cudaError_t err = cudaGetDevice(&device);
+    if (err != cudaSuccess)
+        return err;
+    if (device < 0 || device >= 64)
+        return cudaMallocAsync(out, bytes, stream);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pools[device]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            err = cudaMemPoolCreate(&pools[device], &props);
+            if (err != cudaSuccess)
+                return err;
+            uint64_t keep = 64ull << 20;
+            err = cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+            if (err != cudaSuccess)
+                return err;
+        }
+        pool = pools[device];
+    }
+    return cudaMallocFromPoolAsync(out, bytes, pool, stream);
+}
+
 cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream)
 {
     if (n == 0)
@@ -1011,9 +1048,9 @@ cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order
     uint32_t *keys = nullptr, *keys_out = nullptr, *ids = nullptr;
     void* temp = nullptr;
     size_t temp_bytes = 0;
-    cudaError_t err = cudaMallocAsync(&keys, n * 4, stream);
-    if (err == cudaSuccess) err = cudaMallocAsync(&keys_out, n * 4, stream);
-    if (err == cudaSuccess) err = cudaMallocAsync(&ids, n * 4, stream);
+    cudaError_t err = ScratchAlloc((void**) &keys, n * 4, stream);
+    if (err == cudaSuccess) err = ScratchAlloc((void**) &keys_out, n * 4, stream);
+    if (err == cudaSuccess) err = ScratchAlloc((void**) &ids, n * 4, stream);
     if (err == cudaSuccess) {
         LengthKeysKernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(d_offsets, n, keys, ids);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1021,7 +1058,7 @@ cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order
     }
     if (err == cudaSuccess)
         err = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, keys_out, ids, d_order, (int) n, 0, 8, stream);
-    if (err == cudaSuccess) err = cudaMallocAsync(&temp, temp_bytes, stream);
+    if (err == cudaSuccess) err = ScratchAlloc(&temp, temp_bytes, stream);
     if (err == cudaSuccess)
         err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, ids, d_order, (int) n, 0, 8, stream);
     if (keys) cudaFreeAsync(keys, stream);
@@ -1079,7 +1116,7 @@ cudaError_t SplitLines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_offs
     unsigned long long* d_counts = nullptr;       // [0] newlines, [1] lines
     void* temp = nullptr;
     size_t temp_bytes = 0;
-    cudaError_t err = cudaMallocAsync(&d_counts, 2 * sizeof(unsigned long long), stream);
+    cudaError_t err = ScratchAlloc((void**) &d_counts, 2 * sizeof(unsigned long long), stream);
     cub::CountingInputIterator<unsigned long long> positions(0);
     IsNewline pred{d_text};
     unsigned long long* out = reinterpret_cast<unsigned long long*>(d_offsets + 1);
@@ -1108,7 +1145,7 @@ cudaError_t SplitLines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_offs
     if (err == cudaSuccess)
         err = cub::DeviceSelect::If(nullptr, temp_bytes, positions, out, d_counts, (long long) n_bytes, pred, stream);
     if (err == cudaSuccess)
-        err = cudaMallocAsync(&temp, temp_bytes, stream);
+        err = ScratchAlloc(&temp, temp_bytes, stream);
     if (err == cudaSuccess)
         err = cub::DeviceSelect::If(temp, temp_bytes, positions, out, d_counts, (long long) n_bytes, pred, stream);
     unsigned long long newlines = 0;

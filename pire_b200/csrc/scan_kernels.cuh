@@ -62,6 +62,8 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
 cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream);
 // d_order <- string indices, longest half-octave length bucket first, corpus order inside a bucket (stable CUB radix sort).
+// stream-ordered scratch from the library's own per-device pool (see scan_kernels.cu)
+cudaError_t ScratchAlloc(void** out, size_t bytes, cudaStream_t stream);
 cudaError_t LengthOrder(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, cudaStream_t stream);
 // Line starts of a newline-delimited text (std::getline semantics): d_offsets[0..n_lines], line i =
 // text[off[i] .. off[i+1] - 1).  *n_lines is written on the host after a stream synchronise.
