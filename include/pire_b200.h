@@ -143,6 +143,22 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc,
                           uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest,
                           uint32_t* d_prefix_len, void* stream);
 
+/* Replaces, per string of a batch, the run of a Pire::HalfFinalScanner (pire/scanners/half_final.h):
+ *     HalfFinalScanner::State st;  sc.Initialize(st);            half_final.h:136-141
+ *     [Pire::Step(sc, st, BeginMark);]  Pire::Run(sc, st, begin, end);  [Pire::Step(sc, st, EndMark);]
+ *     st.Result(r) for every regexp r                             half_final.h:88-90
+ * (the driver of tests/count_ut.cpp:54-63).  TakeAction (half_final.h:154-163) adds one to the counter of
+ * every regexp listed for a state each time the walk enters that state while it is final -- so Result(r)
+ * counts the positions where a match of regexp r ends (HalfFinalFsm's counters, half_final_fsm.h:11-20),
+ * and AcceptedRegexps(st) is { r : Result(r) != 0 }.
+ * The image is the Save() stream of the HalfFinalScanner (it inherits Scanner::Save; the same format).
+ * d_counts: n rows of max(1, regexps) u32, row i for string i (overwritten).  d_match_bits: packed
+ * Final(st) per string, may be null.  Counters are 32 bits wide (the reference's are size_t). */
+int pire_gpu_count_batch(const pire_gpu_scanner* sc,
+                         const uint8_t* d_corpus, const uint64_t* d_offsets,
+                         uint64_t fixed_len, uint64_t n, uint32_t flags,
+                         uint32_t* d_counts, uint32_t* d_match_bits, void* stream);
+
 /* The step before the path for line-oriented input (samples/pigrep/pigrep.cpp:38-45 calls
  * std::getline and then Runner(sc).Begin().Run(line).End() per line).
  * pire_gpu_split_lines finds the lines of a newline-delimited text resident in HBM:

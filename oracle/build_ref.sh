@@ -20,7 +20,9 @@ OUT="$HERE/_ref"
 GEN="$OUT/gen"
 OBJ="$OUT/obj"
 CXX="${CXX:-g++}"
-CXXFLAGS="-std=c++11 -O2 -w -fPIC -DPIRE_NO_CONFIG"
+# -include limits: pire/extra/count.cpp uses std::numeric_limits without including <limits> (fine with the
+# compilers of its day, an error with gcc 13); the reference source is left untouched.
+CXXFLAGS="-std=c++11 -O2 -w -fPIC -DPIRE_NO_CONFIG -include limits"
 
 if [ ! -d "$REF/pire" ]; then
     echo "build_ref.sh: reference tree $REF not present; keeping prebuilt oracle/_ref" >&2
@@ -46,7 +48,7 @@ sed -n "${s},$((e-1))p" "$REF/pire/re_parser.y" > "$GEN/re_parser_helpers.inc"
 
 INC="-I$REF -I$REF/pire -I$GEN -I$HERE"
 
-LIBSRC="approx_matching classes easy encoding fsm half_final_fsm re_lexer read_unicode scanner_io scanners/null stub/utf8"
+LIBSRC="approx_matching classes easy encoding fsm half_final_fsm re_lexer read_unicode scanner_io scanners/null stub/utf8 extra/count extra/capture extra/glyphs"
 OBJS=""
 for f in $LIBSRC; do
     o="$OBJ/$(echo "$f" | tr / _).o"
@@ -64,7 +66,7 @@ $CXX -shared -o "$OUT/libpire_ref.so" $OBJS "$OBJ/ref_capi.o" -lpthread
 
 # --- the reference's own unit tests as the gate ------------------------------
 $CXX $CXXFLAGS $INC -I"$REF/tests" \
-    "$REF/tests/stub/cppunit.cpp" "$REF/tests/pire_ut.cpp" "$REF/tests/easy_ut.cpp" \
+    "$REF/tests/stub/cppunit.cpp" "$REF/tests/pire_ut.cpp" "$REF/tests/easy_ut.cpp" "$REF/tests/count_ut.cpp" \
     $OBJS -o "$OUT/pire_ut" &
 # --- the reference's own benchmark driver -------------------------------------
 $CXX $CXXFLAGS $INC -I"$REF/tools" -I"$REF/tools/common" \

@@ -266,3 +266,48 @@ void pire_oracle_prefix_batch(const pire_oracle_scanner* sc, const uint8_t* corp
         out[i] = pos;
     }
 }
+
+/* ---- HalfFinalScanner counting (pire/scanners/half_final.h) ------------------------------- */
+
+/* TakeAction, half_final.h:154-163: in a final state every entry of the state's accept list bumps the
+ * counter of the regexp it names (an id may be listed several times: BuildFinals, half_final.h:215-226). */
+static void oracle_take_action(const pire_oracle_scanner* sc, uint64_t st, uint32_t* row)
+{
+    const uint64_t* it;
+    if (sc->empty || !pire_oracle_final(sc, st))
+        return;
+    for (it = sc->final_tab + sc->final_idx[pire_oracle_state_index(sc, st)]; *it != (uint64_t) -1; ++it)
+        if (*it < sc->regexps)
+            row[*it]++;
+}
+
+void pire_oracle_count_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
+                             const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
+                             int with_begin, int with_end, uint32_t* counts, uint8_t* final_out)
+{
+    uint64_t i;
+    const uint32_t regs = sc->regexps ? sc->regexps : 1;
+    for (i = 0; i < n; ++i) {
+        const uint8_t* b = offsets ? corpus + offsets[i] : corpus + i * fixed_len;
+        const uint8_t* e = offsets ? corpus + offsets[i + 1] : b + fixed_len;
+        const uint8_t* p;
+        uint32_t* row = counts + i * regs;
+        uint64_t st = pire_oracle_initial(sc);             /* Initialize, half_final.h:136-141 ... */
+        memset(row, 0, regs * sizeof(uint32_t));
+        oracle_take_action(sc, st, row);                   /* ... which ends in TakeAction(state, 0) */
+        if (with_begin) {                                  /* Step = Next + TakeAction, run.h:50-57 */
+            st = pire_oracle_step(sc, st, PIRE_ORACLE_BEGIN_MARK);
+            oracle_take_action(sc, st, row);
+        }
+        for (p = b; p != e; ++p) {
+            st = pire_oracle_step(sc, st, *p);
+            oracle_take_action(sc, st, row);
+        }
+        if (with_end) {
+            st = pire_oracle_step(sc, st, PIRE_ORACLE_END_MARK);
+            oracle_take_action(sc, st, row);
+        }
+        if (final_out)
+            final_out[i] = (uint8_t) pire_oracle_final(sc, st);
+    }
+}

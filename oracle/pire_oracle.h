@@ -73,6 +73,13 @@ void pire_oracle_prefix_batch(const pire_oracle_scanner* sc, const uint8_t* corp
                               const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
                               int through_begin, int through_end, int shortest, int64_t* out);
 
+/* HalfFinalScanner (pire/scanners/half_final.h:136-163) per string, as tests/count_ut.cpp:54-63 drives it:
+ *   Initialize (+TakeAction); [Step(BeginMark)]; Step per byte; [Step(EndMark)]; Result(r) for every regexp.
+ * counts: n rows of max(1, regexps) u32.  The image is the same Scanner::Save() stream. */
+void pire_oracle_count_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
+                             const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
+                             int with_begin, int with_end, uint32_t* counts, uint8_t* final_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,34 @@ struct PeekScanner : Pire::Scanner {
 };
 const PeekScanner& AsPeek(const Pire::Scanner& sc) { return static_cast<const PeekScanner&>(sc); }
 
+// ---- HalfFinalScanner (pire/scanners/half_final.h), the "next" row SURVEY.md 8(f) rank 3 ----
+struct RefHalfFinal {
+	Pire::HalfFinalScanner sc;
+};
+
+// The run of tests/count_ut.cpp:54-63: Initialize, [BeginMark], bytes, [EndMark]; then Result(i) per regexp.
+void CountRange(const Pire::HalfFinalScanner& sc, const uint8_t* corpus, const uint64_t* offsets, uint64_t fixedLen,
+                uint64_t lo, uint64_t hi, int withBegin, int withEnd, uint32_t* counts, uint8_t* finalOut)
+{
+	const size_t regs = sc.RegexpsCount();
+	for (uint64_t i = lo; i < hi; ++i) {
+		const char* b = offsets ? (const char*) corpus + offsets[i] : (const char*) corpus + i * fixedLen;
+		const char* e = offsets ? (const char*) corpus + offsets[i + 1] : b + fixedLen;
+		Pire::HalfFinalScanner::State st;
+		sc.Initialize(st);
+		if (withBegin)
+			Pire::Step(sc, st, Pire::BeginMark);
+		Pire::Run(sc, st, b, e);
+		if (withEnd)
+			Pire::Step(sc, st, Pire::EndMark);
+		if (counts)
+			for (size_t r = 0; r < regs; ++r)
+				counts[i * regs + r] = (uint32_t) st.Result(r);
+		if (finalOut)
+			finalOut[i] = sc.Final(st) ? 1 : 0;
+	}
+}
+
 } // namespace
 
 extern "C" {
@@ -287,6 +315,84 @@ int pref_prefix_batch(void* h, int variant, int shortest, const uint8_t* corpus,
 			             : Pire::LongestPrefix(s->nonrelocNoMask, b, e, throughBegin != 0, throughEnd != 0);
 		out[i] = p ? (int64_t) (p - b) : -1;
 	}
+	return 0;
+}
+
+// mode 0: HalfFinalScanner(fsm) (half_final.h:38-46, MakeScanner);  modes 1..5: the counters of
+// tests/count_ut.cpp:503-520 in that order -- MakeGreedyCounter(true), MakeGreedyCounter(false),
+// MakeNonGreedyCounter(true,true), MakeNonGreedyCounter(true,false), MakeNonGreedyCounter(false).
+void* pref_hf_compile(const char* pattern, const char* options, int mode, char* err, size_t errlen)
+{
+	try {
+		Pire::Fsm fsm = Parse(pattern, options);
+		RefHalfFinal* h = new RefHalfFinal;
+		if (mode == 0) {
+			h->sc = Pire::HalfFinalScanner(fsm);
+		} else {
+			Pire::HalfFinalFsm hf(fsm);
+			switch (mode) {
+			case 1: hf.MakeGreedyCounter(true); break;
+			case 2: hf.MakeGreedyCounter(false); break;
+			case 3: hf.MakeNonGreedyCounter(true, true); break;
+			case 4: hf.MakeNonGreedyCounter(true, false); break;
+			case 5: hf.MakeNonGreedyCounter(false); break;
+			default: delete h; throw std::invalid_argument("unknown half-final mode");
+			}
+			h->sc = Pire::HalfFinalScanner(hf);
+		}
+		return h;
+	} catch (std::exception& e) {
+		SetErr(err, errlen, e.what());
+		return nullptr;
+	}
+}
+
+void* pref_hf_glue(void* a, void* b, size_t maxSize, char* err, size_t errlen)
+{
+	try {
+		RefHalfFinal* h = new RefHalfFinal;
+		h->sc = Pire::HalfFinalScanner::Glue(((RefHalfFinal*) a)->sc, ((RefHalfFinal*) b)->sc, maxSize);
+		return h;
+	} catch (std::exception& e) {
+		SetErr(err, errlen, e.what());
+		return nullptr;
+	}
+}
+
+void pref_hf_free(void* h) { delete (RefHalfFinal*) h; }
+int pref_hf_empty(void* h) { return ((RefHalfFinal*) h)->sc.Empty() ? 1 : 0; }
+uint64_t pref_hf_size(void* h) { return ((RefHalfFinal*) h)->sc.Size(); }
+uint64_t pref_hf_regexps_count(void* h) { return ((RefHalfFinal*) h)->sc.RegexpsCount(); }
+
+uint64_t pref_hf_save(void* h, void* buf, uint64_t cap)
+{
+	std::ostringstream out;
+	((RefHalfFinal*) h)->sc.Save(&out);
+	std::string s = out.str();
+	if (buf && cap >= s.size())
+		std::memcpy(buf, s.data(), s.size());
+	return s.size();
+}
+
+// counts: n x RegexpsCount() u32, row per string.
+int pref_hf_count_batch(void* h, const uint8_t* corpus, const uint64_t* offsets, uint64_t fixedLen, uint64_t n,
+                        int withBegin, int withEnd, int threads, uint32_t* counts, uint8_t* finalOut)
+{
+	const Pire::HalfFinalScanner& sc = ((RefHalfFinal*) h)->sc;
+	if (threads <= 1 || n < 2) {
+		CountRange(sc, corpus, offsets, fixedLen, 0, n, withBegin, withEnd, counts, finalOut);
+		return 0;
+	}
+	std::vector<std::thread> pool;
+	uint64_t per = (n + threads - 1) / threads;
+	for (int t = 0; t < threads; ++t) {
+		uint64_t lo = std::min<uint64_t>(n, per * t), hi = std::min<uint64_t>(n, lo + per);
+		if (lo == hi)
+			break;
+		pool.emplace_back([=, &sc] { CountRange(sc, corpus, offsets, fixedLen, lo, hi, withBegin, withEnd, counts, finalOut); });
+	}
+	for (auto& th : pool)
+		th.join();
 	return 0;
 }
 

@@ -54,6 +54,8 @@ struct DeviceTables {
     uint32_t* priv_packed = nullptr;
     uint8_t* hot8_small = nullptr;
     uint8_t* flags = nullptr;
+    uint32_t* acc_begin = nullptr;
+    uint32_t* acc_ids = nullptr;
     size_t full_bytes = 0;
 
     void Free()
@@ -67,6 +69,8 @@ struct DeviceTables {
         cudaFree(priv_packed);
         cudaFree(hot8_small);
         cudaFree(flags);
+        cudaFree(acc_begin);
+        cudaFree(acc_ids);
         *this = DeviceTables();
     }
 };
@@ -142,6 +146,11 @@ int Upload(pire_gpu_scanner* sc)
     CUDA_TRY(cudaMemcpy(d.hot8_small, t.hot8_small.data(), t.hot8_small.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&d.flags, t.flags_new.size()));
     CUDA_TRY(cudaMemcpy(d.flags, t.flags_new.data(), t.flags_new.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.acc_begin, t.acc_begin_new.size() * 4));
+    CUDA_TRY(cudaMemcpy(d.acc_begin, t.acc_begin_new.data(), t.acc_begin_new.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.acc_ids, t.acc_ids_new.size() * 4 + 4));
+    if (!t.acc_ids_new.empty())
+        CUDA_TRY(cudaMemcpy(d.acc_ids, t.acc_ids_new.data(), t.acc_ids_new.size() * 4, cudaMemcpyHostToDevice));
     sc->priv_ok = false;
     for (int v = kVariantPlain; v <= kVariantPriv; ++v)
         for (int u = 0; u < 2; ++u) {
@@ -353,6 +362,40 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     a.through_end = (flags & PIRE_GPU_RUN_END) ? 1 : 0;
     a.prefix_len = d_prefix_len;
     CUDA_TRY(LaunchPrefix(a, shortest != 0, sc->device, static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_count_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                         uint64_t fixed_len, uint64_t n, uint32_t flags, uint32_t* d_counts, uint32_t* d_match_bits,
+                         void* stream)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (flags & ~(PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END | PIRE_GPU_RUN_LINES))
+        return Fail(PIRE_GPU_EINVAL, "unknown run flags");
+    if (n == 0)
+        return PIRE_GPU_OK;
+    if (!d_counts || (!d_corpus && (d_offsets || fixed_len != 0)))
+        return Fail(PIRE_GPU_EINVAL, "null corpus or output");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScanArgs a;
+    FillArgs(sc, &a, d_corpus, d_offsets, fixed_len, n, flags);
+    a.flags = sc->dev.flags;
+    a.end_class = sc->tab.end_class;
+    a.through_end = (flags & PIRE_GPU_RUN_END) ? 1 : 0;
+    a.acc_begin = sc->dev.acc_begin;
+    a.acc_ids = sc->dev.acc_ids;
+    a.first_final_hot = sc->tab.first_final_hot;
+    a.begin_class = sc->tab.begin_class;
+    a.initial = sc->tab.initial;
+    a.with_begin = (flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0;
+    a.regexps = sc->dfa.regexps ? sc->dfa.regexps : 1;
+    a.counts = d_counts;
+    a.match_bits = d_match_bits;
+    CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t) n * a.regexps * 4, st));
+    CUDA_TRY(LaunchCount(a, sc->device, st));
     return PIRE_GPU_OK;
 }
 

@@ -66,9 +66,18 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
         if (t.old_of_new.size() == H)
             break;
         if (s < dfa.states && t.new_of_old[s] == UINT32_MAX) {
-            t.new_of_old[s] = (uint32_t) t.old_of_new.size();
+            t.new_of_old[s] = 0;
             t.old_of_new.push_back(s);
         }
+    }
+    // Final hot states take the highest hot ids (order otherwise kept): the counting kernel then
+    // learns "did this chunk touch a final state or leave the hot rows" from the maximum id seen.
+    std::stable_partition(t.old_of_new.begin(), t.old_of_new.end(), [&](uint32_t s) { return !dfa.Final(s); });
+    t.first_final_hot = (uint32_t) t.old_of_new.size();
+    for (uint32_t k = 0; k < t.old_of_new.size(); ++k) {
+        t.new_of_old[t.old_of_new[k]] = k;
+        if (dfa.Final(t.old_of_new[k]) && t.first_final_hot == t.old_of_new.size())
+            t.first_final_hot = k;
     }
     for (uint32_t s = 0; s < dfa.states; ++s)
         if (t.new_of_old[s] == UINT32_MAX) {
@@ -170,6 +179,20 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
     for (uint32_t ns = 0; ns < dfa.states; ++ns)
         t.flags_new[ns] = dfa.flags[t.old_of_new[ns]];
     t.end_class = dfa.class_of[kEndMark];
+    t.begin_class = dfa.class_of[kBeginMark];
+    t.initial = t.new_of_old[dfa.initial];
+    t.acc_begin_new.assign((size_t) dfa.states + 1, 0);
+    t.acc_ids_new.clear();
+    for (uint32_t ns = 0; ns < dfa.states; ++ns) {
+        t.acc_begin_new[ns] = (uint32_t) t.acc_ids_new.size();
+        const uint32_t os = t.old_of_new[ns];
+        if (!dfa.Final(os))                      // TakeAction only looks at the list of a final state
+            continue;
+        for (uint32_t k = dfa.acc_begin[os]; k < dfa.acc_begin[os + 1]; ++k)
+            if (dfa.acc_ids[k] < std::max<uint32_t>(1, dfa.regexps))     // a counter exists for it
+                t.acc_ids_new.push_back(dfa.acc_ids[k]);
+    }
+    t.acc_begin_new[dfa.states] = (uint32_t) t.acc_ids_new.size();
 
     t.start[0] = t.new_of_old[dfa.initial];                              // Initialize(), multi.h:161
     t.start[1] = t.new_of_old[dfa.Next(dfa.initial, kBeginMark)];        // Begin(), run.h:375

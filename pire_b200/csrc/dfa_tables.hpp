@@ -55,6 +55,13 @@ struct ScanTables {
     std::vector<uint8_t> flags_new;          // [new id]: bit0 Final, bit1 Dead (prefix scans test them per byte)
     uint32_t end_class = 0;                  // letter class of EndMark (prefix scans step it explicitly)
     uint32_t exit_bitmap0 = ~0u;             // bit (b & 31) set if byte b may leave hot id 0 (kPred filter)
+    // Counting (HalfFinalScanner, half_final.h:154-163): hot ids >= first_final_hot are final states
+    // (== hot when none is); accept lists in the new numbering as CSR, ids repeated as the image has them.
+    uint32_t first_final_hot = 0;
+    uint32_t begin_class = 0;                // letter class of BeginMark
+    uint32_t initial = 0;                    // new id of Initialize()'s state
+    std::vector<uint32_t> acc_begin_new;     // [states + 1]
+    std::vector<uint32_t> acc_ids_new;
 
     // Lane-private rows (kernel variant PRIV): the first priv_rows-1 hot ids, plus a sink
     // row (id priv_rows-1) that absorbs every transition into a non-private state.  Only

@@ -783,6 +783,202 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
     }
 }
 
+
+// ---------------------------------------------------------------- counting (HalfFinalScanner)
+//
+// pire/scanners/half_final.h: the same table walk, but after Initialize() and after every symbol
+// TakeAction (:154-163) adds one to the counter of each regexp listed for the state when the state is
+// final.  The per-string result is the vector of counters (State::Result, :88-90).
+//
+// The walk is the generic kernel's (one string per lane, 16-byte chunks through the cp.async ring, fused
+// hot rows in shared memory).  Final hot states carry the highest hot ids, so one running maximum per
+// chunk tells whether any of its 16 steps landed in a final state or left the hot rows; only then is the
+// chunk replayed byte by byte with the counters.  Counters of regexps 0..3 stay in registers, the rest
+// go straight to the string's row in global memory (lane-private, no atomics).
+struct LaneCounts {
+    uint32_t c0, c1, c2, c3;
+    uint32_t* row;
+};
+
+__device__ __forceinline__ void Bump(const ScanArgs& a, uint32_t H, uint32_t s, LaneCounts& c)
+{
+    const bool final = s < H ? s >= a.first_final_hot : (__ldg(a.flags + s) & 1u) != 0;
+    if (!final)
+        return;
+    uint32_t k = __ldg(a.acc_begin + s);
+    const uint32_t e = __ldg(a.acc_begin + s + 1);
+    for (; k < e; ++k) {
+        const uint32_t id = __ldg(a.acc_ids + k);
+        c.c0 += id == 0;
+        c.c1 += id == 1;
+        c.c2 += id == 2;
+        c.c3 += id == 3;
+        if (id >= 4)
+            c.row[id] += 1;
+    }
+}
+
+__device__ __forceinline__ uint32_t FullNext(const Tables& t, uint32_t s, uint32_t letter)
+{
+    size_t at = (size_t) s * t.letters + letter;
+    return t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at) : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
+}
+
+__device__ __forceinline__ void CountChunk16(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, LaneCounts& c)
+{
+    const uint32_t before = s.g;
+    uint32_t g = s.g, top = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+        FastStep<false>(t, g, word, 0x5540);
+        top = max(top, g);
+        FastStep<false>(t, g, word, 0x5541);
+        top = max(top, g);
+        FastStep<false>(t, g, word, 0x5542);
+        top = max(top, g);
+        FastStep<false>(t, g, word, 0x5543);
+        top = max(top, g);
+    }
+    if (top < a.first_final_hot) {           // sixteen steps through non-final hot states: nothing to count
+        s.g = g;
+        return;
+    }
+    uint32_t full = before == t.H ? s.cold : before;
+    EdgeBytes eb(v, 0);
+    for (int k = 0; k < 16; ++k) {
+        full = SlowStep(t, full, eb.Next());
+        Bump(a, t.H, full, c);
+    }
+    SetFull(t, s, full);
+}
+
+__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = 0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    const uint32_t stage = SmemAddr(sv.stage) + (((threadIdx.x >> 5) * kStageSlots) * 32 + lane) * 16;
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
+    const uintptr_t buf_hi = buf_lo + (a.offsets ? a.offsets[a.n] - a.trim : a.n * a.fixed_len);
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        uint64_t b = 0, e = 0;
+        if (valid) {
+            if (a.offsets) {
+                b = a.offsets[i];
+                e = a.offsets[i + 1] - a.trim;
+            } else {
+                b = i * a.fixed_len;
+                e = b + a.fixed_len;
+            }
+        }
+        const uint8_t* p = a.corpus + b;
+        const uint8_t* end = a.corpus + e;
+
+        LaneCounts c;
+        c.c0 = c.c1 = c.c2 = c.c3 = 0;
+        c.row = a.counts + (valid ? i : 0) * a.regexps;
+        uint32_t full = a.initial;
+        if (valid) {
+            Bump(a, t.H, full, c);                                  // Initialize ends in TakeAction, half_final.h:136-141
+            if (a.with_begin) {
+                full = FullNext(t, full, a.begin_class);            // Step(BeginMark), run.h:50-57
+                Bump(a, t.H, full, c);
+            }
+        }
+        {
+            const uint32_t misalign = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
+            if (p < end && misalign != 0) {
+                const uint64_t room = (uint64_t) (end - p);
+                const uint32_t nhead = room < 16 - misalign ? (uint32_t) room : 16 - misalign;
+                const uint8_t* chunk = p - misalign;
+                if (reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi) {
+                    EdgeBytes eb(LoadEdge16(chunk), misalign);
+                    for (uint32_t k = 0; k < nhead; ++k) {
+                        full = SlowStep(t, full, eb.Next());
+                        Bump(a, t.H, full, c);
+                    }
+                } else {
+                    for (uint32_t k = 0; k < nhead; ++k) {
+                        full = SlowStep(t, full, p[k]);
+                        Bump(a, t.H, full, c);
+                    }
+                }
+                p += nhead;
+            }
+        }
+        LaneState s;
+        SetFull(t, s, full);
+        const uint32_t chunks = (uint32_t) ((end - p) >> 4);
+#pragma unroll
+        for (int j = 0; j < kStageSlots; ++j) {
+            if ((uint32_t) j < chunks)
+                CopyAsync16(stage + j * 512, p + 16 * j);
+            CopyAsyncCommit();
+        }
+        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += kStageSlots) {
+#pragma unroll
+            for (int j = 0; j < kStageSlots; ++j) {
+                CopyAsyncWait<kStageSlots - 1>();
+                const uint4 v = LoadShared16(stage + j * 512);
+                if (k + kStageSlots + j < chunks)
+                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
+                CopyAsyncCommit();
+                if (k + j < chunks)
+                    CountChunk16(a, t, s, v, c);
+            }
+        }
+        CopyAsyncWait<0>();
+        full = FullState(t, s);
+        p += 16 * (size_t) chunks;
+        if (p < end) {
+            const uint32_t ntail = (uint32_t) (end - p);
+            if (reinterpret_cast<uintptr_t>(p) + 16 <= buf_hi) {
+                EdgeBytes eb(LoadEdge16(p), 0);
+                for (uint32_t k = 0; k < ntail; ++k) {
+                    full = SlowStep(t, full, eb.Next());
+                    Bump(a, t.H, full, c);
+                }
+            } else {
+                for (uint32_t k = 0; k < ntail; ++k) {
+                    full = SlowStep(t, full, p[k]);
+                    Bump(a, t.H, full, c);
+                }
+            }
+        }
+        if (valid && a.through_end) {
+            full = FullNext(t, full, a.end_class);                   // Step(EndMark)
+            Bump(a, t.H, full, c);
+        }
+        const bool final = valid && (__ldg(a.flags + full) & 1u) != 0;
+        const unsigned matched = __ballot_sync(0xffffffffu, final);
+        if (a.match_bits && lane == 0)
+            a.match_bits[unit] = matched;
+        if (valid) {
+            c.row[0] += c.c0;
+            if (a.regexps > 1) c.row[1] += c.c1;
+            if (a.regexps > 2) c.row[2] += c.c2;
+            if (a.regexps > 3) c.row[3] += c.c3;
+        }
+    }
+}
+
 // Visit counter for pire_gpu_scanner_tune: how many input bytes are consumed in
 // each state (new numbering).  Run-length compressed so that a lane resting in
 // one state issues one atomic per stay, not one per byte.
@@ -967,6 +1163,30 @@ cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStrea
         return err;
     const size_t shared = GenericSharedBytes(a.hot);
     uint64_t want = (a.n + kBlock - 1) / kBlock;
+    int grid = (int) (want < (uint64_t) sms * kGenericBlocksPerSM ? want : (uint64_t) sms * kGenericBlocksPerSM);
+    void* args[] = {const_cast<ScanArgs*>(&a)};
+    err = cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, shared, stream);
+    if (err == cudaSuccess)
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    return err;
+}
+
+
+cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream)
+{
+    if (a.n == 0)
+        return cudaSuccess;
+    const void* fn = reinterpret_cast<const void*>(&CountKernel);
+    int optin = 0, sms = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err == cudaSuccess)
+        err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err != cudaSuccess)
+        return err;
+    const size_t shared = GenericSharedBytes(a.hot);
+    const uint64_t want = ((a.n + 31) / 32 + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int grid = (int) (want < (uint64_t) sms * kGenericBlocksPerSM ? want : (uint64_t) sms * kGenericBlocksPerSM);
     void* args[] = {const_cast<ScanArgs*>(&a)};
     err = cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, shared, stream);

@@ -45,6 +45,15 @@ struct ScanArgs {
     uint32_t end_class;          // prefix kernels: letter class of EndMark
     uint32_t through_end;        // prefix kernels: step EndMark after the bytes
     uint32_t* prefix_len;        // prefix kernels: n words, 0xFFFFFFFF = no accepted prefix
+    // counting kernel (HalfFinalScanner::TakeAction, half_final.h:154-163)
+    const uint32_t* acc_begin;   // [states + 1] CSR of accept lists, new numbering
+    const uint32_t* acc_ids;
+    uint32_t first_final_hot;    // hot ids >= this are final states
+    uint32_t begin_class;        // letter class of BeginMark
+    uint32_t initial;            // Initialize()'s state, new numbering
+    uint32_t with_begin;         // step BeginMark first (with_end == through_end)
+    uint32_t regexps;            // counters per string (>= 1)
+    uint32_t* counts;            // n * regexps words, zeroed by the caller
 };
 
 struct LaunchPlan {
@@ -61,6 +70,7 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
 cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream);
+cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream);
 // d_order <- string indices, longest half-octave length bucket first, corpus order inside a bucket (stable CUB radix sort).
 // stream-ordered scratch from the library's own per-device pool (see scan_kernels.cu)
 cudaError_t ScratchAlloc(void** out, size_t bytes, cudaStream_t stream);

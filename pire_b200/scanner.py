@@ -340,3 +340,41 @@ def LongestPrefix(sc, batch, throughBeginMark=False, throughEndMark=False):
 def ShortestPrefix(sc, batch, throughBeginMark=False, throughEndMark=False):
     """Pire::ShortestPrefix (run.h:294-311) per string: prefix length, or -1 where the reference returns null."""
     return _prefix(sc, batch, True, throughBeginMark, throughEndMark)
+
+
+class HalfFinalResult:
+    """What a batch of HalfFinalScanner states reports (half_final.h:58-120)."""
+
+    def __init__(self, counts, final):
+        self.counts, self.final = counts, final
+
+    def Result(self, i, regexp_id):
+        """State::Result(regexp_id) of string i (half_final.h:88-90)."""
+        return int(self.counts[i, regexp_id])
+
+    def AcceptedRegexps(self, i):
+        """HalfFinalScanner::AcceptedRegexps (half_final.h:130-133): regexps with a non-zero counter."""
+        return [int(r) for r in np.nonzero(self.counts[i])[0]]
+
+    def Final(self, i):
+        return bool(self.final[i])
+
+
+def HalfFinalCount(sc, batch, begin=True, end=True):
+    """Per string: Initialize; [Step(BeginMark)]; Run; [Step(EndMark)] of a Pire::HalfFinalScanner
+    (half_final.h:136-163, driven as tests/count_ut.cpp:54-63 does) -> HalfFinalResult with
+    counts[n, regexps] (numpy u32) and final[n] (bool).  `sc` is a Scanner loaded from the
+    HalfFinalScanner's Save() stream."""
+    torch = _torch()
+    regs = max(1, sc.RegexpsCount())
+    counts = torch.empty((batch.n, regs), dtype=torch.int32, device=batch.device)
+    bits = torch.zeros((batch.n + 31) // 32, dtype=torch.int32, device=batch.device)
+    flags = (N.RUN_BEGIN if begin else 0) | (N.RUN_END if end else 0) | (N.RUN_LINES if batch.trim else 0)
+    stream = torch.cuda.current_stream(batch.device).cuda_stream
+    N.check(N.lib.pire_gpu_count_batch(sc._h, batch.corpus.data_ptr(),
+                                       batch.offsets.data_ptr() if batch.offsets is not None else None,
+                                       batch.fixed_len, batch.n, flags, counts.data_ptr(), bits.data_ptr(), stream),
+            "pire_gpu_count_batch")
+    words = bits.cpu().numpy().view(np.uint32)
+    final = ((words[np.arange(batch.n) // 32] >> (np.arange(batch.n) % 32).astype(np.uint32)) & 1).astype(bool)
+    return HalfFinalResult(counts.cpu().numpy().view(np.uint32), final)

@@ -47,7 +47,31 @@ def load_golden_prefix():
                 for c in json.load(f)["prefix_cases"]]
 
 
+class CountCase:
+    """count_ut.cpp HalfFinal@553: the glue of the five HalfFinalFsm counters of one pattern."""
+
+    def __init__(self, d):
+        import lzma
+        self.pattern = bytes.fromhex(d["pattern"])
+        self.image = lzma.decompress(base64.b64decode(d["image_xz"]))
+        self.strings = [bytes.fromhex(s) for s in d["strings"]]
+        self.counts, self.final, self.expect = d["counts"], d["final"], d["expect"]
+        self.states, self.regexps = d["states"], d["regexps"]
+        self.single = None
+        if "single" in d:
+            self.single = (lzma.decompress(base64.b64decode(d["single"]["image_xz"])), d["single"]["counts"], d["single"]["final"])
+
+    def __repr__(self):
+        return "CountCase(%r, %r)" % (self.pattern, self.strings[0])
+
+
+def load_golden_counts():
+    with open(os.path.join(HERE, "golden", "pire_golden.json")) as f:
+        return [CountCase(c) for c in json.load(f)["count_cases"]]
+
+
 GOLDEN = load_golden()
+GOLDEN_COUNTS = load_golden_counts()
 GOLDEN_PREFIX = load_golden_prefix()
 
 

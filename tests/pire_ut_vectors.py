@@ -103,3 +103,22 @@ PREFIX_CASES = [
     # ScanTermination@475: "aaa" over "aaab\0": the scan must stop in the dead state; longest prefix = 3
     (b"aaa", b"aaab\0", 3, 3),
 ]
+
+
+# tests/count_ut.cpp:540-551 (TestHalfFinalCount) and :562-576 (TestHalfFinalSerialization): pattern (UTF-8 lexer, no
+# Surround), text, and Result(0) of the five HalfFinalFsm counters in the order of MakeHalfFinalCount (:503-520):
+# MakeGreedyCounter(true), MakeGreedyCounter(false), MakeNonGreedyCounter(true,true), (true,false), (false).
+# The glued scanner of all five must report the same numbers as Result(0..4) (:533-537).
+COUNT_CASES = [
+    (b"ab+", b"abbabbbabbbbbb", [3, 3, 3, 11, 3]),
+    (b"(ab)+", b"ababbababbab", [3, 3, 5, 5, 5]),
+    (b"(abab)+", b"ababababab", [1, 1, 4, 4, 2]),
+    (b"ab+c|b", b"abbbbbbbbbb", [1, 10, 10, 10, 10]),
+    (b"ab+c|b", b"abbbbbbbbbbb", [1, 10, 11, 11, 11]),
+    (b"ab+c|b", b"abbbbbbbbbbc", [1, 1, 10, 11, 10]),
+    (b"ab+c|b", b"abbbbbbbbbbbc", [1, 1, 11, 12, 11]),
+    (b"a\\w+c|b", b"abbbdbbbdbbc", [1, 1, 8, 9, 8]),
+    (b"a\\w+c|b", b"abbbdbbbdbb", [1, 8, 8, 8, 8]),
+    (b"a[a-z]+c|b", b"abeeeebeeeeeeeeeceeaeebeeeaeecceebeeaeebeeb", [2, 4, 7, 9, 7]),
+    (b"(\\w\\w)+", b"ab abbb ababa a", [3, 3, 8, 8, 5]),
+]

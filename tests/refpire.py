@@ -99,6 +99,43 @@ class RefScanner:
         return final, mask, state
 
 
+class RefHalfFinal:
+    """A reference HalfFinalScanner (pire/scanners/half_final.h)."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.pref_hf_free(self._h)
+            self._h = None
+
+    empty = property(lambda s: bool(s._lib.pref_hf_empty(s._h)))
+    size = property(lambda s: s._lib.pref_hf_size(s._h))
+    regexps = property(lambda s: s._lib.pref_hf_regexps_count(s._h))
+
+    def save(self):
+        n = self._lib.pref_hf_save(self._h, None, 0)
+        buf = (C.c_uint8 * n)()
+        self._lib.pref_hf_save(self._h, buf, n)
+        return bytes(buf)
+
+    def count(self, corpus, offsets=None, fixed_len=0, n=None, begin=True, end=True, threads=1):
+        """tests/count_ut.cpp:54-63 per string: (counts[n, regexps] u32, final[n] u8)."""
+        corpus = np.ascontiguousarray(corpus, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            n = len(offsets) - 1 if n is None else n
+        elif n is None:
+            n = len(corpus) // fixed_len if fixed_len else 0
+        counts = np.zeros((n, max(1, self.regexps)), np.uint32)
+        final = np.zeros(n, np.uint8)
+        rc = self._lib.pref_hf_count_batch(self._h, _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n, int(begin), int(end),
+                                           threads, _ptr(counts, u32p), _ptr(final, u8p))
+        assert rc == 0
+        return counts, final
+
+
 class Ref:
     def __init__(self):
         if not have_ref():
@@ -127,7 +164,36 @@ class Ref:
         lib.pref_prefix_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                           C.POINTER(C.c_int64)]
         lib.pref_hardware_threads.restype = C.c_uint
+        lib.pref_hf_compile.restype = C.c_void_p
+        lib.pref_hf_compile.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        lib.pref_hf_glue.restype = C.c_void_p
+        lib.pref_hf_glue.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        lib.pref_hf_free.argtypes = [C.c_void_p]
+        lib.pref_hf_empty.argtypes = [C.c_void_p]
+        for f in ("pref_hf_size", "pref_hf_regexps_count"):
+            getattr(lib, f).restype = C.c_uint64
+            getattr(lib, f).argtypes = [C.c_void_p]
+        lib.pref_hf_save.restype = C.c_uint64
+        lib.pref_hf_save.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.pref_hf_count_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, u32p, u8p]
         self.lib = lib
+
+    def compile_half_final(self, pattern, opts="", mode=0):
+        """mode 0 = HalfFinalScanner(fsm); 1..5 = the counters of count_ut.cpp:503-520."""
+        if isinstance(pattern, str):
+            pattern = pattern.encode("latin-1")
+        err = C.create_string_buffer(512)
+        h = self.lib.pref_hf_compile(pattern, opts.encode(), mode, err, len(err))
+        if not h:
+            raise ValueError(err.value.decode(errors="replace"))
+        return RefHalfFinal(self.lib, h)
+
+    def glue_half_final(self, a, b, max_size=0):
+        err = C.create_string_buffer(512)
+        h = self.lib.pref_hf_glue(a._h, b._h, max_size, err, len(err))
+        if not h:
+            raise ValueError(err.value.decode(errors="replace"))
+        return RefHalfFinal(self.lib, h)
 
     def compile(self, pattern, opts=""):
         if isinstance(pattern, str):
@@ -186,6 +252,9 @@ class Oracle:
             lib.pire_oracle_prefix_batch.restype = None
             lib.pire_oracle_prefix_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64, C.c_int,
                                                      C.c_int, C.c_int, C.POINTER(C.c_int64)]
+            lib.pire_oracle_count_batch.restype = None
+            lib.pire_oracle_count_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64, C.c_int,
+                                                    C.c_int, u32p, u8p]
             Oracle._lib = lib
         # keep an 8-byte aligned private copy alive for the views
         self._buf = np.frombuffer(bytes(image) + b"\0" * 8, dtype=np.uint8).copy()
@@ -212,6 +281,21 @@ class Oracle:
                                           int(begin), int(end), int(shortcuts), _ptr(final, u8p), _ptr(mask, u32p),
                                           _ptr(state, u32p))
         return final, mask, state
+
+
+def oracle_count(orc, corpus, offsets=None, fixed_len=0, n=None, begin=True, end=True):
+    """HalfFinalScanner counting through the oracle port: (counts[n, regexps], final[n])."""
+    corpus = np.ascontiguousarray(corpus, dtype=np.uint8)
+    if offsets is not None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1 if n is None else n
+    elif n is None:
+        n = len(corpus) // fixed_len if fixed_len else 0
+    counts = np.zeros((n, max(1, orc.regexps)), np.uint32)
+    final = np.zeros(n, np.uint8)
+    Oracle._lib.pire_oracle_count_batch(C.byref(orc._sc), _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n, int(begin),
+                                        int(end), _ptr(counts, u32p), _ptr(final, u8p))
+    return counts, final
 
 
 def oracle_prefix(orc, corpus, offsets=None, fixed_len=0, n=None, shortest=False, through_begin=False, through_end=False):

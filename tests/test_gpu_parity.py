@@ -508,3 +508,81 @@ def test_lines_front_end(cuda_device, ref):
     assert empty.n == 0
     one = P.Batch.from_text(torch.from_numpy(np.frombuffer(b"\n", np.uint8).copy()).to("cuda:0"))
     assert one.n == 1 and P.Runner(sc).Begin().Run(one).End().Matches().tolist() == [False]
+
+
+def test_half_final_counts_golden(cuda_device):
+    """pire_gpu_count_batch against the numbers of count_ut.cpp HalfFinal@553 (committed fixtures)."""
+    import pire_b200 as P
+    from conftest import GOLDEN_COUNTS
+    for case in GOLDEN_COUNTS:
+        for max_hot in (255, 3):
+            sc = P.Scanner(case.image, cuda_device)
+            sc.set_max_hot(max_hot)
+            res = P.HalfFinalCount(sc, P.Batch.from_strings(case.strings))
+            assert res.counts[0].tolist() == case.expect, (case, max_hot)
+            assert res.counts.tolist() == case.counts and res.final.astype(int).tolist() == case.final, (case, max_hot)
+            assert res.AcceptedRegexps(0) == [r for r, c in enumerate(case.expect) if c]
+        if case.single:
+            image, want, fin = case.single
+            res = P.HalfFinalCount(P.Scanner(image, cuda_device), P.Batch.from_strings(case.strings))
+            assert res.counts[:, 0].tolist() == want and res.final.astype(int).tolist() == fin
+
+
+def test_half_final_counts_vs_reference(cuda_device, ref):
+    """Random text, long and short strings, all mark combinations, hot sets small enough to force cold
+    states, more than four glued counters (the register / global counter split), fixed-length batches."""
+    import torch
+    import pire_b200 as P
+    from refpire import oracle_count
+    rng = np.random.default_rng(44)
+    alphabet = np.frombuffer(b"abcde z", np.uint8)
+    for pat in (b"ab+", b"(ab)+", b"ab+c|b", rb"a\w+c|b", b"[a-c]+", rb"(\w\w)+"):
+        scs = [ref.compile_half_final(pat, "un", mode) for mode in (1, 2, 3, 4, 5)]
+        glued = scs[0]
+        for sc in scs[1:] + [scs[3], scs[1]]:               # 7 counters
+            glued = ref.glue_half_final(glued, sc)
+        assert not glued.empty and glued.regexps == 7
+        strs = [bytes(rng.choice(alphabet, size=int(k))) for k in rng.integers(0, 300, size=600)]
+        strs += [bytes(rng.choice(alphabet, size=int(k))) for k in (4096, 5000, 15, 16, 17, 31, 32, 33)]
+        corpus, offs = csr(strs)
+        batch = P.Batch.from_strings(strs)
+        for ref_sc in (glued, scs[3], ref.compile_half_final(pat, "u", 0)):
+            image = ref_sc.save()
+            orc = Oracle(image)
+            for max_hot in (255, 2):
+                sc = P.Scanner(image, cuda_device)
+                sc.set_max_hot(max_hot)
+                for begin, end in ((True, True), (False, False), (True, False), (False, True)):
+                    want, wfin = ref_sc.count(corpus, offs, begin=begin, end=end)
+                    res = P.HalfFinalCount(sc, batch, begin=begin, end=end)
+                    assert (res.counts == want).all(), (pat, max_hot, begin, end, np.argwhere(res.counts != want)[:4])
+                    assert (res.final == wfin.astype(bool)).all()
+                    got, _ = oracle_count(orc, corpus, offs, begin=begin, end=end)
+                    assert (got == want).all()
+    # fixed-length strings, tuned hot rows
+    ref_sc = ref.compile_half_final(b"ab+c|b", "un", 4)
+    sc = P.Scanner(ref_sc.save(), cuda_device)
+    host = rng.choice(np.frombuffer(b"abc ", np.uint8), size=(6000, 96)).reshape(-1)
+    batch = P.Batch(torch.from_numpy(host).to("cuda:0"), fixed_len=96, n=6000)
+    want, wfin = ref_sc.count(host, fixed_len=96, n=6000)
+    for tuned in (False, True):
+        if tuned:
+            sc.Tune(batch, 6000)
+        res = P.HalfFinalCount(sc, batch)
+        assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all()
+
+
+def test_half_final_scanner_matches_like_scanner(cuda_device, ref):
+    """A HalfFinalScanner image through the ordinary run entry point: pire_ut.cpp runs its Matches() vectors on
+    HalfFinalScanner too (TestGlue@701-704, Serialization@576-579); Final() must agree with the reference's."""
+    import pire_b200 as P
+    rng = np.random.default_rng(45)
+    for pat, opts in ((b"regexp", ""), (b"a.*b", ""), (b"^abc$", ""), (b"hello\\s+w.+d$", "")):
+        ref_sc = ref.compile_half_final(pat, opts, 0)
+        strs = [b"regexp", b"regxp", b"regexp t", b"abc", b"xabcx", b"hello  world", b"a--b", b""]
+        strs += [bytes(rng.choice(np.frombuffer(b"abcreg xp", np.uint8), size=int(k))) for k in rng.integers(0, 80, size=200)]
+        corpus, offs = csr(strs)
+        _, wfin = ref_sc.count(corpus, offs)
+        sc = P.Scanner(ref_sc.save(), cuda_device)
+        final, _, _ = gpu_run(sc, strs)
+        assert (final == wfin).all(), pat

@@ -101,3 +101,40 @@ def test_oracle_prefix_scans_vs_reference_live(ref):
                     want = sc.prefix(corpus, offs, shortest=shortest, through_begin=tb, through_end=te, variant=2)
                     got = oracle_prefix(orc, corpus, offs, shortest=shortest, through_begin=tb, through_end=te)
                     assert (got == want).all(), (pat, tb, te, shortest)
+
+
+def test_oracle_half_final_counts_match_golden():
+    """count_ut.cpp HalfFinal@553 / HalfFinalSerialization@578: Result(0..4) of the glued counters."""
+    from conftest import GOLDEN_COUNTS
+    from refpire import oracle_count
+    for case in GOLDEN_COUNTS:
+        orc = Oracle(case.image)
+        assert (orc.states, orc.regexps) == (case.states, case.regexps)
+        corpus, offs = csr(case.strings)
+        counts, final = oracle_count(orc, corpus, offs)
+        assert counts[0].tolist() == case.expect                 # the number written in the reference's test
+        assert counts.tolist() == case.counts and final.tolist() == case.final
+        if case.single:
+            image, want, fin = case.single
+            counts, final = oracle_count(Oracle(image), corpus, offs)
+            assert counts[:, 0].tolist() == want and final.tolist() == fin
+
+
+def test_oracle_half_final_vs_reference_live(ref):
+    """All five counters, their glue and the plain HalfFinalScanner(fsm), every mark combination."""
+    from pire_ut_vectors import COUNT_CASES
+    from refpire import oracle_count
+    rng = np.random.default_rng(5)
+    for pat in sorted({p for p, _, _ in COUNT_CASES}):
+        scs = [ref.compile_half_final(pat, "un", mode) for mode in (1, 2, 3, 4, 5)]
+        glued = scs[0]
+        for sc in scs[1:]:
+            glued = ref.glue_half_final(glued, sc)
+        strs = [bytes(rng.choice(np.frombuffer(b"abcde z", np.uint8), size=int(k))) for k in rng.integers(0, 120, size=150)]
+        corpus, offs = csr(strs)
+        for sc in scs + [glued, ref.compile_half_final(pat, "u", 0)]:
+            orc = Oracle(sc.save())
+            for begin, end in ((True, True), (False, False), (True, False), (False, True)):
+                want, wfin = sc.count(corpus, offs, begin=begin, end=end)
+                got, gfin = oracle_count(orc, corpus, offs, begin=begin, end=end)
+                assert (want == got).all() and (wfin == gfin).all(), (pat, begin, end)
