@@ -359,6 +359,20 @@ void* pref_hf_glue(void* a, void* b, size_t maxSize, char* err, size_t errlen)
 	}
 }
 
+// Scanner::Load (multi.h:575-599) of a stored HalfFinalScanner image (it inherits Save/Load from Scanner).
+void* pref_hf_load(const void* image, size_t size, char* err, size_t errlen)
+{
+	try {
+		std::istringstream in(std::string((const char*) image, size));
+		RefHalfFinal* h = new RefHalfFinal;
+		h->sc.Load(&in);
+		return h;
+	} catch (std::exception& e) {
+		SetErr(err, errlen, e.what());
+		return nullptr;
+	}
+}
+
 void pref_hf_free(void* h) { delete (RefHalfFinal*) h; }
 int pref_hf_empty(void* h) { return ((RefHalfFinal*) h)->sc.Empty() ? 1 : 0; }
 uint64_t pref_hf_size(void* h) { return ((RefHalfFinal*) h)->sc.Size(); }

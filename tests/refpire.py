@@ -168,6 +168,8 @@ class Ref:
         lib.pref_hf_compile.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         lib.pref_hf_glue.restype = C.c_void_p
         lib.pref_hf_glue.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        lib.pref_hf_load.restype = C.c_void_p
+        lib.pref_hf_load.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         lib.pref_hf_free.argtypes = [C.c_void_p]
         lib.pref_hf_empty.argtypes = [C.c_void_p]
         for f in ("pref_hf_size", "pref_hf_regexps_count"):
@@ -184,6 +186,14 @@ class Ref:
             pattern = pattern.encode("latin-1")
         err = C.create_string_buffer(512)
         h = self.lib.pref_hf_compile(pattern, opts.encode(), mode, err, len(err))
+        if not h:
+            raise ValueError(err.value.decode(errors="replace"))
+        return RefHalfFinal(self.lib, h)
+
+    def load_half_final(self, image):
+        """Scanner::Load of a stored HalfFinalScanner image."""
+        err = C.create_string_buffer(512)
+        h = self.lib.pref_hf_load(bytes(image), len(image), err, len(err))
         if not h:
             raise ValueError(err.value.decode(errors="replace"))
         return RefHalfFinal(self.lib, h)

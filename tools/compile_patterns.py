@@ -36,6 +36,25 @@ def main():
         print("%s: %d patterns -> %d states x %d letters, image %d bytes (%d compressed)"
               % (name, len(pats), sc.size, sc.letters, len(img), os.path.getsize(path)))
 
+    # HalfFinalScanner images (pire/scanners/half_final.h) for the counting entry point:
+    #  hf_glue10     the same ten patterns, each as HalfFinalScanner(fsm), glued (half_final.h:196-198)
+    #  count_words5  the five HalfFinalFsm counters of tests/count_ut.cpp:503-520 for [a-z]+, glued
+    hf = None
+    for pat, opts in ns["GLUE10"]:
+        one = ref.compile_half_final(pat, opts, 0)
+        hf = one if hf is None else ref.glue_half_final(hf, one)
+    words = None
+    for mode in (1, 2, 3, 4, 5):
+        one = ref.compile_half_final(b"[a-z]+", "n", mode)
+        words = one if words is None else ref.glue_half_final(words, one)
+    for name, sc in (("hf_glue10", hf), ("count_words5", words)):
+        assert not sc.empty
+        img = sc.save()
+        path = os.path.join(out, name + ".pire.xz")
+        with open(path, "wb") as f:
+            f.write(lzma.compress(img, preset=9))
+        print("%s: %d states, %d regexps, image %d bytes (%d compressed)" % (name, sc.size, sc.regexps, len(img), os.path.getsize(path)))
+
 
 if __name__ == "__main__":
     main()
