@@ -154,6 +154,16 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc,
  * The image is the Save() stream of the HalfFinalScanner (it inherits Scanner::Save; the same format).
  * d_counts: n rows of max(1, regexps) u32, row i for string i (overwritten).  d_match_bits: packed
  * Final(st) per string, may be null.  Counters are 32 bits wide (the reference's are size_t). */
+/* How pire_gpu_count_batch keeps the counters (results are identical; for tests and measurements).
+ * AUTO: packed per-state increments when the automaton has at most 16 regexps, behind a look-ahead pass
+ * that skips chunks without final states -- or on every chunk when pire_gpu_scanner_tune saw more than
+ * 2.5 % of the sample's steps end in a final state; the accept lists otherwise. */
+#define PIRE_GPU_COUNT_AUTO        0u
+#define PIRE_GPU_COUNT_LISTS       1u
+#define PIRE_GPU_COUNT_PACKED      2u
+#define PIRE_GPU_COUNT_EVERY_CHUNK 3u
+int pire_gpu_scanner_set_count_mode(pire_gpu_scanner* sc, uint32_t mode);
+
 int pire_gpu_count_batch(const pire_gpu_scanner* sc,
                          const uint8_t* d_corpus, const uint64_t* d_offsets,
                          uint64_t fixed_len, uint64_t n, uint32_t flags,

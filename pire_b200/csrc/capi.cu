@@ -56,6 +56,7 @@ struct DeviceTables {
     uint8_t* flags = nullptr;
     uint32_t* acc_begin = nullptr;
     uint32_t* acc_ids = nullptr;
+    uint64_t* weights = nullptr;
     size_t full_bytes = 0;
 
     void Free()
@@ -71,6 +72,7 @@ struct DeviceTables {
         cudaFree(flags);
         cudaFree(acc_begin);
         cudaFree(acc_ids);
+        cudaFree(weights);
         *this = DeviceTables();
     }
 };
@@ -87,6 +89,10 @@ struct pire_gpu_scanner {
     uint32_t max_hot = kMaxHot;
     bool tuned = false;
     bool priv_ok = false;
+    // counting kernel: 0 = automatic, 1 = accept lists, 2 = packed increments behind the look-ahead pass,
+    // 3 = packed increments on every chunk (pire_gpu_scanner_set_count_mode; for tests and experiments)
+    uint32_t count_mode = 0;
+    double final_share = 0.0;       // share of a tune sample's steps that ended in a final state
     std::vector<uint32_t> hot_order;
     LaunchPlan plan[4][2];          // [variant][uniform]
 
@@ -151,6 +157,9 @@ int Upload(pire_gpu_scanner* sc)
     CUDA_TRY(cudaMalloc(&d.acc_ids, t.acc_ids_new.size() * 4 + 4));
     if (!t.acc_ids_new.empty())
         CUDA_TRY(cudaMemcpy(d.acc_ids, t.acc_ids_new.data(), t.acc_ids_new.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d.weights, t.weights.size() * 8 + 8));
+    if (!t.weights.empty())
+        CUDA_TRY(cudaMemcpy(d.weights, t.weights.data(), t.weights.size() * 8, cudaMemcpyHostToDevice));
     sc->priv_ok = false;
     for (int v = kVariantPlain; v <= kVariantPriv; ++v)
         for (int u = 0; u < 2; ++u) {
@@ -311,6 +320,14 @@ int pire_gpu_scanner_set_max_hot(pire_gpu_scanner* sc, uint32_t max_hot_rows)
     return Upload(sc);
 }
 
+int pire_gpu_scanner_set_count_mode(pire_gpu_scanner* sc, uint32_t mode)
+{
+    if (!sc || mode > PIRE_GPU_COUNT_EVERY_CHUNK)
+        return Fail(PIRE_GPU_EINVAL, "bad count mode");
+    sc->count_mode = mode;
+    return PIRE_GPU_OK;
+}
+
 int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
                        uint64_t fixed_len, uint64_t n, uint32_t flags,
                        uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)
@@ -394,6 +411,9 @@ int pire_gpu_count_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, co
     a.regexps = sc->dfa.regexps ? sc->dfa.regexps : 1;
     a.counts = d_counts;
     a.match_bits = d_match_bits;
+    a.weights = sc->dev.weights;
+    a.count_words = sc->count_mode == 1 ? 0 : sc->tab.count_words;
+    a.count_always = (sc->count_mode == 3 || (sc->count_mode == 0 && sc->final_share > 0.025)) ? 1 : 0;
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t) n * a.regexps * 4, st));
     CUDA_TRY(LaunchCount(a, sc->device, st));
     return PIRE_GPU_OK;
@@ -600,6 +620,13 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc, const uint8_t* d_corpus, const u
     for (uint32_t ns = 0; ns < sc->tab.states; ++ns)
         by_old[sc->tab.old_of_new[ns]] = by_new[ns];
     sc->hot_order = HotOrderFromCounts(sc->dfa, by_old);
+    uint64_t steps = 0, in_final = 0;
+    for (uint32_t s = 0; s < sc->dfa.states; ++s) {
+        steps += by_old[s];
+        if (sc->dfa.Final(s))
+            in_final += by_old[s];
+    }
+    sc->final_share = steps ? (double) in_final / (double) steps : 0.0;
     sc->tuned = true;
     Rebuild(sc);
     return Upload(sc);

@@ -194,6 +194,23 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
     }
     t.acc_begin_new[dfa.states] = (uint32_t) t.acc_ids_new.size();
 
+    const uint32_t regs = std::max<uint32_t>(1, dfa.regexps);
+    t.count_words = regs <= 16 ? (regs + 7) / 8 : 0;
+    t.weights.assign((size_t) dfa.states * t.count_words, 0);
+    for (uint32_t ns = 0; ns < dfa.states && t.count_words; ++ns) {
+        uint32_t times[16] = {0};
+        for (uint32_t k = t.acc_begin_new[ns]; k < t.acc_begin_new[ns + 1]; ++k)
+            ++times[t.acc_ids_new[k]];
+        for (uint32_t r = 0; r < regs; ++r) {
+            if (times[r] > 15) {
+                t.count_words = 0;
+                t.weights.clear();
+                break;
+            }
+            t.weights[(size_t) ns * t.count_words + r / 8] |= (uint64_t) times[r] << (8 * (r % 8));
+        }
+    }
+
     t.start[0] = t.new_of_old[dfa.initial];                              // Initialize(), multi.h:161
     t.start[1] = t.new_of_old[dfa.Next(dfa.initial, kBeginMark)];        // Begin(), run.h:375
 }

@@ -62,6 +62,12 @@ struct ScanTables {
     uint32_t initial = 0;                    // new id of Initialize()'s state
     std::vector<uint32_t> acc_begin_new;     // [states + 1]
     std::vector<uint32_t> acc_ids_new;
+    // The same lists as packed per-state increments: weights[s * count_words + j] holds, 8 bits each, how
+    // often regexps 8j..8j+7 are listed for state s (0 for a non-final state), so TakeAction is one 64-bit
+    // add per word.  count_words = 0 when the automaton does not fit (more than 16 regexps, or a regexp
+    // listed more than 15 times for one state); the kernel then walks the lists.
+    uint32_t count_words = 0;
+    std::vector<uint64_t> weights;
 
     // Lane-private rows (kernel variant PRIV): the first priv_rows-1 hot ids, plus a sink
     // row (id priv_rows-1) that absorbs every transition into a non-private state.  Only

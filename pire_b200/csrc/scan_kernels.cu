@@ -791,32 +791,113 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
 // final.  The per-string result is the vector of counters (State::Result, :88-90).
 //
 // The walk is the generic kernel's (one string per lane, 16-byte chunks through the cp.async ring, fused
-// hot rows in shared memory).  Final hot states carry the highest hot ids, so one running maximum per
-// chunk tells whether any of its 16 steps landed in a final state or left the hot rows; only then is the
-// chunk replayed byte by byte with the counters.  Counters of regexps 0..3 stay in registers, the rest
-// go straight to the string's row in global memory (lane-private, no atomics).
-struct LaneCounts {
-    uint32_t c0, c1, c2, c3;
+// hot rows in shared memory).  Two ways to keep the counters, chosen per automaton on the host:
+//  * packed (kWords = 1 or 2, up to 16 regexps): every state has its increments as 8-bit fields of one
+//    or two 64-bit words (zero for non-final states; the hot states' words sit in shared memory), so
+//    TakeAction is an unconditional 64-bit add per word.  Fields are widened to 16 bits after every
+//    chunk and written to the string's row of counters every 120 chunks, before they can wrap;
+//  * lists (kWords = 0): the accept list of a final state is walked; counters 0..3 in registers, the
+//    rest straight in the string's row in global memory (lane-private, no atomics).
+// Final hot states carry the highest hot ids, so one running maximum per chunk tells whether any of its
+// 16 steps landed in a final state or left the hot rows; if not, the chunk costs what a plain scan costs.
+// When a sample showed final states to be frequent (kAlways) that first pass is skipped and every chunk
+// is counted.
+template <int kWords>
+struct Counter {
+    uint64_t a8[kWords];            // 8 x 8 bits: at most 16 steps x 15 per field between Widen() calls
+    uint64_t even[kWords], odd[kWords];   // 4 x 16 bits each
+    uint32_t groups;
     uint32_t* row;
+    const uint64_t* hot_w;          // shared: (H + 1) * kWords words, the sink's are zero
+    const uint64_t* all_w;          // global: states * kWords
+
+    __device__ __forceinline__ void Reset(const ScanArgs& a, const uint64_t* hot_weights, uint32_t* r)
+    {
+#pragma unroll
+        for (int j = 0; j < kWords; ++j)
+            a8[j] = even[j] = odd[j] = 0;
+        groups = 0;
+        row = r;
+        hot_w = hot_weights;
+        all_w = a.weights;
+    }
+    __device__ __forceinline__ void Step(const ScanArgs&, uint32_t H, uint32_t s)          // TakeAction
+    {
+#pragma unroll
+        for (int j = 0; j < kWords; ++j)
+            a8[j] += s < H ? hot_w[s * kWords + j] : __ldg(all_w + (size_t) s * kWords + j);
+    }
+    __device__ __forceinline__ void Flush(uint32_t regexps)
+    {
+#pragma unroll
+        for (int j = 0; j < kWords; ++j) {
+            for (uint32_t f = 0; f < 8 && j * 8 + f < regexps; ++f) {
+                const uint64_t src = (f & 1) ? odd[j] : even[j];
+                const uint32_t add = (uint32_t) (src >> (16 * (f >> 1))) & 0xffffu;
+                if (add)
+                    row[j * 8 + f] += add;
+            }
+            even[j] = odd[j] = 0;
+        }
+        groups = 0;
+    }
+    __device__ __forceinline__ void EndGroup(uint32_t regexps)      // after at most 16 steps
+    {
+#pragma unroll
+        for (int j = 0; j < kWords; ++j) {
+            even[j] += a8[j] & 0x00FF00FF00FF00FFull;
+            odd[j] += (a8[j] >> 8) & 0x00FF00FF00FF00FFull;
+            a8[j] = 0;
+        }
+        if (++groups >= 120)                                        // 120 x 16 x 15 < 65536
+            Flush(regexps);
+    }
+    __device__ __forceinline__ void Discard()
+    {
+#pragma unroll
+        for (int j = 0; j < kWords; ++j)
+            a8[j] = 0;
+    }
+    __device__ __forceinline__ void Finish(uint32_t regexps) { Flush(regexps); }
 };
 
-__device__ __forceinline__ void Bump(const ScanArgs& a, uint32_t H, uint32_t s, LaneCounts& c)
-{
-    const bool final = s < H ? s >= a.first_final_hot : (__ldg(a.flags + s) & 1u) != 0;
-    if (!final)
-        return;
-    uint32_t k = __ldg(a.acc_begin + s);
-    const uint32_t e = __ldg(a.acc_begin + s + 1);
-    for (; k < e; ++k) {
-        const uint32_t id = __ldg(a.acc_ids + k);
-        c.c0 += id == 0;
-        c.c1 += id == 1;
-        c.c2 += id == 2;
-        c.c3 += id == 3;
-        if (id >= 4)
-            c.row[id] += 1;
+template <>
+struct Counter<0> {
+    uint32_t c0, c1, c2, c3;
+    uint32_t* row;
+
+    __device__ __forceinline__ void Reset(const ScanArgs&, const uint64_t*, uint32_t* r)
+    {
+        c0 = c1 = c2 = c3 = 0;
+        row = r;
     }
-}
+    __device__ __forceinline__ void Step(const ScanArgs& a, uint32_t H, uint32_t s)
+    {
+        const bool final = s < H ? s >= a.first_final_hot : (__ldg(a.flags + s) & 1u) != 0;
+        if (!final)
+            return;
+        uint32_t k = __ldg(a.acc_begin + s);
+        const uint32_t e = __ldg(a.acc_begin + s + 1);
+        for (; k < e; ++k) {
+            const uint32_t id = __ldg(a.acc_ids + k);
+            c0 += id == 0;
+            c1 += id == 1;
+            c2 += id == 2;
+            c3 += id == 3;
+            if (id >= 4)
+                row[id] += 1;
+        }
+    }
+    __device__ __forceinline__ void EndGroup(uint32_t) {}
+    __device__ __forceinline__ void Discard() {}
+    __device__ __forceinline__ void Finish(uint32_t regexps)
+    {
+        row[0] += c0;
+        if (regexps > 1) row[1] += c1;
+        if (regexps > 2) row[2] += c2;
+        if (regexps > 3) row[3] += c3;
+    }
+};
 
 __device__ __forceinline__ uint32_t FullNext(const Tables& t, uint32_t s, uint32_t letter)
 {
@@ -824,40 +905,72 @@ __device__ __forceinline__ uint32_t FullNext(const Tables& t, uint32_t s, uint32
     return t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at) : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
 }
 
-__device__ __forceinline__ void CountChunk16(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, LaneCounts& c)
+template <int kWords, bool kAlways>
+__device__ __forceinline__ void CountChunk16(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, Counter<kWords>& c)
 {
     const uint32_t before = s.g;
-    uint32_t g = s.g, top = 0;
+    if (!kAlways || kWords == 0) {
+        uint32_t g = before, top = 0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
-        FastStep<false>(t, g, word, 0x5540);
-        top = max(top, g);
-        FastStep<false>(t, g, word, 0x5541);
-        top = max(top, g);
-        FastStep<false>(t, g, word, 0x5542);
-        top = max(top, g);
-        FastStep<false>(t, g, word, 0x5543);
-        top = max(top, g);
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+            FastStep<false>(t, g, word, 0x5540);
+            top = max(top, g);
+            FastStep<false>(t, g, word, 0x5541);
+            top = max(top, g);
+            FastStep<false>(t, g, word, 0x5542);
+            top = max(top, g);
+            FastStep<false>(t, g, word, 0x5543);
+            top = max(top, g);
+        }
+        if (top < a.first_final_hot) {       // sixteen steps through non-final hot states: nothing to count
+            s.g = g;
+            return;
+        }
     }
-    if (top < a.first_final_hot) {           // sixteen steps through non-final hot states: nothing to count
-        s.g = g;
-        return;
+    if (kWords > 0 && before != t.H) {
+        // the chunk again (or, kAlways, for the first time) with the packed increments of every state entered
+        uint32_t g = before;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                FastStep<false>(t, g, word, 0x5540 + b);
+                c.Step(a, 0xffffffffu, g);              // g <= H: always the shared copy
+            }
+        }
+        if (g != t.H) {
+            c.EndGroup(a.regexps);
+            s.g = g;
+            return;
+        }
+        // left the hot rows somewhere inside: forget what was added (the sink's increments are zero, but
+        // the steps after the miss were not the real ones) and replay through the complete table
+        c.Discard();
     }
     uint32_t full = before == t.H ? s.cold : before;
     EdgeBytes eb(v, 0);
     for (int k = 0; k < 16; ++k) {
         full = SlowStep(t, full, eb.Next());
-        Bump(a, t.H, full, c);
+        c.Step(a, t.H, full);
     }
+    c.EndGroup(a.regexps);
     SetFull(t, s, full);
 }
-
+template <int kWords, bool kAlways>
 __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv, a.hot8, a.hot);
+    // packed increments of the hot states (and zeros for the sink) behind the staging ring
+    uint64_t* const hot_w = reinterpret_cast<uint64_t*>(sv.stage + kStageBytes);
+    if (kWords > 0) {
+        for (uint32_t i = threadIdx.x; i < (a.hot + 1) * kWords; i += blockDim.x)
+            hot_w[i] = i < a.hot * kWords ? a.weights[i] : 0;
+        __syncthreads();
+    }
 
     Tables t;
     t.hot = sv.hot;
@@ -891,16 +1004,16 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
         const uint8_t* p = a.corpus + b;
         const uint8_t* end = a.corpus + e;
 
-        LaneCounts c;
-        c.c0 = c.c1 = c.c2 = c.c3 = 0;
-        c.row = a.counts + (valid ? i : 0) * a.regexps;
+        Counter<kWords> c;
+        c.Reset(a, hot_w, a.counts + (valid ? i : 0) * a.regexps);
         uint32_t full = a.initial;
         if (valid) {
-            Bump(a, t.H, full, c);                                  // Initialize ends in TakeAction, half_final.h:136-141
+            c.Step(a, t.H, full);                                   // Initialize ends in TakeAction, half_final.h:136-141
             if (a.with_begin) {
                 full = FullNext(t, full, a.begin_class);            // Step(BeginMark), run.h:50-57
-                Bump(a, t.H, full, c);
+                c.Step(a, t.H, full);
             }
+            c.EndGroup(a.regexps);
         }
         {
             const uint32_t misalign = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
@@ -912,14 +1025,15 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
                     EdgeBytes eb(LoadEdge16(chunk), misalign);
                     for (uint32_t k = 0; k < nhead; ++k) {
                         full = SlowStep(t, full, eb.Next());
-                        Bump(a, t.H, full, c);
+                        c.Step(a, t.H, full);
                     }
                 } else {
                     for (uint32_t k = 0; k < nhead; ++k) {
                         full = SlowStep(t, full, p[k]);
-                        Bump(a, t.H, full, c);
+                        c.Step(a, t.H, full);
                     }
                 }
+                c.EndGroup(a.regexps);
                 p += nhead;
             }
         }
@@ -941,7 +1055,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
                     CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
                 CopyAsyncCommit();
                 if (k + j < chunks)
-                    CountChunk16(a, t, s, v, c);
+                    CountChunk16<kWords, kAlways>(a, t, s, v, c);
             }
         }
         CopyAsyncWait<0>();
@@ -953,29 +1067,26 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
                 EdgeBytes eb(LoadEdge16(p), 0);
                 for (uint32_t k = 0; k < ntail; ++k) {
                     full = SlowStep(t, full, eb.Next());
-                    Bump(a, t.H, full, c);
+                    c.Step(a, t.H, full);
                 }
             } else {
                 for (uint32_t k = 0; k < ntail; ++k) {
                     full = SlowStep(t, full, p[k]);
-                    Bump(a, t.H, full, c);
+                    c.Step(a, t.H, full);
                 }
             }
         }
         if (valid && a.through_end) {
             full = FullNext(t, full, a.end_class);                   // Step(EndMark)
-            Bump(a, t.H, full, c);
+            c.Step(a, t.H, full);
         }
+        c.EndGroup(a.regexps);
         const bool final = valid && (__ldg(a.flags + full) & 1u) != 0;
         const unsigned matched = __ballot_sync(0xffffffffu, final);
         if (a.match_bits && lane == 0)
             a.match_bits[unit] = matched;
-        if (valid) {
-            c.row[0] += c.c0;
-            if (a.regexps > 1) c.row[1] += c.c1;
-            if (a.regexps > 2) c.row[2] += c.c2;
-            if (a.regexps > 3) c.row[3] += c.c3;
-        }
+        if (valid)
+            c.Finish(a.regexps);
     }
 }
 
@@ -1176,7 +1287,14 @@ cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream)
 {
     if (a.n == 0)
         return cudaSuccess;
-    const void* fn = reinterpret_cast<const void*>(&CountKernel);
+    const void* fn = nullptr;
+    switch (a.count_words * 2 + (a.count_always ? 1 : 0)) {
+    case 2: fn = reinterpret_cast<const void*>(&CountKernel<1, false>); break;
+    case 3: fn = reinterpret_cast<const void*>(&CountKernel<1, true>); break;
+    case 4: fn = reinterpret_cast<const void*>(&CountKernel<2, false>); break;
+    case 5: fn = reinterpret_cast<const void*>(&CountKernel<2, true>); break;
+    default: fn = reinterpret_cast<const void*>(&CountKernel<0, false>); break;
+    }
     int optin = 0, sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err == cudaSuccess)
@@ -1185,7 +1303,7 @@ cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream)
         err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess)
         return err;
-    const size_t shared = GenericSharedBytes(a.hot);
+    const size_t shared = GenericSharedBytes(a.hot) + (size_t) (a.hot + 1) * a.count_words * 8;
     const uint64_t want = ((a.n + 31) / 32 + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int grid = (int) (want < (uint64_t) sms * kGenericBlocksPerSM ? want : (uint64_t) sms * kGenericBlocksPerSM);
     void* args[] = {const_cast<ScanArgs*>(&a)};

@@ -140,6 +140,10 @@ class Scanner:
     def Empty(self):
         return bool(self.info().empty)
 
+    def set_count_mode(self, mode):
+        """0 auto, 1 accept lists, 2 packed increments, 3 packed on every chunk (pire_gpu_scanner_set_count_mode)."""
+        N.check(N.lib.pire_gpu_scanner_set_count_mode(self._h, mode), "pire_gpu_scanner_set_count_mode")
+
     def RegexpsCount(self):
         return self.info().regexps
 

@@ -515,12 +515,13 @@ def test_half_final_counts_golden(cuda_device):
     import pire_b200 as P
     from conftest import GOLDEN_COUNTS
     for case in GOLDEN_COUNTS:
-        for max_hot in (255, 3):
+        for max_hot, mode in ((255, 0), (255, 1), (255, 2), (255, 3), (3, 1), (3, 2), (3, 3)):
             sc = P.Scanner(case.image, cuda_device)
             sc.set_max_hot(max_hot)
+            sc.set_count_mode(mode)           # accept lists / packed increments / packed on every chunk
             res = P.HalfFinalCount(sc, P.Batch.from_strings(case.strings))
-            assert res.counts[0].tolist() == case.expect, (case, max_hot)
-            assert res.counts.tolist() == case.counts and res.final.astype(int).tolist() == case.final, (case, max_hot)
+            assert res.counts[0].tolist() == case.expect, (case, max_hot, mode)
+            assert res.counts.tolist() == case.counts and res.final.astype(int).tolist() == case.final, (case, max_hot, mode)
             assert res.AcceptedRegexps(0) == [r for r, c in enumerate(case.expect) if c]
         if case.single:
             image, want, fin = case.single
@@ -554,11 +555,31 @@ def test_half_final_counts_vs_reference(cuda_device, ref):
                 sc.set_max_hot(max_hot)
                 for begin, end in ((True, True), (False, False), (True, False), (False, True)):
                     want, wfin = ref_sc.count(corpus, offs, begin=begin, end=end)
-                    res = P.HalfFinalCount(sc, batch, begin=begin, end=end)
-                    assert (res.counts == want).all(), (pat, max_hot, begin, end, np.argwhere(res.counts != want)[:4])
-                    assert (res.final == wfin.astype(bool)).all()
+                    for mode in (1, 2, 3):
+                        sc.set_count_mode(mode)
+                        res = P.HalfFinalCount(sc, batch, begin=begin, end=end)
+                        assert (res.counts == want).all(), (pat, max_hot, mode, begin, end, np.argwhere(res.counts != want)[:4])
+                        assert (res.final == wfin.astype(bool)).all()
                     got, _ = oracle_count(orc, corpus, offs, begin=begin, end=end)
                     assert (got == want).all()
+        # 21 counters: too many for the packed form, the accept lists are walked whatever the mode says
+        many = glued
+        for _ in range(2):
+            many = ref.glue_half_final(many, glued)
+        assert many.regexps == 21
+        sc = P.Scanner(many.save(), cuda_device)
+        want, _ = many.count(corpus, offs)
+        for mode in (0, 2):
+            sc.set_count_mode(mode)
+            assert (P.HalfFinalCount(sc, batch).counts == want).all()
+        # long strings: the 16-bit stage of the packed counters is flushed before it can wrap
+        long_strs = [bytes(rng.choice(np.frombuffer(b"ab", np.uint8), size=int(k))) for k in (70000, 66000, 1 << 17, 5)]
+        lc, lo = csr(long_strs)
+        want, _ = glued.count(lc, lo)
+        sc = P.Scanner(glued.save(), cuda_device)
+        for mode in (2, 3):
+            sc.set_count_mode(mode)
+            assert (P.HalfFinalCount(sc, P.Batch.from_strings(long_strs)).counts == want).all(), (pat, mode)
     # fixed-length strings, tuned hot rows
     ref_sc = ref.compile_half_final(b"ab+c|b", "un", 4)
     sc = P.Scanner(ref_sc.save(), cuda_device)
@@ -567,7 +588,7 @@ def test_half_final_counts_vs_reference(cuda_device, ref):
     want, wfin = ref_sc.count(host, fixed_len=96, n=6000)
     for tuned in (False, True):
         if tuned:
-            sc.Tune(batch, 6000)
+            sc.Tune(batch, 6000)           # also measures how often final states are entered (AUTO -> every chunk)
         res = P.HalfFinalCount(sc, batch)
         assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all()
 

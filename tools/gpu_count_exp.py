@@ -53,7 +53,8 @@ def main():
             N.check(N.lib.pire_gpu_count_batch(sc._h, corpus.data_ptr(), None, 1024, n, flags, counts.data_ptr(), bits.data_ptr(),
                                                stream), "pire_gpu_count_batch")
         res = {}
-        for tuned in (False, True):
+        for label, mode, tuned in (("lists", 1, False), ("packed", 2, False), ("every_chunk", 3, False), ("auto_tuned", 0, True)):
+            sc.set_count_mode(mode)
             if tuned:
                 sc.Tune(batch, 16384)
             for _ in range(2):
@@ -66,13 +67,14 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
-            res["tuned" if tuned else "static"] = {"ms": ms, "GBps": payload / 1e9 / (ms / 1e3)}
-        got = counts[:sample].cpu().numpy().view(np.uint32)
-        if ref:
-            want, wfin = ref.load_half_final(image).count(host, fixed_len=1024, n=sample, threads=8)
-        else:
-            want, wfin = refpire.oracle_count(refpire.Oracle(image), host, fixed_len=1024, n=sample)
-        assert (got == want).all(), (name, np.argwhere(got != want)[:5])
+            res[label] = {"ms": ms, "GBps": payload / 1e9 / (ms / 1e3)}
+            got = counts[:sample].cpu().numpy().view(np.uint32)
+            if label == "lists":
+                if ref:
+                    want, wfin = ref.load_half_final(image).count(host, fixed_len=1024, n=sample, threads=8)
+                else:
+                    want, wfin = refpire.oracle_count(refpire.Oracle(image), host, fixed_len=1024, n=sample)
+            assert (got == want).all(), (name, label, np.argwhere(got != want)[:5])
         words = bits[: sample // 32].cpu().numpy().view(np.uint32)
         fin = (words[np.arange(sample) // 32] >> (np.arange(sample) % 32).astype(np.uint32)) & 1
         assert (fin == wfin).all()
