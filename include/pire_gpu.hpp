@@ -199,6 +199,17 @@ inline void ShortestPrefix(const Scanner& sc, const Batch& b, uint32_t* d_prefix
           "pire_gpu_prefix_batch");
 }
 
+// Batch counterpart of running a Pire::HalfFinalScanner over each string the way tests/count_ut.cpp:54-63
+// does -- Initialize, [Step(BeginMark)], Run, [Step(EndMark)] -- and reading State::Result(r)
+// (pire/scanners/half_final.h:88-90,:136-163) for every regexp: d_counts holds Count rows of
+// max(1, RegexpsCount()) u32.  `sc` is built from the HalfFinalScanner (its Save() stream is Scanner's).
+inline void HalfFinalCount(const Scanner& sc, const Batch& b, uint32_t* d_counts, uint32_t* d_match_bits = nullptr,
+                           unsigned flags = PIRE_GPU_RUN_BEGIN | PIRE_GPU_RUN_END, void* stream = nullptr)
+{
+    Check(pire_gpu_count_batch(sc.Raw(), b.Corpus, b.Offsets, b.FixedLen, b.Count, flags, d_counts, d_match_bits, stream),
+          "pire_gpu_count_batch");
+}
+
 // Host-buffer counterpart of `bool Pire::Runner(sc).Begin().Run(p, n).End()` for many
 // strings at once (CSR): fills `matched[i]`.
 inline void MatchesHost(const Scanner& sc, const uint8_t* corpus, const uint64_t* offsets, uint64_t n,

@@ -78,6 +78,32 @@ int main()
         if (e.Code != PIRE_GPU_ENODEVICE)
             ++bad;
     }
+    // a HalfFinalScanner (pire/scanners/half_final.h) ingests through the same Save() stream; the host concept
+    // walks the same states, and the counting entry point refuses a host-only handle as well
+    {
+        Pire::Fsm fsm = Pire::Lexer("ab+c|b").Parse();
+        Pire::HalfFinalScanner hf(fsm);
+        Pire::Gpu::Scanner hmine(hf, -1);
+        ++checked;
+        if (hmine.Size() != hf.Size() || hmine.RegexpsCount() != hf.RegexpsCount())
+            ++bad;
+        for (const char* t : {"abbbc", "b", "xabcb", ""}) {
+            Pire::HalfFinalScanner::State a = RunRegexp(hf, t);
+            Pire::Gpu::Scanner::State b = RunRegexp(hmine, t);
+            ++checked;
+            if (hf.StateIndex(a) != hmine.StateIndex(b) || hf.Final(a) != hmine.Final(b))
+                ++bad;
+        }
+        try {
+            uint32_t counts[1];
+            Pire::Gpu::Batch batch{(const uint8_t*) "abc", nullptr, 3, 1};
+            Pire::Gpu::HalfFinalCount(hmine, batch, counts);
+            ++bad;
+        } catch (Pire::Gpu::Error& e) {
+            if (e.Code != PIRE_GPU_ENODEVICE)
+                ++bad;
+        }
+    }
     std::printf("mirror_check: %d comparisons, %d mismatches\n", checked, bad);
     return bad ? 1 : 0;
 }
