@@ -76,4 +76,32 @@ rng = np.random.default_rng(5)
 fx = rng.choice(np.frombuffer("x\u0424y ab".encode() + bytes(range(120, 256)), np.uint8), size=(1024, 64)).reshape(-1)
 fb = P.Batch(torch.from_numpy(fx).to(dev), fixed_len=64, n=1024)
 check(sc, orc, fb, fx, None, 64, 1024, "tiny DFA, high bytes, PRIV")
-XX, N.lib.pire_gpu_launch_count())
+# counting kernels (HalfFinalScanner): accept lists / packed / packed on every chunk, tiny hot sets, ragged + fixed
+from refpire import oracle_count
+for name in ("hf_glue10", "count_words5"):
+    image = W.load_image(name)
+    orc = Oracle(image)
+    strings = [b"", b"x", b"GET /a error timeout", b"hello  world fatal https://x", b"ab cd" * 40, b"a" * 33, b"zz"] * 40
+    c, o = csr(strings)
+    want, wfin = oracle_count(orc, c, o)
+    bb = P.Batch.from_strings(strings)
+    for max_hot in (255, 2):
+        sc = P.Scanner(image, 0)
+        sc.set_max_hot(max_hot)
+        for mode in (1, 2, 3):
+            sc.set_count_mode(mode)
+            res = P.HalfFinalCount(sc, bb)
+            assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all(), (name, max_hot, mode)
+    spec = W.SynthSpec(1024 + 5, 256, plants=W.GLUE10_PLANTS)
+    d = torch.empty(spec.total_bytes(), dtype=torch.uint8, device=dev)
+    spec.fill_device(d)
+    host = spec.host_sample(0, 1024 + 5)
+    want, wfin = oracle_count(orc, host, fixed_len=256, n=1024 + 5)
+    sc = P.Scanner(image, 0)
+    fbatch = P.Batch(d, fixed_len=256, n=1024 + 5)
+    sc.Tune(fbatch, 512)
+    res = P.HalfFinalCount(sc, fbatch)
+    assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all(), name
+    print("ok counting", name, flush=True)
+torch.cuda.synchronize()
+print("sanitize_run done, launches:", N.lib.pire_gpu_launch_count())
