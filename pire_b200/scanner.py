@@ -125,8 +125,9 @@ class Scanner:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            N.lib.pire_gpu_scanner_destroy(h)
+        lib = getattr(N, "lib", None)          # None while the interpreter is shutting down
+        if h and lib is not None:
+            lib.pire_gpu_scanner_destroy(h)
             self._h = None
 
     def info(self):
