@@ -378,6 +378,7 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     a.end_class = sc->tab.end_class;
     a.through_end = (flags & PIRE_GPU_RUN_END) ? 1 : 0;
     a.prefix_len = d_prefix_len;
+    a.first_final_hot = sc->tab.first_final_hot;
     CUDA_TRY(LaunchPrefix(a, shortest != 0, sc->device, static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
 }

@@ -70,8 +70,8 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
             t.old_of_new.push_back(s);
         }
     }
-    // Final hot states take the highest hot ids (order otherwise kept): the counting kernel then
-    // learns "did this chunk touch a final state or leave the hot rows" from the maximum id seen.
+    // Final hot states take the highest hot ids (order otherwise kept): the counting and prefix kernels
+    // then learn "did this chunk enter a final state or leave the hot rows" from the maximum id seen.
     std::stable_partition(t.old_of_new.begin(), t.old_of_new.end(), [&](uint32_t s) { return !dfa.Final(s); });
     t.first_final_hot = (uint32_t) t.old_of_new.size();
     for (uint32_t k = 0; k < t.old_of_new.size(); ++k) {

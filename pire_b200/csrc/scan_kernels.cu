@@ -717,20 +717,82 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
     }
 }
 
+__device__ __forceinline__ uint32_t FullNext(const Tables& t, uint32_t s, uint32_t letter)
+{
+    size_t at = (size_t) s * t.letters + letter;
+    return t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at) : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
+}
+
 // ---------------------------------------------------------------- prefix scans
 //
-// Pire::LongestPrefix / ShortestPrefix (run.h:277-311, predicates run.h:69-100) for a batch:
-// the same walk, but Final() and Dead() are looked at after every byte -- the longest scan
-// remembers the last position whose state is final, the shortest stops at the first, both
-// stop in a dead state (pire_ut.cpp ScanTermination@475).  One string per lane; hot rows and
-// the flags of hot states come from shared memory, the rest from the complete table.
+// Pire::LongestPrefix / ShortestPrefix (run.h:277-311, predicates run.h:69-100) for a batch: the same
+// walk, but Final() and Dead() matter after every byte -- the longest scan remembers the last position
+// whose state is final, the shortest stops at the first, both stop in a dead state (pire_ut.cpp
+// ScanTermination@475).  One string per lane through the generic kernel's machinery (cp.async ring, fused
+// hot rows).  Final hot states carry the highest hot ids, so the maximum id over the 16 steps of a chunk
+// says whether the chunk entered a final state or left the hot rows; only such chunks are replayed byte by
+// byte with the predicate.  A dead state is never final and only leads to dead states, so noticing it late
+// cannot change the answer: it is looked for once per ring round (64 bytes) to stop the lane, and a lane
+// that has stopped no longer fetches its string.
+struct PrefixLane {
+    uint32_t consumed;      // bytes walked so far
+    uint32_t pos;           // answer so far, kNoPrefix = none
+    bool stop;
+};
+constexpr uint32_t kNoPrefix = 0xFFFFFFFFu;
+
+template <bool kShortest>
+__device__ __forceinline__ void PrefixCheck(const ScanArgs& a, uint32_t H, const uint8_t* hot_flags, uint32_t state, PrefixLane& l)
+{
+    const uint32_t fl = state < H ? hot_flags[state] : __ldg(a.flags + state);
+    if (fl & 1u) {                                                   // Final: run.h:76-79 / :92-93
+        l.pos = l.consumed;
+        l.stop = kShortest;
+    }
+    if (fl & 2u)                                                     // Dead: run.h:82 / :94
+        l.stop = true;
+}
+
+template <bool kShortest>
+__device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t, const uint8_t* hot_flags, LaneState& s, uint4 v,
+                                              PrefixLane& l)
+{
+    const uint32_t before = s.g;
+    uint32_t g = before, top = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+        FastStep<false>(t, g, word, 0x5540);
+        top = max(top, g);
+        FastStep<false>(t, g, word, 0x5541);
+        top = max(top, g);
+        FastStep<false>(t, g, word, 0x5542);
+        top = max(top, g);
+        FastStep<false>(t, g, word, 0x5543);
+        top = max(top, g);
+    }
+    if (top < a.first_final_hot) {           // sixteen steps through non-final hot states
+        s.g = g;
+        l.consumed += 16;
+        return;
+    }
+    uint32_t full = before == t.H ? s.cold : before;
+    EdgeBytes eb(v, 0);
+    for (int k = 0; k < 16 && !l.stop; ++k) {
+        full = SlowStep(t, full, eb.Next());
+        ++l.consumed;
+        PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+    }
+    SetFull(t, s, full);
+}
+
 template <bool kShortest>
 __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv, a.hot8, a.hot);
-    uint8_t* hot_flags = sv.stage;                       // reuse the (unused here) staging area: H+1 bytes
+    uint8_t* const hot_flags = sv.stage + kStageBytes;              // H + 1 bytes behind the staging ring
     for (uint32_t i = threadIdx.x; i <= a.hot; i += blockDim.x)
         hot_flags[i] = i < a.hot ? a.flags[i] : 0;
     __syncthreads();
@@ -744,45 +806,125 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
     t.wide = a.wide;
     t.m0 = 0;
 
-    constexpr uint32_t kNone = 0xFFFFFFFFu;
-    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        uint64_t b, e;
-        if (a.offsets) {
-            b = a.offsets[i];
-            e = a.offsets[i + 1] - a.trim;
-        } else {
-            b = i * a.fixed_len;
-            e = b + a.fixed_len;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    const uint32_t stage = SmemAddr(sv.stage) + (((threadIdx.x >> 5) * kStageSlots) * 32 + lane) * 16;
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
+    const uintptr_t buf_hi = buf_lo + (a.offsets ? a.offsets[a.n] - a.trim : a.n * a.fixed_len);
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        uint64_t b = 0, e = 0;
+        if (valid) {
+            if (a.offsets) {
+                b = a.offsets[i];
+                e = a.offsets[i + 1] - a.trim;
+            } else {
+                b = i * a.fixed_len;
+                e = b + a.fixed_len;
+            }
         }
         const uint8_t* p = a.corpus + b;
+        const uint8_t* end = a.corpus + e;
         const uint32_t len = (uint32_t) (e - b);
-        uint32_t st = a.start;                                           // Initialize() [+ Step(BeginMark)]
-        uint32_t fl = st < t.H ? hot_flags[st] : a.flags[st];
-        uint32_t pos = (fl & 1u) ? 0u : kNone;                           // run.h:284 / :301-302
-        bool stop = kShortest && (fl & 1u);
-        uint32_t k = 0;
-        for (; k < len && !stop; ++k) {
-            st = SlowStep(t, st, p[k]);
-            fl = st < t.H ? hot_flags[st] : a.flags[st];
-            if (fl & 1u) {                                               // Final: run.h:76-79 / :92-93
-                pos = k + 1;
-                stop = kShortest;
+
+        uint32_t full = a.start;                                         // Initialize() [+ Step(BeginMark)]
+        PrefixLane l;
+        l.consumed = 0;
+        l.pos = kNoPrefix;
+        l.stop = !valid;
+        {
+            const uint32_t fl = full < t.H ? hot_flags[full] : __ldg(a.flags + full);
+            if (fl & 1u) {                                               // run.h:284 / :301-302
+                l.pos = 0;
+                l.stop = l.stop || kShortest;
             }
-            if (fl & 2u)                                                 // Dead: run.h:82 / :94
-                stop = true;
         }
-        if (a.through_end) {                                             // run.h:286-290 / :305-309
-            size_t at = (size_t) st * t.letters + a.end_class;
-            uint32_t last = t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at)
-                                   : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
-            if ((a.flags[last] & 1u) && (!kShortest || pos == kNone))
-                pos = len;
+        {
+            const uint32_t misalign = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
+            if (p < end && misalign != 0) {
+                const uint64_t room = (uint64_t) (end - p);
+                const uint32_t nhead = room < 16 - misalign ? (uint32_t) room : 16 - misalign;
+                const uint8_t* chunk = p - misalign;
+                if (!l.stop) {
+                    if (reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi) {
+                        EdgeBytes eb(LoadEdge16(chunk), misalign);
+                        for (uint32_t k = 0; k < nhead && !l.stop; ++k) {
+                            full = SlowStep(t, full, eb.Next());
+                            ++l.consumed;
+                            PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+                        }
+                    } else {
+                        for (uint32_t k = 0; k < nhead && !l.stop; ++k) {
+                            full = SlowStep(t, full, p[k]);
+                            ++l.consumed;
+                            PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+                        }
+                    }
+                }
+                p += nhead;
+            }
         }
-        a.prefix_len[i] = pos;
+        LaneState s;
+        SetFull(t, s, full);
+        const uint32_t chunks = (uint32_t) ((end - p) >> 4);
+#pragma unroll
+        for (int j = 0; j < kStageSlots; ++j) {
+            if ((uint32_t) j < chunks && !l.stop)
+                CopyAsync16(stage + j * 512, p + 16 * j);
+            CopyAsyncCommit();
+        }
+        for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks && !l.stop); k += kStageSlots) {
+#pragma unroll
+            for (int j = 0; j < kStageSlots; ++j) {
+                CopyAsyncWait<kStageSlots - 1>();
+                const uint4 v = LoadShared16(stage + j * 512);
+                const bool had = k + j < chunks && !l.stop;              // this slot was filled for this lane
+                if (k + kStageSlots + j < chunks && !l.stop)
+                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
+                CopyAsyncCommit();
+                if (had)
+                    PrefixChunk16<kShortest>(a, t, hot_flags, s, v, l);
+            }
+            // a dead state only leads to dead states: stop the lane (and its fetches) once it is noticed
+            if (!l.stop) {
+                const uint32_t at = FullState(t, s);
+                if ((at < t.H ? hot_flags[at] : __ldg(a.flags + at)) & 2u)
+                    l.stop = true;
+            }
+        }
+        CopyAsyncWait<0>();
+        full = FullState(t, s);
+        p += 16 * (size_t) chunks;
+        if (p < end && !l.stop) {
+            const uint32_t ntail = (uint32_t) (end - p);
+            if (reinterpret_cast<uintptr_t>(p) + 16 <= buf_hi) {
+                EdgeBytes eb(LoadEdge16(p), 0);
+                for (uint32_t k = 0; k < ntail && !l.stop; ++k) {
+                    full = SlowStep(t, full, eb.Next());
+                    ++l.consumed;
+                    PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+                }
+            } else {
+                for (uint32_t k = 0; k < ntail && !l.stop; ++k) {
+                    full = SlowStep(t, full, p[k]);
+                    ++l.consumed;
+                    PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+                }
+            }
+        }
+        if (valid) {
+            if (a.through_end) {                                         // run.h:286-290 / :305-309
+                const uint32_t last = FullNext(t, full, a.end_class);
+                if ((__ldg(a.flags + last) & 1u) && (!kShortest || l.pos == kNoPrefix))
+                    l.pos = len;
+            }
+            a.prefix_len[i] = l.pos;
+        }
     }
 }
-
 
 // ---------------------------------------------------------------- counting (HalfFinalScanner)
 //
@@ -898,12 +1040,6 @@ struct Counter<0> {
         if (regexps > 3) row[3] += c3;
     }
 };
-
-__device__ __forceinline__ uint32_t FullNext(const Tables& t, uint32_t s, uint32_t letter)
-{
-    size_t at = (size_t) s * t.letters + letter;
-    return t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at) : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
-}
 
 template <int kWords, bool kAlways>
 __device__ __forceinline__ void CountChunk16(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, Counter<kWords>& c)
@@ -1272,7 +1408,7 @@ cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStrea
         err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess)
         return err;
-    const size_t shared = GenericSharedBytes(a.hot);
+    const size_t shared = GenericSharedBytes(a.hot) + 272;      // + the hot states' flag bytes
     uint64_t want = (a.n + kBlock - 1) / kBlock;
     int grid = (int) (want < (uint64_t) sms * kGenericBlocksPerSM ? want : (uint64_t) sms * kGenericBlocksPerSM);
     void* args[] = {const_cast<ScanArgs*>(&a)};
