@@ -776,6 +776,34 @@ __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t
         l.consumed += 16;
         return;
     }
+    if (before != t.H) {
+        // a final state (or the sink) was entered: the chunk again, branch-free, noting where.  `mark` is the
+        // 1-based step of the last (longest) or first (shortest) final state entered; the sink id also
+        // compares >= first_final_hot, but a lane that reached the sink takes the slow path below instead.
+        uint32_t h = before, mark = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                FastStep<false>(t, h, word, 0x5540 + b);
+                const bool final = h >= a.first_final_hot;
+                if (kShortest)
+                    mark = final && mark == 0 ? (uint32_t) (4 * w + b + 1) : mark;
+                else
+                    mark = final ? (uint32_t) (4 * w + b + 1) : mark;
+            }
+        }
+        if (h != t.H) {
+            if (mark) {
+                l.pos = l.consumed + mark;
+                l.stop = kShortest;
+            }
+            l.consumed += 16;
+            s.g = h;
+            return;
+        }
+    }
     uint32_t full = before == t.H ? s.cold : before;
     EdgeBytes eb(v, 0);
     for (int k = 0; k < 16 && !l.stop; ++k) {
