@@ -154,6 +154,21 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc,
  * The image is the Save() stream of the HalfFinalScanner (it inherits Scanner::Save; the same format).
  * d_counts: n rows of max(1, regexps) u32, row i for string i (overwritten).  d_match_bits: packed
  * Final(st) per string, may be null.  Counters are 32 bits wide (the reference's are size_t). */
+/* Replaces, per string of a batch,
+ *     Pire::LongestSuffix (sc, rbegin, rend, throughEndMark, throughBeginMark)   run.h:316-342
+ *     Pire::ShortestSuffix(sc, rbegin, rend, throughEndMark, throughBeginMark)   run.h:345-362
+ * with rbegin = the string's last byte and rend = one before its first: the scanner (normally compiled from
+ * Fsm::Reverse()) is walked over the string from right to left.  d_suffix_len[i] = length of the longest /
+ * shortest suffix accepted that way (the reference returns the pointer rbegin - length), or
+ * PIRE_GPU_NO_PREFIX for its null.  PIRE_GPU_RUN_END = throughEndMark (stepped before the bytes),
+ * PIRE_GPU_RUN_BEGIN = throughBeginMark (stepped after them).  ShortestSuffix's quirk is kept: with
+ * throughBeginMark the mark is stepped from the state the scan stopped in, and the answer is null unless that
+ * state is final (run.h:357-360). */
+int pire_gpu_suffix_batch(const pire_gpu_scanner* sc,
+                          const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest,
+                          uint32_t* d_suffix_len, void* stream);
+
 /* How pire_gpu_count_batch keeps the counters (results are identical; for tests and measurements).
  * AUTO: packed per-state increments when the automaton has at most 16 regexps, behind a look-ahead pass
  * that skips chunks without final states -- or on every chunk when pire_gpu_scanner_tune saw more than

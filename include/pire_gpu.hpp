@@ -199,6 +199,24 @@ inline void ShortestPrefix(const Scanner& sc, const Batch& b, uint32_t* d_prefix
           "pire_gpu_prefix_batch");
 }
 
+// Batch counterparts of Pire::LongestSuffix / Pire::ShortestSuffix (run.h:316-362): every string is walked from
+// its last byte to its first; one suffix length per string (PIRE_GPU_NO_PREFIX for null).
+inline void LongestSuffix(const Scanner& sc, const Batch& b, uint32_t* d_suffix_len, bool throughEndMark = false,
+                          bool throughBeginMark = false, void* stream = nullptr)
+{
+    unsigned flags = (throughBeginMark ? PIRE_GPU_RUN_BEGIN : 0u) | (throughEndMark ? PIRE_GPU_RUN_END : 0u);
+    Check(pire_gpu_suffix_batch(sc.Raw(), b.Corpus, b.Offsets, b.FixedLen, b.Count, flags, 0, d_suffix_len, stream),
+          "pire_gpu_suffix_batch");
+}
+
+inline void ShortestSuffix(const Scanner& sc, const Batch& b, uint32_t* d_suffix_len, bool throughEndMark = false,
+                           bool throughBeginMark = false, void* stream = nullptr)
+{
+    unsigned flags = (throughBeginMark ? PIRE_GPU_RUN_BEGIN : 0u) | (throughEndMark ? PIRE_GPU_RUN_END : 0u);
+    Check(pire_gpu_suffix_batch(sc.Raw(), b.Corpus, b.Offsets, b.FixedLen, b.Count, flags, 1, d_suffix_len, stream),
+          "pire_gpu_suffix_batch");
+}
+
 // Batch counterpart of running a Pire::HalfFinalScanner over each string the way tests/count_ut.cpp:54-63
 // does -- Initialize, [Step(BeginMark)], Run, [Step(EndMark)] -- and reading State::Result(r)
 // (pire/scanners/half_final.h:88-90,:136-163) for every regexp: d_counts holds Count rows of

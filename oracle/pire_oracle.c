@@ -267,6 +267,50 @@ void pire_oracle_prefix_batch(const pire_oracle_scanner* sc, const uint8_t* corp
     }
 }
 
+/* LongestSuffix / ShortestSuffix, run.h:316-362: the string is walked from its last byte to its first. */
+void pire_oracle_suffix_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
+                              const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
+                              int through_end, int through_begin, int shortest, int64_t* out)
+{
+    uint64_t i;
+    for (i = 0; i < n; ++i) {
+        const uint8_t* b = offsets ? corpus + offsets[i] : corpus + i * fixed_len;
+        const uint8_t* e = offsets ? corpus + offsets[i + 1] : b + fixed_len;
+        const uint8_t* rbegin = e;                 /* one past the next byte to read (the reference's rbegin + 1) */
+        uint64_t st = pire_oracle_initial(sc);
+        int64_t pos = -1;
+        if (through_end)
+            st = pire_oracle_step(sc, st, PIRE_ORACLE_END_MARK);            /* run.h:321-322 / :350-351 */
+        if (shortest) {
+            /* run.h:353-360 */
+            while (rbegin != b && !pire_oracle_final(sc, st) && !pire_oracle_dead(sc, st)) {
+                --rbegin;
+                st = pire_oracle_step(sc, st, *rbegin);
+            }
+            if (through_begin)
+                st = pire_oracle_step(sc, st, PIRE_ORACLE_BEGIN_MARK);      /* from wherever the scan stopped */
+            if (pire_oracle_final(sc, st))
+                pos = (int64_t) (e - rbegin);
+        } else {
+            /* run.h:327-340 */
+            while (rbegin != b && !pire_oracle_dead(sc, st)) {
+                if (pire_oracle_final(sc, st))
+                    pos = (int64_t) (e - rbegin);
+                --rbegin;
+                st = pire_oracle_step(sc, st, *rbegin);
+            }
+            if (pire_oracle_final(sc, st))
+                pos = (int64_t) (e - rbegin);
+            if (through_begin) {
+                st = pire_oracle_step(sc, st, PIRE_ORACLE_BEGIN_MARK);
+                if (pire_oracle_final(sc, st))
+                    pos = (int64_t) (e - rbegin);
+            }
+        }
+        out[i] = pos;
+    }
+}
+
 /* ---- HalfFinalScanner counting (pire/scanners/half_final.h) ------------------------------- */
 
 /* TakeAction, half_final.h:154-163: in a final state every entry of the state's accept list bumps the

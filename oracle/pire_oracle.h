@@ -73,6 +73,12 @@ void pire_oracle_prefix_batch(const pire_oracle_scanner* sc, const uint8_t* corp
                               const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
                               int through_begin, int through_end, int shortest, int64_t* out);
 
+/* LongestSuffix / ShortestSuffix (run.h:316-362), the string walked from its last byte (rbegin) down to its
+ * first: out[i] = suffix length, or -1 where the reference returns a null pointer. */
+void pire_oracle_suffix_batch(const pire_oracle_scanner* sc, const uint8_t* corpus,
+                              const uint64_t* offsets, uint64_t fixed_len, uint64_t n,
+                              int through_end, int through_begin, int shortest, int64_t* out);
+
 /* HalfFinalScanner (pire/scanners/half_final.h:136-163) per string, as tests/count_ut.cpp:54-63 drives it:
  *   Initialize (+TakeAction); [Step(BeginMark)]; Step per byte; [Step(EndMark)]; Result(r) for every regexp.
  * counts: n rows of max(1, regexps) u32.  The image is the same Scanner::Save() stream. */

@@ -59,7 +59,7 @@ Pire::Fsm Parse(const char* pattern, const char* options)
 {
 	Pire::Lexer lexer;
 	Pire::TVector<Pire::wchar32> ucs4;
-	bool surround = true;
+	bool surround = true, reverse = false;
 	for (; options && *options; ++options) {
 		if (*options == 'i')
 			lexer.AddFeature(Pire::Features::CaseInsensitive());
@@ -69,6 +69,8 @@ Pire::Fsm Parse(const char* pattern, const char* options)
 			surround = false;
 		else if (*options == 'a')
 			lexer.AddFeature(Pire::Features::AndNotSupport());
+		else if (*options == 'r')
+			reverse = true;
 		else
 			throw std::invalid_argument(std::string("Unknown option: ") + *options);
 	}
@@ -77,6 +79,8 @@ Pire::Fsm Parse(const char* pattern, const char* options)
 	Pire::Fsm fsm = lexer.Parse();
 	if (surround)
 		fsm.Surround();
+	if (reverse)
+		fsm = fsm.Reverse();                         // tests/pire_ut.cpp:284: the scanner for suffix scans
 	return fsm;
 }
 
@@ -314,6 +318,29 @@ int pref_prefix_batch(void* h, int variant, int shortest, const uint8_t* corpus,
 			p = shortest ? Pire::ShortestPrefix(s->nonrelocNoMask, b, e, throughBegin != 0, throughEnd != 0)
 			             : Pire::LongestPrefix(s->nonrelocNoMask, b, e, throughBegin != 0, throughEnd != 0);
 		out[i] = p ? (int64_t) (p - b) : -1;
+	}
+	return 0;
+}
+
+// Pire::LongestSuffix / ShortestSuffix (run.h:316-362) per string, called the way tests/pire_ut.cpp:326-340 does:
+// rbegin = the last byte, rend = one before the first.  out[i] = suffix length (rbegin - returned pointer) or -1.
+int pref_suffix_batch(void* h, int variant, int shortest, const uint8_t* corpus, const uint64_t* offsets,
+                      uint64_t fixedLen, uint64_t n, int throughEnd, int throughBegin, int64_t* out)
+{
+	RefScanner* s = (RefScanner*) h;
+	for (uint64_t i = 0; i < n; ++i) {
+		const char* b = (const char*) corpus + (offsets ? offsets[i] : i * fixedLen);
+		const char* e = offsets ? (const char*) corpus + offsets[i + 1] : b + fixedLen;
+		const char* rbegin = e - 1;
+		const char* rend = b - 1;
+		const char* p;
+		if (variant == 0)
+			p = shortest ? Pire::ShortestSuffix(s->reloc, rbegin, rend, throughEnd != 0, throughBegin != 0)
+			             : Pire::LongestSuffix(s->reloc, rbegin, rend, throughEnd != 0, throughBegin != 0);
+		else
+			p = shortest ? Pire::ShortestSuffix(s->nonrelocNoMask, rbegin, rend, throughEnd != 0, throughBegin != 0)
+			             : Pire::LongestSuffix(s->nonrelocNoMask, rbegin, rend, throughEnd != 0, throughBegin != 0);
+		out[i] = p ? (int64_t) (rbegin - p) : -1;
 	}
 	return 0;
 }

@@ -8,5 +8,5 @@ Only what the path needs lives here:
     dist.py       shard-by-string + the one bitmap all-reduce
 """
 from ._native import PireGpuError, RUN_BEGIN, RUN_END, VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV  # noqa: F401
-from .scanner import (Batch, BeginMark, EndMark, HalfFinalCount, HalfFinalResult, LongestPrefix, Matches, RunHelper, Runner, Scanner,  # noqa: F401
-                      ShortestPrefix)
+from .scanner import (Batch, BeginMark, EndMark, HalfFinalCount, HalfFinalResult, LongestPrefix, LongestSuffix, Matches, RunHelper, Runner, Scanner,  # noqa: F401
+                      ShortestPrefix, ShortestSuffix)

@@ -23,7 +23,7 @@ VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV = 0, 1, 2, 3
 SYMBOLS = [
     "pire_gpu_scanner_create", "pire_gpu_scanner_destroy", "pire_gpu_scanner_info",
     "pire_gpu_scanner_set_variant", "pire_gpu_scanner_set_max_hot", "pire_gpu_run_batch",
-    "pire_gpu_run_batch_host", "pire_gpu_prefix_batch", "pire_gpu_count_batch", "pire_gpu_scanner_set_count_mode", "pire_gpu_length_order", "pire_gpu_run_batch_ordered", "pire_gpu_split_lines", "pire_gpu_run_lines", "pire_gpu_scanner_tune", "pire_gpu_scanner_autoselect", "pire_gpu_launch_count", "pire_gpu_initial",
+    "pire_gpu_run_batch_host", "pire_gpu_prefix_batch", "pire_gpu_suffix_batch", "pire_gpu_count_batch", "pire_gpu_scanner_set_count_mode", "pire_gpu_length_order", "pire_gpu_run_batch_ordered", "pire_gpu_split_lines", "pire_gpu_run_lines", "pire_gpu_scanner_tune", "pire_gpu_scanner_autoselect", "pire_gpu_launch_count", "pire_gpu_initial",
     "pire_gpu_next", "pire_gpu_final", "pire_gpu_dead", "pire_gpu_accepted_regexps",
     "pire_gpu_synth_fill_device", "pire_gpu_synth_fill_host", "pire_gpu_synth_mixed_lengths_device",
     "pire_gpu_synth_mixed_lengths_host", "pire_gpu_synth_mixed_fill_device", "pire_gpu_synth_mixed_fill_host",
@@ -60,6 +60,7 @@ def _load():
     lib.pire_gpu_run_batch.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp, vp]
     lib.pire_gpu_run_batch_host.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp]
     lib.pire_gpu_prefix_batch.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, vp, vp]
+    lib.pire_gpu_suffix_batch.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, vp, vp]
     lib.pire_gpu_scanner_set_count_mode.argtypes = [vp, C.c_uint32]
     lib.pire_gpu_count_batch.argtypes = [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp]
     lib.pire_gpu_length_order.argtypes = [vp, C.c_uint64, vp, C.c_int, vp]

@@ -357,8 +357,8 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     return PIRE_GPU_OK;
 }
 
-int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
-                          uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest, uint32_t* d_prefix_len, void* stream)
+static int PrefixOrSuffix(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets, uint64_t fixed_len,
+                          uint64_t n, uint32_t flags, int shortest, bool reverse, uint32_t* d_len, void* stream)
 {
     int rc = CheckRunnable(sc);
     if (rc != PIRE_GPU_OK)
@@ -367,7 +367,7 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
         return Fail(PIRE_GPU_EINVAL, "unknown run flags");
     if (n == 0)
         return PIRE_GPU_OK;
-    if (!d_prefix_len || (!d_corpus && (d_offsets || fixed_len != 0)))
+    if (!d_len || (!d_corpus && (d_offsets || fixed_len != 0)))
         return Fail(PIRE_GPU_EINVAL, "null corpus or output");
     if (!d_offsets && fixed_len > 0xfffffffeull)
         return Fail(PIRE_GPU_EINVAL, "strings longer than 4 GiB");
@@ -375,12 +375,30 @@ int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     ScanArgs a;
     FillArgs(sc, &a, d_corpus, d_offsets, fixed_len, n, flags);
     a.flags = sc->dev.flags;
-    a.end_class = sc->tab.end_class;
-    a.through_end = (flags & PIRE_GPU_RUN_END) ? 1 : 0;
-    a.prefix_len = d_prefix_len;
+    a.initial = sc->tab.initial;
+    // the mark stepped before the bytes and the one stepped after them: Begin..End for a prefix scan
+    // (run.h:282-283,:286-290), End..Begin for a suffix scan (run.h:321-322,:336-340)
+    const uint32_t begin = (flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0, end = (flags & PIRE_GPU_RUN_END) ? 1 : 0;
+    a.with_begin = reverse ? end : begin;
+    a.begin_class = reverse ? sc->tab.end_class : sc->tab.begin_class;
+    a.through_end = reverse ? begin : end;
+    a.end_class = reverse ? sc->tab.begin_class : sc->tab.end_class;
+    a.prefix_len = d_len;
     a.first_final_hot = sc->tab.first_final_hot;
-    CUDA_TRY(LaunchPrefix(a, shortest != 0, sc->device, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(LaunchPrefix(a, shortest != 0, reverse, sc->device, static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
+}
+
+int pire_gpu_prefix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest, uint32_t* d_prefix_len, void* stream)
+{
+    return PrefixOrSuffix(sc, d_corpus, d_offsets, fixed_len, n, flags, shortest, false, d_prefix_len, stream);
+}
+
+int pire_gpu_suffix_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,
+                          uint64_t fixed_len, uint64_t n, uint32_t flags, int shortest, uint32_t* d_suffix_len, void* stream)
+{
+    return PrefixOrSuffix(sc, d_corpus, d_offsets, fixed_len, n, flags, shortest, true, d_suffix_len, stream);
 }
 
 int pire_gpu_count_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uint64_t* d_offsets,

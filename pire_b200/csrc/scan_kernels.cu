@@ -723,17 +723,19 @@ __device__ __forceinline__ uint32_t FullNext(const Tables& t, uint32_t s, uint32
     return t.wide ? __ldg(static_cast<const uint32_t*>(t.full) + at) : (uint32_t) __ldg(static_cast<const uint16_t*>(t.full) + at);
 }
 
-// ---------------------------------------------------------------- prefix scans
+// ---------------------------------------------------------------- prefix and suffix scans
 //
-// Pire::LongestPrefix / ShortestPrefix (run.h:277-311, predicates run.h:69-100) for a batch: the same
-// walk, but Final() and Dead() matter after every byte -- the longest scan remembers the last position
-// whose state is final, the shortest stops at the first, both stop in a dead state (pire_ut.cpp
-// ScanTermination@475).  One string per lane through the generic kernel's machinery (cp.async ring, fused
-// hot rows).  Final hot states carry the highest hot ids, so the maximum id over the 16 steps of a chunk
-// says whether the chunk entered a final state or left the hot rows; only such chunks are replayed byte by
-// byte with the predicate.  A dead state is never final and only leads to dead states, so noticing it late
-// cannot change the answer: it is looked for once per ring round (64 bytes) to stop the lane, and a lane
-// that has stopped no longer fetches its string.
+// Pire::LongestPrefix / ShortestPrefix (run.h:277-311, predicates run.h:69-100) and LongestSuffix /
+// ShortestSuffix (run.h:316-362) for a batch: the same walk, but Final() and Dead() matter after every
+// byte -- the longest scan remembers the last position whose state is final, the shortest stops at the
+// first, both stop in a dead state (pire_ut.cpp ScanTermination@475).  The suffix scans walk the string
+// from its last byte to its first (the scanner is normally built from Fsm::Reverse()).  One string per
+// lane through the generic kernel's machinery (cp.async ring, fused hot rows).  Final hot states carry the
+// highest hot ids, so the maximum id over the 16 steps of a chunk says whether the chunk entered a final
+// state or left the hot rows; such a chunk is walked again, branch-free, marking where; only a chunk that
+// leaves the hot rows is replayed byte by byte with the predicate.  A dead state is never final and only
+// leads to dead states, so noticing it late cannot change the answer: it is looked for once per ring round
+// (64 bytes) to stop the lane, and a lane that has stopped no longer fetches its string.
 struct PrefixLane {
     uint32_t consumed;      // bytes walked so far
     uint32_t pos;           // answer so far, kNoPrefix = none
@@ -741,19 +743,46 @@ struct PrefixLane {
 };
 constexpr uint32_t kNoPrefix = 0xFFFFFFFFu;
 
+// The bytes of an edge chunk from index `top` downwards (suffix scans).
+struct EdgeBytesDown {
+    uint64_t lo, hi;
+    __device__ __forceinline__ EdgeBytesDown(uint4 v, uint32_t top)
+    {
+        lo = (uint64_t) v.x | ((uint64_t) v.y << 32);
+        hi = (uint64_t) v.z | ((uint64_t) v.w << 32);
+        uint32_t drop = 15 - top;                       // bytes above `top` are not ours
+        if (drop >= 8) {
+            hi = lo;
+            lo = 0;
+            drop -= 8;
+        }
+        if (drop) {
+            hi = (hi << (8 * drop)) | (lo >> (64 - 8 * drop));
+            lo <<= 8 * drop;
+        }
+    }
+    __device__ __forceinline__ uint32_t Next()
+    {
+        uint32_t b = (uint32_t) (hi >> 56);
+        hi = (hi << 8) | (lo >> 56);
+        lo <<= 8;
+        return b;
+    }
+};
+
 template <bool kShortest>
 __device__ __forceinline__ void PrefixCheck(const ScanArgs& a, uint32_t H, const uint8_t* hot_flags, uint32_t state, PrefixLane& l)
 {
     const uint32_t fl = state < H ? hot_flags[state] : __ldg(a.flags + state);
-    if (fl & 1u) {                                                   // Final: run.h:76-79 / :92-93
+    if (fl & 1u) {                                                   // Final: run.h:76-79 / :92-93 / :329-330 / :353
         l.pos = l.consumed;
         l.stop = kShortest;
     }
-    if (fl & 2u)                                                     // Dead: run.h:82 / :94
+    if (fl & 2u)                                                     // Dead: run.h:82 / :94 / :328 / :353
         l.stop = true;
 }
 
-template <bool kShortest>
+template <bool kShortest, bool kReverse>
 __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t, const uint8_t* hot_flags, LaneState& s, uint4 v,
                                               PrefixLane& l)
 {
@@ -761,32 +790,34 @@ __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t
     uint32_t g = before, top = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
-        FastStep<false>(t, g, word, 0x5540);
-        top = max(top, g);
-        FastStep<false>(t, g, word, 0x5541);
-        top = max(top, g);
-        FastStep<false>(t, g, word, 0x5542);
-        top = max(top, g);
-        FastStep<false>(t, g, word, 0x5543);
-        top = max(top, g);
+        const int at = kReverse ? 3 - w : w;
+        const uint32_t word = at == 0 ? v.x : at == 1 ? v.y : at == 2 ? v.z : v.w;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            FastStep<false>(t, g, word, 0x5540 + (kReverse ? 3 - b : b));
+            top = max(top, g);
+        }
     }
     if (top < a.first_final_hot) {           // sixteen steps through non-final hot states
         s.g = g;
         l.consumed += 16;
         return;
     }
-    if (before != t.H) {
+    // ShortestSuffix steps BeginMark from the state it stopped in (run.h:357-359), so that scan needs the
+    // state at the first final step, not the one after the chunk: it goes straight to the byte-wise replay
+    // (once per string).
+    if (before != t.H && !(kShortest && kReverse)) {
         // a final state (or the sink) was entered: the chunk again, branch-free, noting where.  `mark` is the
         // 1-based step of the last (longest) or first (shortest) final state entered; the sink id also
         // compares >= first_final_hot, but a lane that reached the sink takes the slow path below instead.
         uint32_t h = before, mark = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+            const int at = kReverse ? 3 - w : w;
+            const uint32_t word = at == 0 ? v.x : at == 1 ? v.y : at == 2 ? v.z : v.w;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                FastStep<false>(t, h, word, 0x5540 + b);
+                FastStep<false>(t, h, word, 0x5540 + (kReverse ? 3 - b : b));
                 const bool final = h >= a.first_final_hot;
                 if (kShortest)
                     mark = final && mark == 0 ? (uint32_t) (4 * w + b + 1) : mark;
@@ -805,16 +836,25 @@ __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t
         }
     }
     uint32_t full = before == t.H ? s.cold : before;
-    EdgeBytes eb(v, 0);
-    for (int k = 0; k < 16 && !l.stop; ++k) {
-        full = SlowStep(t, full, eb.Next());
-        ++l.consumed;
-        PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+    if (kReverse) {
+        EdgeBytesDown eb(v, 15);
+        for (int k = 0; k < 16 && !l.stop; ++k) {
+            full = SlowStep(t, full, eb.Next());
+            ++l.consumed;
+            PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+        }
+    } else {
+        EdgeBytes eb(v, 0);
+        for (int k = 0; k < 16 && !l.stop; ++k) {
+            full = SlowStep(t, full, eb.Next());
+            ++l.consumed;
+            PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
+        }
     }
     SetFull(t, s, full);
 }
 
-template <bool kShortest>
+template <bool kShortest, bool kReverse>
 __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
@@ -854,54 +894,67 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
                 e = b + a.fixed_len;
             }
         }
-        const uint8_t* p = a.corpus + b;
-        const uint8_t* end = a.corpus + e;
+        const uint8_t* const first = a.corpus + b;
+        const uint8_t* const end = a.corpus + e;
         const uint32_t len = (uint32_t) (e - b);
 
-        uint32_t full = a.start;                                         // Initialize() [+ Step(BeginMark)]
+        // Initialize() and the first mark: BeginMark for a prefix scan (run.h:282-283), EndMark for a
+        // suffix scan (run.h:321-322)
+        uint32_t full = a.initial;
+        if (a.with_begin)
+            full = FullNext(t, full, a.begin_class);
         PrefixLane l;
         l.consumed = 0;
         l.pos = kNoPrefix;
         l.stop = !valid;
         {
             const uint32_t fl = full < t.H ? hot_flags[full] : __ldg(a.flags + full);
-            if (fl & 1u) {                                               // run.h:284 / :301-302
+            if (fl & 1u) {                                               // run.h:284 / :301-302 / :329-330 / :353
                 l.pos = 0;
                 l.stop = l.stop || kShortest;
             }
+            if (kReverse && (fl & 2u))                                   // run.h:328 / :353: Dead is looked at before the first byte
+                l.stop = true;
         }
+        // edge bytes on the side the walk starts from, up to a 16-byte boundary
+        const uint8_t* p = kReverse ? end : first;                       // forward: next byte; reverse: one past the next byte
         {
             const uint32_t misalign = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
-            if (p < end && misalign != 0) {
-                const uint64_t room = (uint64_t) (end - p);
-                const uint32_t nhead = room < 16 - misalign ? (uint32_t) room : 16 - misalign;
+            if (len != 0 && misalign != 0) {
+                const uint32_t span = kReverse ? misalign : 16 - misalign;      // bytes between p and the boundary
+                const uint32_t nedge = len < span ? len : span;
                 const uint8_t* chunk = p - misalign;
                 if (!l.stop) {
-                    if (reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi) {
-                        EdgeBytes eb(LoadEdge16(chunk), misalign);
-                        for (uint32_t k = 0; k < nhead && !l.stop; ++k) {
-                            full = SlowStep(t, full, eb.Next());
+                    const bool whole = reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi;
+                    if (kReverse) {
+                        EdgeBytesDown eb(whole ? LoadEdge16(chunk) : make_uint4(0, 0, 0, 0), misalign - 1);
+                        for (uint32_t k = 0; k < nedge && !l.stop; ++k) {
+                            const uint32_t byte = whole ? eb.Next() : (uint32_t) p[-1 - (int) k];
+                            full = SlowStep(t, full, byte);
                             ++l.consumed;
                             PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
                         }
                     } else {
-                        for (uint32_t k = 0; k < nhead && !l.stop; ++k) {
-                            full = SlowStep(t, full, p[k]);
+                        EdgeBytes eb(whole ? LoadEdge16(chunk) : make_uint4(0, 0, 0, 0), misalign);
+                        for (uint32_t k = 0; k < nedge && !l.stop; ++k) {
+                            const uint32_t byte = whole ? eb.Next() : (uint32_t) p[k];
+                            full = SlowStep(t, full, byte);
                             ++l.consumed;
                             PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
                         }
                     }
                 }
-                p += nhead;
+                p = kReverse ? p - nedge : p + nedge;
             }
         }
         LaneState s;
         SetFull(t, s, full);
-        const uint32_t chunks = (uint32_t) ((end - p) >> 4);
+        // body: whole 16-byte chunks; chunk c is at p + 16c (forward) or p - 16(c+1) (reverse)
+        const uint32_t chunks = (uint32_t) ((kReverse ? p - first : end - p) >> 4);
 #pragma unroll
         for (int j = 0; j < kStageSlots; ++j) {
             if ((uint32_t) j < chunks && !l.stop)
-                CopyAsync16(stage + j * 512, p + 16 * j);
+                CopyAsync16(stage + j * 512, kReverse ? p - 16 * (j + 1) : p + 16 * j);
             CopyAsyncCommit();
         }
         for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks && !l.stop); k += kStageSlots) {
@@ -910,11 +963,13 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
                 CopyAsyncWait<kStageSlots - 1>();
                 const uint4 v = LoadShared16(stage + j * 512);
                 const bool had = k + j < chunks && !l.stop;              // this slot was filled for this lane
-                if (k + kStageSlots + j < chunks && !l.stop)
-                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
+                if (k + kStageSlots + j < chunks && !l.stop) {
+                    const size_t c = (size_t) k + kStageSlots + j;
+                    CopyAsync16(stage + j * 512, kReverse ? p - 16 * (c + 1) : p + 16 * c);
+                }
                 CopyAsyncCommit();
                 if (had)
-                    PrefixChunk16<kShortest>(a, t, hot_flags, s, v, l);
+                    PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, v, l);
             }
             // a dead state only leads to dead states: stop the lane (and its fetches) once it is noticed
             if (!l.stop) {
@@ -925,26 +980,38 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
         }
         CopyAsyncWait<0>();
         full = FullState(t, s);
-        p += 16 * (size_t) chunks;
-        if (p < end && !l.stop) {
-            const uint32_t ntail = (uint32_t) (end - p);
-            if (reinterpret_cast<uintptr_t>(p) + 16 <= buf_hi) {
-                EdgeBytes eb(LoadEdge16(p), 0);
-                for (uint32_t k = 0; k < ntail && !l.stop; ++k) {
-                    full = SlowStep(t, full, eb.Next());
+        p = kReverse ? p - 16 * (size_t) chunks : p + 16 * (size_t) chunks;
+        // edge bytes on the far side: fewer than 16, p is on a 16-byte boundary
+        const uint32_t nfar = (uint32_t) (kReverse ? p - first : end - p);
+        if (nfar != 0 && !l.stop) {
+            const uint8_t* chunk = kReverse ? p - 16 : p;
+            const bool whole = reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi;
+            if (kReverse) {
+                EdgeBytesDown eb(whole ? LoadEdge16(chunk) : make_uint4(0, 0, 0, 0), 15);
+                for (uint32_t k = 0; k < nfar && !l.stop; ++k) {
+                    const uint32_t byte = whole ? eb.Next() : (uint32_t) p[-1 - (int) k];
+                    full = SlowStep(t, full, byte);
                     ++l.consumed;
                     PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
                 }
             } else {
-                for (uint32_t k = 0; k < ntail && !l.stop; ++k) {
-                    full = SlowStep(t, full, p[k]);
+                EdgeBytes eb(whole ? LoadEdge16(chunk) : make_uint4(0, 0, 0, 0), 0);
+                for (uint32_t k = 0; k < nfar && !l.stop; ++k) {
+                    const uint32_t byte = whole ? eb.Next() : (uint32_t) p[k];
+                    full = SlowStep(t, full, byte);
                     ++l.consumed;
                     PrefixCheck<kShortest>(a, t.H, hot_flags, full, l);
                 }
             }
         }
         if (valid) {
-            if (a.through_end) {                                         // run.h:286-290 / :305-309
+            if (kReverse && kShortest) {
+                // run.h:357-360: the last mark is stepped from wherever the scan stopped, and the answer is
+                // the stopping place if that state is final
+                if (a.through_end)
+                    full = FullNext(t, full, a.end_class);
+                l.pos = (__ldg(a.flags + full) & 1u) ? l.consumed : kNoPrefix;
+            } else if (a.through_end) {                                  // run.h:286-290 / :305-309 / :336-340
                 const uint32_t last = FullNext(t, full, a.end_class);
                 if ((__ldg(a.flags + last) & 1u) && (!kShortest || l.pos == kNoPrefix))
                     l.pos = len;
@@ -1423,11 +1490,14 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     return err;
 }
 
-cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream)
+cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, bool reverse, int device, cudaStream_t stream)
 {
     if (a.n == 0)
         return cudaSuccess;
-    const void* fn = shortest ? reinterpret_cast<const void*>(&PrefixKernel<true>) : reinterpret_cast<const void*>(&PrefixKernel<false>);
+    const void* fn = reverse ? (shortest ? reinterpret_cast<const void*>(&PrefixKernel<true, true>)
+                                         : reinterpret_cast<const void*>(&PrefixKernel<false, true>))
+                             : (shortest ? reinterpret_cast<const void*>(&PrefixKernel<true, false>)
+                                         : reinterpret_cast<const void*>(&PrefixKernel<false, false>));
     int optin = 0, sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err == cudaSuccess)

@@ -72,7 +72,9 @@ cudaError_t PrepareScanKernels(int device);                       // raises the 
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
-cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, int device, cudaStream_t stream);
+// prefix (left to right) or suffix (right to left) scan; a.with_begin/begin_class name the mark stepped first,
+// a.through_end/end_class the mark stepped last
+cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, bool reverse, int device, cudaStream_t stream);
 cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream);
 // d_order <- string indices, longest half-octave length bucket first, corpus order inside a bucket (stable CUB radix sort).
 // stream-ordered scratch from the library's own per-device pool (see scan_kernels.cu)

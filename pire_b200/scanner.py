@@ -323,15 +323,15 @@ def Matches(sc, batch):
     return Runner(sc).Run(batch).Matches()
 
 
-def _prefix(sc, batch, shortest, throughBeginMark, throughEndMark):
+def _prefix(sc, batch, shortest, throughBeginMark, throughEndMark, suffix=False):
     torch = _torch()
     out = torch.empty(batch.n, dtype=torch.int32, device=batch.device)
     flags = (N.RUN_BEGIN if throughBeginMark else 0) | (N.RUN_END if throughEndMark else 0) | (N.RUN_LINES if batch.trim else 0)
     stream = torch.cuda.current_stream(batch.device).cuda_stream
-    N.check(N.lib.pire_gpu_prefix_batch(sc._h, batch.corpus.data_ptr(),
-                                        batch.offsets.data_ptr() if batch.offsets is not None else None,
-                                        batch.fixed_len, batch.n, flags, int(shortest), out.data_ptr(), stream),
-            "pire_gpu_prefix_batch")
+    fn = N.lib.pire_gpu_suffix_batch if suffix else N.lib.pire_gpu_prefix_batch
+    N.check(fn(sc._h, batch.corpus.data_ptr(), batch.offsets.data_ptr() if batch.offsets is not None else None,
+               batch.fixed_len, batch.n, flags, int(shortest), out.data_ptr(), stream),
+            "pire_gpu_suffix_batch" if suffix else "pire_gpu_prefix_batch")
     res = out.cpu().numpy().view(np.uint32).astype(np.int64)
     res[res == 0xFFFFFFFF] = -1
     return res
@@ -345,6 +345,16 @@ def LongestPrefix(sc, batch, throughBeginMark=False, throughEndMark=False):
 def ShortestPrefix(sc, batch, throughBeginMark=False, throughEndMark=False):
     """Pire::ShortestPrefix (run.h:294-311) per string: prefix length, or -1 where the reference returns null."""
     return _prefix(sc, batch, True, throughBeginMark, throughEndMark)
+
+
+def LongestSuffix(sc, batch, throughEndMark=False, throughBeginMark=False):
+    """Pire::LongestSuffix (run.h:316-342) per string, walked from its last byte: suffix length, or -1 for null."""
+    return _prefix(sc, batch, False, throughBeginMark, throughEndMark, suffix=True)
+
+
+def ShortestSuffix(sc, batch, throughEndMark=False, throughBeginMark=False):
+    """Pire::ShortestSuffix (run.h:345-362) per string: suffix length, or -1 for null."""
+    return _prefix(sc, batch, True, throughBeginMark, throughEndMark, suffix=True)
 
 
 class HalfFinalResult:

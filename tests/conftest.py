@@ -70,7 +70,14 @@ def load_golden_counts():
         return [CountCase(c) for c in json.load(f)["count_cases"]]
 
 
+def load_golden_suffix():
+    with open(os.path.join(HERE, "golden", "pire_golden.json")) as f:
+        return [(bytes.fromhex(c["pattern"]), base64.b64decode(c["image"]), [bytes.fromhex(t) for t in c["texts"]], c["shortest"],
+                 c["longest"]) for c in json.load(f)["suffix_cases"]]
+
+
 GOLDEN = load_golden()
+GOLDEN_SUFFIX = load_golden_suffix()
 GOLDEN_COUNTS = load_golden_counts()
 GOLDEN_PREFIX = load_golden_prefix()
 

@@ -80,6 +80,19 @@ class RefScanner:
         assert rc == 0
         return out
 
+    def suffix(self, corpus, offsets=None, fixed_len=0, n=None, shortest=False, through_end=False, through_begin=False,
+               variant=2):
+        """Pire::LongestSuffix / ShortestSuffix per string (walked from its last byte): length or -1."""
+        corpus = np.ascontiguousarray(corpus, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            n = len(offsets) - 1 if n is None else n
+        out = np.zeros(n, np.int64)
+        rc = self._lib.pref_suffix_batch(self._h, variant, int(shortest), _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n,
+                                         int(through_end), int(through_begin), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert rc == 0
+        return out
+
     def run(self, corpus, offsets=None, fixed_len=0, n=None, begin=True, end=True, variant=1, threads=1,
             want=("final", "mask", "state")):
         """Runner(sc).[Begin()].Run(str).[End()] per string (run.h:365-392)."""
@@ -162,6 +175,8 @@ class Ref:
         lib.pref_run_batch.argtypes = [C.c_void_p, C.c_int, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                        C.c_int, u8p, u32p, u32p]
         lib.pref_prefix_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int64)]
+        lib.pref_suffix_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
                                           C.POINTER(C.c_int64)]
         lib.pref_hardware_threads.restype = C.c_uint
         lib.pref_hf_compile.restype = C.c_void_p
@@ -262,6 +277,9 @@ class Oracle:
             lib.pire_oracle_prefix_batch.restype = None
             lib.pire_oracle_prefix_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64, C.c_int,
                                                      C.c_int, C.c_int, C.POINTER(C.c_int64)]
+            lib.pire_oracle_suffix_batch.restype = None
+            lib.pire_oracle_suffix_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64, C.c_int,
+                                                     C.c_int, C.c_int, C.POINTER(C.c_int64)]
             lib.pire_oracle_count_batch.restype = None
             lib.pire_oracle_count_batch.argtypes = [C.POINTER(_OracleStruct), u8p, u64p, C.c_uint64, C.c_uint64, C.c_int,
                                                     C.c_int, u32p, u8p]
@@ -316,6 +334,18 @@ def oracle_prefix(orc, corpus, offsets=None, fixed_len=0, n=None, shortest=False
     out = np.zeros(n, np.int64)
     Oracle._lib.pire_oracle_prefix_batch(C.byref(orc._sc), _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n,
                                          int(through_begin), int(through_end), int(shortest),
+                                         out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return out
+
+
+def oracle_suffix(orc, corpus, offsets=None, fixed_len=0, n=None, shortest=False, through_end=False, through_begin=False):
+    corpus = np.ascontiguousarray(corpus, dtype=np.uint8)
+    if offsets is not None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1 if n is None else n
+    out = np.zeros(n, np.int64)
+    Oracle._lib.pire_oracle_suffix_batch(C.byref(orc._sc), _ptr(corpus, u8p), _ptr(offsets, u64p), fixed_len, n,
+                                         int(through_end), int(through_begin), int(shortest),
                                          out.ctypes.data_as(C.POINTER(C.c_int64)))
     return out
 

@@ -607,3 +607,56 @@ def test_half_final_scanner_matches_like_scanner(cuda_device, ref):
         sc = P.Scanner(ref_sc.save(), cuda_device)
         final, _, _ = gpu_run(sc, strs)
         assert (final == wfin).all(), pat
+
+
+def test_suffix_scans_golden(cuda_device):
+    """Pire::LongestSuffix / ShortestSuffix on the device: PrefixSuffix@278 and, like ScanBoundaries@469-471, the
+    prefix table through the suffix scans on the reversed text."""
+    import pire_b200 as P
+    from conftest import GOLDEN_PREFIX, GOLDEN_SUFFIX
+    for pat, image, texts, shortest, longest in GOLDEN_SUFFIX:
+        sc = P.Scanner(image, cuda_device)
+        batch = P.Batch.from_strings(texts)
+        assert P.ShortestSuffix(sc, batch).tolist() == shortest and P.LongestSuffix(sc, batch).tolist() == longest
+    for pat, image, text, shortest, longest in GOLDEN_PREFIX:
+        sc = P.Scanner(image, cuda_device)
+        batch = P.Batch.from_strings([b"junk", text[::-1], b"", b"tail" + text[::-1]])
+        s = P.ShortestSuffix(sc, batch)
+        l = P.LongestSuffix(sc, batch)
+        assert s[1] == shortest and l[1] == longest, (pat, s.tolist(), l.tolist())
+
+
+def test_suffix_scans_vs_reference(cuda_device, ref):
+    """Random text, every mark combination (incl. ShortestSuffix stepping BeginMark from where it stopped), every
+    start alignment through ragged neighbours, hot sets small enough to force cold states; fixed-length batch."""
+    import torch
+    import pire_b200 as P
+    from refpire import oracle_suffix
+    rng = np.random.default_rng(34)
+    for pat, opts in [(b"a+b", "n"), (b"a+b", "nr"), (b"foo.*bar", "n"), (rb"[0-9]+\.[0-9]+", "r"), (b"x*", "n"), (b"(ab)*c", "nr"),
+                      (b".*z", "n"), (b"^ab", ""), (b"ab$", "r"), (b"[^x]*", "n")]:
+        sc_ref = ref.compile(pat, opts)
+        image = sc_ref.save()
+        orc = Oracle(image)
+        strs = [bytes(rng.choice(np.frombuffer(b"abfoxz019. r", np.uint8), size=int(n))) for n in rng.integers(0, 400, size=700)]
+        strs += [b"a" * n for n in (15, 16, 17, 31, 32, 33, 64)] + [b"ab" * 40 + b"z" * k for k in range(0, 20)]
+        corpus, offs = csr(strs)
+        batch = P.Batch.from_strings(strs)
+        for max_hot in (255, 2):
+            sc = P.Scanner(image, cuda_device)
+            sc.set_max_hot(max_hot)
+            for te in (False, True):
+                for tb in (False, True):
+                    for shortest in (False, True):
+                        fn = P.ShortestSuffix if shortest else P.LongestSuffix
+                        got = fn(sc, batch, throughEndMark=te, throughBeginMark=tb)
+                        want = sc_ref.suffix(corpus, offs, shortest=shortest, through_end=te, through_begin=tb, variant=2)
+                        assert (got == want).all(), (pat, opts, max_hot, te, tb, shortest, np.nonzero(got != want)[0][:5])
+                        assert (got == oracle_suffix(orc, corpus, offs, shortest=shortest, through_end=te, through_begin=tb)).all()
+    sc_ref = ref.compile(b"ab+c", "r")
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    host = rng.choice(np.frombuffer(b"abc ", np.uint8), size=(5000, 72)).reshape(-1)
+    batch = P.Batch(torch.from_numpy(host).to("cuda:0"), fixed_len=72, n=5000)
+    for shortest in (False, True):
+        got = (P.ShortestSuffix if shortest else P.LongestSuffix)(sc, batch)
+        assert (got == sc_ref.suffix(host, fixed_len=72, n=5000, shortest=shortest, variant=2)).all()

@@ -138,3 +138,38 @@ def test_oracle_half_final_vs_reference_live(ref):
                 want, wfin = sc.count(corpus, offs, begin=begin, end=end)
                 got, gfin = oracle_count(orc, corpus, offs, begin=begin, end=end)
                 assert (want == got).all() and (wfin == gfin).all(), (pat, begin, end)
+
+
+def test_oracle_suffix_scans_match_golden():
+    """PrefixSuffix@278 (scanner of the reversed pattern) and ScanBoundaries@469-471 (the prefix table through the
+    suffix scans on the reversed text)."""
+    from conftest import GOLDEN_PREFIX, GOLDEN_SUFFIX
+    from refpire import oracle_suffix
+    for pat, image, texts, shortest, longest in GOLDEN_SUFFIX:
+        orc = Oracle(image)
+        corpus, offs = csr(texts)
+        assert oracle_suffix(orc, corpus, offs, shortest=True).tolist() == shortest
+        assert oracle_suffix(orc, corpus, offs, shortest=False).tolist() == longest
+    for pat, image, text, shortest, longest in GOLDEN_PREFIX:
+        orc = Oracle(image)
+        corpus, offs = csr([b"junk", text[::-1], b""])
+        assert oracle_suffix(orc, corpus, offs, shortest=True)[1] == shortest, pat
+        assert oracle_suffix(orc, corpus, offs, shortest=False)[1] == longest, pat
+
+
+def test_oracle_suffix_scans_vs_reference_live(ref):
+    from refpire import oracle_suffix
+    rng = np.random.default_rng(22)
+    for pat, opts in [(b"a+b", "n"), (b"a+b", "nr"), (b"foo.*bar", "n"), (b"x*", "n"), (b"(ab)*c", "nr"), (b".*z", "n"), (b"^ab", ""),
+                      (b"ab$", "r"), (b"[^x]*", "n")]:
+        sc = ref.compile(pat, opts)
+        orc = Oracle(sc.save())
+        strs = [bytes(rng.choice(np.frombuffer(b"abfoxz019. r", np.uint8), size=int(n))) for n in rng.integers(0, 90, size=300)]
+        corpus, offs = csr(strs)
+        for te in (False, True):
+            for tb in (False, True):
+                for shortest in (False, True):
+                    want = sc.suffix(corpus, offs, shortest=shortest, through_end=te, through_begin=tb, variant=2)
+                    assert (want == sc.suffix(corpus, offs, shortest=shortest, through_end=te, through_begin=tb, variant=0)).all()
+                    got = oracle_suffix(orc, corpus, offs, shortest=shortest, through_end=te, through_begin=tb)
+                    assert (got == want).all(), (pat, opts, te, tb, shortest)
