@@ -76,6 +76,25 @@ rng = np.random.default_rng(5)
 fx = rng.choice(np.frombuffer("x\u0424y ab".encode() + bytes(range(120, 256)), np.uint8), size=(1024, 64)).reshape(-1)
 fb = P.Batch(torch.from_numpy(fx).to(dev), fixed_len=64, n=1024)
 check(sc, orc, fb, fx, None, 64, 1024, "tiny DFA, high bytes, PRIV")
+# prefix and suffix scans (all four kernels), ragged + fixed, tiny hot set
+from refpire import oracle_prefix, oracle_suffix
+for name in ("headline", "count_words5"):
+    image = W.load_image(name)
+    orc = Oracle(image)
+    strings = [b"", b"x", b"hello  world", b"ab cd" * 40, b"a" * 33, b"zz hello\tworld", b"q" * 100] * 30
+    c, o = csr(strings)
+    bb = P.Batch.from_strings(strings)
+    for max_hot in (255, 2):
+        sc = P.Scanner(image, 0)
+        sc.set_max_hot(max_hot)
+        for shortest in (False, True):
+            for m1 in (False, True):
+                for m2 in (False, True):
+                    got = (P.ShortestPrefix if shortest else P.LongestPrefix)(sc, bb, throughBeginMark=m1, throughEndMark=m2)
+                    assert (got == oracle_prefix(orc, c, o, shortest=shortest, through_begin=m1, through_end=m2)).all()
+                    got = (P.ShortestSuffix if shortest else P.LongestSuffix)(sc, bb, throughEndMark=m1, throughBeginMark=m2)
+                    assert (got == oracle_suffix(orc, c, o, shortest=shortest, through_end=m1, through_begin=m2)).all()
+    print("ok prefix/suffix", name, flush=True)
 # counting kernels (HalfFinalScanner): accept lists / packed / packed on every chunk, tiny hot sets, ragged + fixed
 from refpire import oracle_count
 for name in ("hf_glue10", "count_words5"):
