@@ -457,6 +457,39 @@ def main():
         except Exception as ex:      # noqa: BLE001
             also = {"error": repr(ex)}
 
+    # the rows next to the path on the same resident bytes, a few launches each: LongestPrefix with this
+    # workload's automaton and HalfFinalScanner counting with the ten patterns glued as HalfFinalScanners
+    next_rows = None
+    if not mixed:
+        try:
+            lens = torch.empty(n_local, dtype=torch.int32, device=dev)
+            hf = P.Scanner(W.load_image("hf_glue10"), local)
+            counts = torch.empty((n_local, hf.RegexpsCount()), dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+
+            def prefix_run():
+                N.check(N.lib.pire_gpu_prefix_batch(sc._h, corpus.data_ptr(), None, STRING_LEN, n_local, flags, 0, lens.data_ptr(), stream),
+                        "pire_gpu_prefix_batch")
+
+            def count_run():
+                N.check(N.lib.pire_gpu_count_batch(hf._h, corpus.data_ptr(), None, STRING_LEN, n_local, flags, counts.data_ptr(), None,
+                                                   stream), "pire_gpu_count_batch")
+            next_rows = {}
+            for key, fn in (("longest_prefix", prefix_run), ("half_final_count_hf_glue10", count_run)):
+                fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                next_rows[key] = {"value": payload_local / 1e9 / (e0.elapsed_time(e1) / 3 / 1e3), "unit": "GB/s"}
+            next_rows["note"] = "this GPU only, same resident corpus; parity of these entry points is in tests/test_gpu_parity.py"
+            del lens, counts, hf
+        except Exception as ex:      # noqa: BLE001
+            next_rows = {"error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -498,6 +531,7 @@ def main():
         "clocks": clocks,
         "e2e": e2e,
         "also": also,
+        "next_rows": next_rows,
     }
     if not args.no_cpu and world == 1:
         try:
