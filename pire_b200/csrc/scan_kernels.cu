@@ -436,7 +436,45 @@ struct EdgeBytes {
         hi >>= 8;
         return b;
     }
+    // the remaining bytes as four words, the next byte in bits 0-7 of .x
+    __device__ __forceinline__ uint4 Words() const
+    {
+        return make_uint4((uint32_t) lo, (uint32_t) (lo >> 32), (uint32_t) hi, (uint32_t) (hi >> 32));
+    }
 };
+
+// The first n (1..15) bytes of `v` through the hot rows: whole words with the fast step, the last one to
+// three bytes one by one -- two to three instructions per byte instead of the slow step's compare, branch
+// and table choice.  Short strings (lines of text) consist mostly of such edge bytes.  A lane that is, or
+// ends up, outside the hot rows replays the bytes through the complete table.
+template <bool kPred>
+__device__ __forceinline__ void EdgeFast(const Tables& t, LaneState& s, uint4 v, uint32_t n)
+{
+    const uint32_t before = s.g;
+    uint32_t g = before;
+    const uint32_t words = n >> 2, rest = n & 3;
+    if (words > 0)
+        FastWord<kPred>(t, g, v.x);
+    if (words > 1)
+        FastWord<kPred>(t, g, v.y);
+    if (words > 2)
+        FastWord<kPred>(t, g, v.z);
+    const uint32_t last = words == 0 ? v.x : words == 1 ? v.y : words == 2 ? v.z : v.w;
+    if (rest > 0)
+        FastStep<kPred>(t, g, last, 0x5540);
+    if (rest > 1)
+        FastStep<kPred>(t, g, last, 0x5541);
+    if (rest > 2)
+        FastStep<kPred>(t, g, last, 0x5542);
+    s.g = g;
+    if (g == t.H) {
+        uint32_t full = before == t.H ? s.cold : before;
+        EdgeBytes eb(v, 0);
+        for (uint32_t k = 0; k < n; ++k)
+            full = SlowStep(t, full, eb.Next());
+        SetFull(t, s, full);
+    }
+}
 
 // Generic batch: CSR offsets or arbitrary fixed length / alignment.  Head and
 // tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
@@ -506,18 +544,16 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             if (p < end && misalign != 0) {
                 const uint64_t room = (uint64_t) (end - p);
                 const uint32_t nhead = room < 16 - misalign ? (uint32_t) room : 16 - misalign;
-                uint32_t full = FullState(t, s);
                 const uint8_t* chunk = p - misalign;
                 if (reinterpret_cast<uintptr_t>(chunk) >= buf_lo && reinterpret_cast<uintptr_t>(chunk) + 16 <= buf_hi) {
-                    EdgeBytes eb(LoadEdge16(chunk), misalign);
-                    for (uint32_t k = 0; k < nhead; ++k)
-                        full = SlowStep(t, full, eb.Next());
+                    EdgeFast<kPred>(t, s, EdgeBytes(LoadEdge16(chunk), misalign).Words(), nhead);
                 } else {
+                    uint32_t full = FullState(t, s);
                     for (uint32_t k = 0; k < nhead; ++k)
                         full = SlowStep(t, full, p[k]);
+                    SetFull(t, s, full);
                 }
                 p += nhead;
-                SetFull(t, s, full);
             }
         }
         // body: 16-byte chunks through a four-deep cp.async ring in shared memory (slot
@@ -556,16 +592,14 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             p += 16 * (size_t) chunks;
             if (p < end) {
                 const uint32_t ntail = (uint32_t) (end - p);
-                uint32_t full = FullState(t, s);
                 if (reinterpret_cast<uintptr_t>(p) + 16 <= buf_hi) {
-                    EdgeBytes eb(LoadEdge16(p), 0);
-                    for (uint32_t k = 0; k < ntail; ++k)
-                        full = SlowStep(t, full, eb.Next());
+                    EdgeFast<kPred>(t, s, LoadEdge16(p), ntail);
                 } else {
+                    uint32_t full = FullState(t, s);
                     for (uint32_t k = 0; k < ntail; ++k)
                         full = SlowStep(t, full, p[k]);
+                    SetFull(t, s, full);
                 }
-                SetFull(t, s, full);
             }
         }
         if (a.order)

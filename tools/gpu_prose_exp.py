@@ -37,7 +37,23 @@ for name in ("headline", "glue10"):
         e1.record(); torch.cuda.synchronize()
         res[vname] = len(data) / 1e9 / (e0.elapsed_time(e1) / 5 / 1e3)
     matched = int((masks != 0).sum().item())
-    line = "%-8s GPU plain %.1f GB/s, pred %.1f GB/s, %d matching lines" % (name, res["plain"], res["pred"], matched)
+    # the same lines claimed in half-octave length buckets (pire_gpu_length_order): less divergence inside a warp
+    import copy
+    binned = copy.copy(batch)
+    binned.bin_by_length()
+    sc.set_variant(N.VARIANT_PLAIN)
+    masks2 = torch.empty(batch.n, dtype=torch.int32, device="cuda:0")
+    for _ in range(2):
+        sc.run_batch(binned, flags, bits, masks2, None)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5):
+        sc.run_batch(binned, flags, bits, masks2, None)
+    e1.record(); torch.cuda.synchronize()
+    res["binned"] = len(data) / 1e9 / (e0.elapsed_time(e1) / 5 / 1e3)
+    assert torch.equal(masks, masks2)
+    line = "%-8s GPU plain %.1f GB/s, pred %.1f GB/s, plain binned by length %.1f GB/s, %d matching lines" % (
+        name, res["plain"], res["pred"], res["binned"], matched)
     if ref:
         sc_ref = ref.glue_all(W.GLUE10 if name == "glue10" else [W.HEADLINE])
         offs = batch.offsets.cpu().numpy().astype(np.uint64)
