@@ -443,7 +443,7 @@ struct EdgeBytes {
     }
 };
 
-// The first n (1..15) bytes of `v` through the hot rows: whole words with the fast step, the last one to
+// The first n (1..16) bytes of `v` through the hot rows: whole words with the fast step, the last one to
 // three bytes one by one -- two to three instructions per byte instead of the slow step's compare, branch
 // and table choice.  Short strings (lines of text) consist mostly of such edge bytes.  A lane that is, or
 // ends up, outside the hot rows replays the bytes through the complete table.
@@ -459,6 +459,8 @@ __device__ __forceinline__ void EdgeFast(const Tables& t, LaneState& s, uint4 v,
         FastWord<kPred>(t, g, v.y);
     if (words > 2)
         FastWord<kPred>(t, g, v.z);
+    if (words > 3)
+        FastWord<kPred>(t, g, v.w);
     const uint32_t last = words == 0 ? v.x : words == 1 ? v.y : words == 2 ? v.z : v.w;
     if (rest > 0)
         FastStep<kPred>(t, g, last, 0x5540);
@@ -473,6 +475,55 @@ __device__ __forceinline__ void EdgeFast(const Tables& t, LaneState& s, uint4 v,
         for (uint32_t k = 0; k < n; ++k)
             full = SlowStep(t, full, eb.Next());
         SetFull(t, s, full);
+    }
+}
+
+// An aligned 16-byte chunk that may stick out of the caller's buffer at either end (the very first and the
+// very last chunk of a corpus): bytes outside read as zero.  Out of line, it is rare.
+__device__ __noinline__ uint4 LoadEdge16Clipped(const uint8_t* aligned, uintptr_t buf_lo, uintptr_t buf_hi)
+{
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 16; ++k) {
+        const uintptr_t at = reinterpret_cast<uintptr_t>(aligned) + k;
+        if (at >= buf_lo && at < buf_hi)
+            w[k >> 2] |= (uint32_t) aligned[k] << (8 * (k & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ uint4 LoadChunk16(const uint8_t* aligned, uintptr_t buf_lo, uintptr_t buf_hi)
+{
+    if (reinterpret_cast<uintptr_t>(aligned) >= buf_lo && reinterpret_cast<uintptr_t>(aligned) + 16 <= buf_hi)
+        return LoadEdge16(aligned);
+    return LoadEdge16Clipped(aligned, buf_lo, buf_hi);
+}
+
+// A unit whose 32 strings are all short (lines of text): no head / body / tail phases and no staging ring,
+// which cost more than the walk at these lengths and leave most lanes idle (each phase lasts as long as its
+// slowest lane).  Every lane walks the aligned 16-byte chunks its string touches in lockstep with the others,
+// one register load per chunk fetched a chunk ahead, the first and last chunk clipped to the string.
+constexpr uint32_t kShortMax = 240;
+
+template <bool kPred>
+__device__ __forceinline__ void ShortUnit(const Tables& t, LaneState& s, const uint8_t* p, uint32_t len, uintptr_t buf_lo, uintptr_t buf_hi)
+{
+    const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
+    const uint8_t* chunk = p - mis;
+    const uint32_t span = mis + len;                            // from the first chunk's start to the string's end
+    const uint32_t pieces = len ? (span + 15) >> 4 : 0;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (pieces > 0)
+        cur = LoadChunk16(chunk, buf_lo, buf_hi);
+    for (uint32_t j = 0; __any_sync(0xffffffffu, j < pieces); ++j) {
+        uint4 next = make_uint4(0, 0, 0, 0);
+        if (j + 1 < pieces)
+            next = LoadChunk16(chunk + 16 * (size_t) (j + 1), buf_lo, buf_hi);
+        if (j < pieces) {
+            const uint32_t skip = j == 0 ? mis : 0;
+            const uint32_t upto = span - 16 * j < 16 ? span - 16 * j : 16;
+            EdgeFast<kPred>(t, s, skip ? EdgeBytes(cur, skip).Words() : cur, upto - skip);
+        }
+        cur = next;
     }
 }
 
@@ -534,6 +585,15 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 
         LaneState s;
         SetFull(t, s, a.start);
+
+        if (__all_sync(0xffffffffu, e - b <= kShortMax)) {
+            ShortUnit<kPred>(t, s, p, (uint32_t) (e - b), buf_lo, buf_hi);
+            if (a.order)
+                ReportScattered(a, t, s, i, valid);
+            else
+                Report(a, t, s, unit, i, valid);
+            continue;
+        }
 
         // head: up to the first 16-byte boundary.  The bytes come from ONE load of the aligned
         // chunk that holds them (the reference's RunChunk does the same with its head word,
