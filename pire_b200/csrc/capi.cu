@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -522,7 +523,17 @@ static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uin
     uint32_t variant = ResolveVariant(sc, false);
     if (variant == PIRE_GPU_VARIANT_PRIV)
         variant = PIRE_GPU_VARIANT_PLAIN;
-    if (ce == cudaSuccess)
+    static const bool lines_kernel = [] {
+        const char* env = getenv("PIRE_B200_LINES_KERNEL");       // experiments: 0 = lines go through the generic kernel
+        return !(env && env[0] == '0');
+    }();
+    if ((flags & PIRE_GPU_RUN_LINES) && !d_order && lines_kernel) {
+        // lines of text: lanes pull lines dynamically and OR their match bits into a zeroed bitmap
+        if (d_match_bits)
+            ce = cudaMemsetAsync(d_match_bits, 0, (size_t) ((n + 31) / 32) * 4, st);
+        if (ce == cudaSuccess)
+            ce = LaunchLines(a, (int) variant, sc->device, st);
+    } else if (ce == cudaSuccess)
         ce = LaunchScan(a, (int) variant, false, sc->plan[variant][0], st);
     if (counter)
         cudaFreeAsync(counter, st);

@@ -498,35 +498,6 @@ __device__ __forceinline__ uint4 LoadChunk16(const uint8_t* aligned, uintptr_t b
     return LoadEdge16Clipped(aligned, buf_lo, buf_hi);
 }
 
-// A unit whose 32 strings are all short (lines of text): no head / body / tail phases and no staging ring,
-// which cost more than the walk at these lengths and leave most lanes idle (each phase lasts as long as its
-// slowest lane).  Every lane walks the aligned 16-byte chunks its string touches in lockstep with the others,
-// one register load per chunk fetched a chunk ahead, the first and last chunk clipped to the string.
-constexpr uint32_t kShortMax = 240;
-
-template <bool kPred>
-__device__ __forceinline__ void ShortUnit(const Tables& t, LaneState& s, const uint8_t* p, uint32_t len, uintptr_t buf_lo, uintptr_t buf_hi)
-{
-    const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
-    const uint8_t* chunk = p - mis;
-    const uint32_t span = mis + len;                            // from the first chunk's start to the string's end
-    const uint32_t pieces = len ? (span + 15) >> 4 : 0;
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (pieces > 0)
-        cur = LoadChunk16(chunk, buf_lo, buf_hi);
-    for (uint32_t j = 0; __any_sync(0xffffffffu, j < pieces); ++j) {
-        uint4 next = make_uint4(0, 0, 0, 0);
-        if (j + 1 < pieces)
-            next = LoadChunk16(chunk + 16 * (size_t) (j + 1), buf_lo, buf_hi);
-        if (j < pieces) {
-            const uint32_t skip = j == 0 ? mis : 0;
-            const uint32_t upto = span - 16 * j < 16 ? span - 16 * j : 16;
-            EdgeFast<kPred>(t, s, skip ? EdgeBytes(cur, skip).Words() : cur, upto - skip);
-        }
-        cur = next;
-    }
-}
-
 // Generic batch: CSR offsets or arbitrary fixed length / alignment.  Head and
 // tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
 // with its word-aligned body.
@@ -585,15 +556,6 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 
         LaneState s;
         SetFull(t, s, a.start);
-
-        if (__all_sync(0xffffffffu, e - b <= kShortMax)) {
-            ShortUnit<kPred>(t, s, p, (uint32_t) (e - b), buf_lo, buf_hi);
-            if (a.order)
-                ReportScattered(a, t, s, i, valid);
-            else
-                Report(a, t, s, unit, i, valid);
-            continue;
-        }
 
         // head: up to the first 16-byte boundary.  The bytes come from ONE load of the aligned
         // chunk that holds them (the reference's RunChunk does the same with its head word,
@@ -666,6 +628,97 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             ReportScattered(a, t, s, i, valid);
         else
             Report(a, t, s, unit, i, valid);
+    }
+}
+
+// ---------------------------------------------------------------- lines of text
+//
+// The step before the path for line-oriented input (samples/pigrep/pigrep.cpp:38-45): strings of a few dozen
+// bytes of very unequal length (the reference's own benchmark prose: median 21 B, 90 % under 80 B, the longest
+// of 32 consecutive lines 115 B on average).  One string per lane in lockstep units wastes three quarters of the
+// lanes there -- each unit lasts as long as its longest line.  Here a warp owns 256 consecutive lines and its
+// lanes pull them one at a time: every iteration each busy lane walks one aligned 16-byte chunk of its line
+// (clipped to the line at both ends, fetched one chunk ahead into registers), and a lane that finishes reports
+// its line and takes the next unassigned one (ballot + popcount over a warp-uniform cursor).  No staging ring:
+// neighbouring lines share cache lines, so the chunks come from L1/L2.
+constexpr uint32_t kLinesPerWarp = 256;
+
+template <bool kPred>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.exit_bitmap0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint64_t groups = (a.n + kLinesPerWarp - 1) / kLinesPerWarp;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
+    const uintptr_t buf_hi = buf_lo + (a.offsets[a.n] - a.trim);
+
+    for (uint64_t group = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); group < groups; group += warps) {
+        const uint64_t last = (group + 1) * kLinesPerWarp < a.n ? (group + 1) * kLinesPerWarp : a.n;
+        uint64_t cursor = group * kLinesPerWarp;             // next unassigned line, the same in every lane
+        bool busy = false;
+        uint64_t line = 0;
+        const uint8_t* chunk = a.corpus;
+        uint32_t mis = 0, span = 0, pieces = 0, piece = 0;
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        LaneState s;
+        s.g = 0;
+        s.cold = 0;
+        for (;;) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+            if (idle != 0 && cursor < last) {
+                const uint64_t mine = cursor + __popc(idle & below);
+                cursor += __popc(idle);
+                if (!busy && mine < last) {
+                    line = mine;
+                    const uint64_t b = a.offsets[line];
+                    const uint64_t e = a.offsets[line + 1] - a.trim;
+                    const uint8_t* p = a.corpus + b;
+                    const uint32_t len = (uint32_t) (e - b);
+                    mis = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
+                    chunk = p - mis;
+                    span = mis + len;
+                    pieces = len ? (span + 15) >> 4 : 0;
+                    piece = 0;
+                    SetFull(t, s, a.start);
+                    busy = true;
+                    if (pieces)
+                        cur = LoadChunk16(chunk, buf_lo, buf_hi);
+                }
+            }
+            if (!__any_sync(0xffffffffu, busy))
+                break;
+            if (busy) {
+                if (piece < pieces) {
+                    uint4 next = make_uint4(0, 0, 0, 0);
+                    if (piece + 1 < pieces)
+                        next = LoadChunk16(chunk + 16 * (size_t) (piece + 1), buf_lo, buf_hi);
+                    const uint32_t skip = piece == 0 ? mis : 0;
+                    const uint32_t left = span - 16 * piece;
+                    const uint32_t upto = left < 16 ? left : 16;
+                    EdgeFast<kPred>(t, s, skip ? EdgeBytes(cur, skip).Words() : cur, upto - skip);
+                    cur = next;
+                    ++piece;
+                }
+                if (piece >= pieces) {
+                    ReportScattered(a, t, s, line, true);
+                    busy = false;
+                }
+            }
+        }
     }
 }
 
@@ -1610,6 +1663,36 @@ cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, bool reverse, int dev
     return err;
 }
 
+
+// Lines of text (CSR, PIRE_GPU_RUN_LINES, no order): lanes pull lines dynamically.  The caller zeroes the bitmap.
+cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t stream)
+{
+    if (a.n == 0)
+        return cudaSuccess;
+    const void* fn = variant == kVariantPred ? reinterpret_cast<const void*>(&ScanLinesKernel<true>)
+                                             : reinterpret_cast<const void*>(&ScanLinesKernel<false>);
+    const size_t shared = ScanSharedBytes(a.hot, 0);
+    int optin = 0, sms = 0, per_sm = 0;
+    cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err == cudaSuccess)
+        err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err == cudaSuccess)
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, shared);
+    if (err != cudaSuccess)
+        return err;
+    if (per_sm < 1)
+        return cudaErrorLaunchOutOfResources;
+    const uint64_t groups = (a.n + kLinesPerWarp - 1) / kLinesPerWarp;
+    const uint64_t want = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int grid = (int) (want < (uint64_t) sms * per_sm ? want : (uint64_t) sms * per_sm);
+    void* args[] = {const_cast<ScanArgs*>(&a)};
+    err = cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, shared, stream);
+    if (err == cudaSuccess)
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    return err;
+}
 
 cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream)
 {
