@@ -642,6 +642,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 // its line and takes the next unassigned one (ballot + popcount over a warp-uniform cursor).  No staging ring:
 // neighbouring lines share cache lines, so the chunks come from L1/L2.
 constexpr uint32_t kLinesPerWarp = 256;
+constexpr uint32_t kPiecesPerTurn = 3;
 
 template <bool kPred>
 __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const __grid_constant__ ScanArgs a)
@@ -702,7 +703,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
             if (!__any_sync(0xffffffffu, busy))
                 break;
             if (busy) {
-                if (piece < pieces) {
+                // up to kPiecesPerTurn chunks before the lanes look for new lines again: most lines end within
+                // one turn, and the bookkeeping around a turn costs as much as walking two chunks
+#pragma unroll 1
+                for (uint32_t turn = 0; turn < kPiecesPerTurn && piece < pieces; ++turn) {
                     uint4 next = make_uint4(0, 0, 0, 0);
                     if (piece + 1 < pieces)
                         next = LoadChunk16(chunk + 16 * (size_t) (piece + 1), buf_lo, buf_hi);
