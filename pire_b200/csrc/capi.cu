@@ -119,7 +119,12 @@ uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform = true)
     if (sc->auto_choice[uniform ? 1 : 0])
         return sc->auto_choice[uniform ? 1 : 0];
     // AUTO: predication pays when lanes outside the resident state would
-    // collide with it in the banks, i.e. for large (glued) automata.
+    // collide with it in the banks, i.e. for large (glued) automata -- in the uniform kernel, which is bound
+    // by shared-memory wavefronts.  The CSR kernels (generic, lines) are bound by instruction issue on short
+    // strings, where the filter's two extra instructions per byte cost more than the conflicts they save
+    // (lines of text, glued ten: 903 GB/s plain, 717 pred).
+    if (!uniform)
+        return PIRE_GPU_VARIANT_PLAIN;
     return sc->tab.states > 64 ? PIRE_GPU_VARIANT_PRED : PIRE_GPU_VARIANT_PLAIN;
 }
 
