@@ -76,6 +76,30 @@ rng = np.random.default_rng(5)
 fx = rng.choice(np.frombuffer("x\u0424y ab".encode() + bytes(range(120, 256)), np.uint8), size=(1024, 64)).reshape(-1)
 fb = P.Batch(torch.from_numpy(fx).to(dev), fixed_len=64, n=1024)
 check(sc, orc, fb, fx, None, 64, 1024, "tiny DFA, high bytes, PRIV")
+# lines of text: split on the device, lines kernel (plain / pred) and the generic kernel on the same lines;
+# the text starts and ends off a 16-byte boundary so that the clipped chunk loads are exercised
+rng = np.random.default_rng(9)
+words = [b"hello", b"world", b"GET /x", b"error", b"timeout", b"", b"fatal https://a", b"x" * 70, b"hello   wd"]
+text_lines = [b" ".join(words[int(j)] for j in rng.integers(0, len(words), size=int(k))) for k in rng.integers(0, 9, size=3000)]
+blob = b"\n".join(text_lines) + b"\n"
+pad = torch.zeros(len(blob) + 64, dtype=torch.uint8, device=dev)
+text_dev = pad[5:5 + len(blob)]
+text_dev.copy_(torch.from_numpy(np.frombuffer(blob, np.uint8).copy()))
+lb = P.Batch.from_text(text_dev)
+assert lb.n == len(text_lines)
+c, o = csr(text_lines)
+for name in ("headline", "glue10"):
+    image = W.load_image(name)
+    orc = Oracle(image)
+    f, m, s_ = orc.run(c, o)
+    for max_hot in (255, 2):
+        sc = P.Scanner(image, 0)
+        sc.set_max_hot(max_hot)
+        for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED):
+            sc.set_variant(variant)
+            r = P.Runner(sc).Begin().Run(lb).End()
+            assert (r.Matches().astype(np.uint8) == f).all() and (r.AcceptMasks() == m).all() and (r.States() == s_).all(), (name, max_hot, variant)
+print("ok lines", flush=True)
 # prefix and suffix scans (all four kernels), ragged + fixed, tiny hot set
 from refpire import oracle_prefix, oracle_suffix
 for name in ("headline", "count_words5"):
