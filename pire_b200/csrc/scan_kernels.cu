@@ -631,124 +631,6 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     }
 }
 
-// ---------------------------------------------------------------- ragged batches, 32-byte body
-//
-// The same contract as ScanGenericKernel (CSR or any fixed length / alignment, optional length-binned
-// claiming), but the body of every string is fetched like the uniform kernel fetches: one LDG.256 per lane
-// per 32 bytes into a ping-pong register set, one request ahead.  Per-lane requests to far-apart addresses
-// are bound by the request rate of the memory system, not by bytes (load microbenchmark, 64 KiB stride:
-// 16 B per request 2.0 TB/s, 32 B per request 4.0 TB/s), and cp.async moves at most 16 bytes.
-template <bool kPred>
-__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanRaggedKernel(const __grid_constant__ ScanArgs a)
-{
-    uint8_t* const smem = pire_b200_smem;
-    SharedView sv = CarveShared(smem, a.hot);
-    StageTables(a, sv, a.hot8, a.hot);
-
-    Tables t;
-    t.hot = sv.hot;
-    t.cls = sv.cls;
-    t.full = a.full;
-    t.H = a.hot;
-    t.letters = a.letters;
-    t.wide = a.wide;
-    t.m0 = a.exit_bitmap0;
-
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t units = (a.n + 31) / 32;
-    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
-    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
-    const uintptr_t buf_hi = buf_lo + (a.offsets ? a.offsets[a.n] - a.trim : a.n * a.fixed_len);
-
-    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);; unit += warps) {
-        if (a.work_counter) {
-            unsigned int claimed = 0;
-            if (lane == 0)
-                claimed = atomicAdd(a.work_counter, 1u);
-            unit = __shfl_sync(0xffffffffu, claimed, 0);
-        }
-        if (unit >= units)
-            break;
-        const uint64_t slot = unit * 32 + lane;
-        const bool valid = slot < a.n;
-        const uint64_t i = valid && a.order ? a.order[slot] : slot;
-        uint64_t b = 0, e = 0;
-        if (valid) {
-            if (a.offsets) {
-                b = a.offsets[i];
-                e = a.offsets[i + 1] - a.trim;
-            } else {
-                b = i * a.fixed_len;
-                e = b + a.fixed_len;
-            }
-        }
-        const uint8_t* p = a.corpus + b;
-        const uint8_t* end = a.corpus + e;
-
-        LaneState s;
-        SetFull(t, s, a.start);
-
-        // head: up to the first 32-byte boundary, at most two clipped 16-byte chunks
-        {
-            const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 31);
-            if (p < end && mis != 0) {
-                const uint64_t room = (uint64_t) (end - p);
-                const uint32_t nhead = room < 32 - mis ? (uint32_t) room : 32 - mis;
-                const uint32_t skip = mis & 15;
-                const uint8_t* chunk = p - skip;
-                const uint32_t first = nhead < 16 - skip ? nhead : 16 - skip;
-                EdgeFast<kPred>(t, s, EdgeBytes(LoadChunk16(chunk, buf_lo, buf_hi), skip).Words(), first);
-                if (nhead > first)
-                    EdgeFast<kPred>(t, s, LoadChunk16(chunk + 16, buf_lo, buf_hi), nhead - first);
-                p += nhead;
-            }
-        }
-        // body: 32 bytes per request, two register sets in ping-pong
-        const uint32_t body = (uint32_t) ((end - p) >> 5);
-        bool parked = false;
-        {
-            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
-            if (body > 0)
-                LoadStream32(p, a0, a1);
-            for (uint32_t k = 0; __any_sync(0xffffffffu, k < body); k += 2) {
-                if (k + 1 < body)
-                    LoadStream32(p + 32 * (size_t) (k + 1), b0, b1);
-                if (k < body) {
-                    Chunk16<kPred>(t, s, a0);
-                    Chunk16<kPred>(t, s, a1);
-                }
-                if (k + 2 < body)
-                    LoadStream32(p + 32 * (size_t) (k + 2), a0, a1);
-                if (k + 1 < body) {
-                    Chunk16<kPred>(t, s, b0);
-                    Chunk16<kPred>(t, s, b1);
-                }
-                // multi.h:955-958,:979-982: a NoExit state cannot be left by any byte.
-                const bool live = k + 2 < body;
-                const bool stuck = sv.noexit[s.g] != 0;
-                if (__all_sync(0xffffffffu, !live || stuck)) {
-                    parked = live && stuck;
-                    break;
-                }
-            }
-        }
-        // tail: fewer than 32 bytes at a 32-byte boundary
-        if (!parked) {
-            p += 32 * (size_t) body;
-            if (p < end) {
-                const uint32_t ntail = (uint32_t) (end - p);
-                EdgeFast<kPred>(t, s, LoadChunk16(p, buf_lo, buf_hi), ntail < 16 ? ntail : 16);
-                if (ntail > 16)
-                    EdgeFast<kPred>(t, s, LoadChunk16(p + 16, buf_lo, buf_hi), ntail - 16);
-            }
-        }
-        if (a.order)
-            ReportScattered(a, t, s, i, valid);
-        else
-            Report(a, t, s, unit, i, valid);
-    }
-}
-
 // ---------------------------------------------------------------- lines of text
 //
 // The step before the path for line-oriented input (samples/pigrep/pigrep.cpp:38-45): strings of a few dozen
@@ -1694,15 +1576,7 @@ const void* KernelFor(int variant, bool uniform)
     const bool pred = variant == kVariantPred;
     if (uniform)
         return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
-    // CSR / ragged batches: PIRE_B200_GENERIC_BODY=ring keeps the cp.async staging ring (16 bytes per request),
-    // the default fetches 32 bytes per request straight into registers
-    static const bool ring = [] {
-        const char* env = getenv("PIRE_B200_GENERIC_BODY");
-        return env && env[0] == 'r';
-    }();
-    if (ring)
-        return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
-    return pred ? reinterpret_cast<const void*>(&ScanRaggedKernel<true>) : reinterpret_cast<const void*>(&ScanRaggedKernel<false>);
+    return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
 }
 
 } // namespace
