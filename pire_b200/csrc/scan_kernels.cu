@@ -642,7 +642,8 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 // its line and takes the next unassigned one (ballot + popcount over a warp-uniform cursor).  No staging ring:
 // neighbouring lines share cache lines, so the chunks come from L1/L2.
 constexpr uint32_t kLinesPerWarp = 256;
-constexpr uint32_t kPiecesPerTurn = 3;
+constexpr uint32_t kPiecesPerTurn = 3;      // chunks a busy lane walks before lines are handed out again
+constexpr uint32_t kLinesMinIdle = 1;       // lanes that must be waiting before lines are handed out
 
 template <bool kPred>
 __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const __grid_constant__ ScanArgs a)
@@ -680,7 +681,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
         s.cold = 0;
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-            if (idle != 0 && cursor < last) {
+            // lines are handed out when enough lanes wait for one (or nobody is busy): handing out costs the
+            // whole warp ~56 instructions however few lanes take part
+            if (cursor < last && ((uint32_t) __popc(idle) >= a.lines_min_idle || idle == 0xffffffffu)) {
                 const uint64_t mine = cursor + __popc(idle & below);
                 cursor += __popc(idle);
                 if (!busy && mine < last) {
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
                 // up to kPiecesPerTurn chunks before the lanes look for new lines again: most lines end within
                 // one turn, and the bookkeeping around a turn costs as much as walking two chunks
 #pragma unroll 1
-                for (uint32_t turn = 0; turn < kPiecesPerTurn && piece < pieces; ++turn) {
+                for (uint32_t turn = 0; turn < a.lines_turn && piece < pieces; ++turn) {
                     uint4 next = make_uint4(0, 0, 0, 0);
                     if (piece + 1 < pieces)
                         next = LoadChunk16(chunk + 16 * (size_t) (piece + 1), buf_lo, buf_hi);
@@ -1691,7 +1694,14 @@ cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t
     const uint64_t groups = (a.n + kLinesPerWarp - 1) / kLinesPerWarp;
     const uint64_t want = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int) (want < (uint64_t) sms * per_sm ? want : (uint64_t) sms * per_sm);
-    void* args[] = {const_cast<ScanArgs*>(&a)};
+    ScanArgs tuned = a;
+    tuned.lines_turn = kPiecesPerTurn;
+    tuned.lines_min_idle = kLinesMinIdle;
+    if (const char* env = getenv("PIRE_B200_LINES_TURN"))          // experiments
+        tuned.lines_turn = atoi(env) > 0 ? (uint32_t) atoi(env) : tuned.lines_turn;
+    if (const char* env = getenv("PIRE_B200_LINES_MIN_IDLE"))
+        tuned.lines_min_idle = atoi(env) > 0 ? (uint32_t) atoi(env) : tuned.lines_min_idle;
+    void* args[] = {&tuned};
     err = cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);

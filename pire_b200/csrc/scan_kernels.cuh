@@ -54,6 +54,8 @@ struct ScanArgs {
     uint32_t with_begin;         // step BeginMark first (with_end == through_end)
     uint32_t regexps;            // counters per string (>= 1)
     uint32_t* counts;            // n * regexps words, zeroed by the caller
+    uint32_t lines_turn;         // lines kernel: chunks per lane between two hand-outs of lines
+    uint32_t lines_min_idle;     // lines kernel: waiting lanes needed for a hand-out
     const uint64_t* weights;     // [states * count_words] packed per-state increments, or null
     uint32_t count_words;        // 0 = walk the accept lists, 1..2 = packed increments
     uint32_t count_always;       // final states are frequent: count every chunk, skip the look-ahead pass
