@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 // its line and takes the next unassigned one (ballot + popcount over a warp-uniform cursor).  No staging ring:
 // neighbouring lines share cache lines, so the chunks come from L1/L2.
 constexpr uint32_t kLinesPerWarp = 256;
-constexpr uint32_t kPiecesPerTurn = 3;      // chunks a busy lane walks before lines are handed out again
+constexpr uint32_t kPiecesPerTurn = 2;      // chunks a busy lane walks before lines are handed out again
 constexpr uint32_t kLinesMinIdle = 1;       // lanes that must be waiting before lines are handed out
 
 template <bool kPred>
