@@ -501,8 +501,8 @@ __device__ __forceinline__ uint4 LoadChunk16(const uint8_t* aligned, uintptr_t b
 // Generic batch: CSR offsets or arbitrary fixed length / alignment.  Head and
 // tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
 // with its word-aligned body.
-template <bool kPred, int kCtas>
-__global__ void __launch_bounds__(kBlock, kCtas) ScanGenericKernel(const __grid_constant__ ScanArgs a)
+template <bool kPred>
+__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
@@ -1569,23 +1569,17 @@ __global__ void __launch_bounds__(256) SynthMixedFillKernel(uint64_t seed, uint3
 
 template <bool kPred>
 const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUniformKernel<kPred>); }
-// The CSR kernel is compiled for two and for three resident CTAs per SM (64 / 42 registers): small automata
-// leave room in shared memory for a third CTA, and sixteen more warps hide more of the table-load latency.
 template <bool kPred>
-const void* GenericKernelPtr(int ctas)
-{
-    return ctas >= 3 ? reinterpret_cast<const void*>(&ScanGenericKernel<kPred, 3>)
-                     : reinterpret_cast<const void*>(&ScanGenericKernel<kPred, kGenericBlocksPerSM>);
-}
+const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kPred>); }
 
-const void* KernelFor(int variant, bool uniform, int ctas = kGenericBlocksPerSM)
+const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
     const bool pred = variant == kVariantPred;
     if (uniform)
         return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
-    return pred ? GenericKernelPtr<true>(ctas) : GenericKernelPtr<false>(ctas);
+    return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
 }
 
 } // namespace
@@ -1604,11 +1598,9 @@ cudaError_t PrepareScanKernels(int device)
         return err;
     for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv})
         for (bool uniform : {false, true}) {
-            for (int ctas : {kGenericBlocksPerSM, 3}) {
-                err = cudaFuncSetAttribute(KernelFor(variant, uniform, ctas), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-                if (err != cudaSuccess)
-                    return err;
-            }
+            err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+            if (err != cudaSuccess)
+                return err;
         }
     return cudaSuccess;
 }
@@ -1622,23 +1614,17 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (err != cudaSuccess)
         return err;
-    plan->ctas = kGenericBlocksPerSM;
-    if (!uniform) {
-        int want = 3;
-        if (const char* env = getenv("PIRE_B200_GENERIC_CTAS"))       // experiments: resident CTAs per SM (2 or 3)
-            want = atoi(env) > 0 ? atoi(env) : want;
-        int fit = 0;
-        if (want >= 3 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, KernelFor(variant, false, 3), plan->block, plan->shared) == cudaSuccess
-            && fit >= 3)
-            plan->ctas = 3;
-    }
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KernelFor(variant, uniform, plan->ctas), plan->block, plan->shared);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KernelFor(variant, uniform), plan->block, plan->shared);
     if (err != cudaSuccess)
         return err;
     if (per_sm < 1)
         return cudaErrorLaunchOutOfResources;
-    if (!uniform)
-        per_sm = per_sm < plan->ctas ? per_sm : plan->ctas;
+    if (!uniform) {
+        int cap = kGenericBlocksPerSM;
+        if (const char* env = getenv("PIRE_B200_GENERIC_CTAS"))       // experiments: resident CTAs per SM
+            cap = atoi(env) > 0 ? atoi(env) : cap;
+        per_sm = per_sm < cap ? per_sm : cap;
+    }
     plan->grid = sms * per_sm;     // persistent: every SM holds its full share of CTAs
     return cudaSuccess;
 }
@@ -1652,7 +1638,7 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     uint64_t want = (units + warps_per_block - 1) / warps_per_block;
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
     void* args[] = {const_cast<ScanArgs*>(&a)};
-    cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform, plan.ctas), dim3(grid), dim3(plan.block), args, plan.shared, stream);
+    cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);
     return err;

@@ -65,7 +65,6 @@ struct LaunchPlan {
     int block = 0;
     int grid = 0;
     size_t shared = 0;
-    int ctas = 2;           // CSR kernel: which instantiation (resident CTAs per SM it is compiled for)
 };
 
 enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3 };
