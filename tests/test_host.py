@@ -66,6 +66,29 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == -4 and "no CPU fallback" in str(e.value)
 
 
+def test_every_device_entry_point_refuses_a_host_only_handle():
+    """prefix / suffix scans, counting, CSR and line runs, tune: all PIRE_GPU_ENODEVICE, none falls back."""
+    import ctypes as C
+    from pire_b200 import _native as N
+    sc = host_scanner(GOLDEN[0].image)
+    fake = C.c_void_p(256)            # never dereferenced: the handle is checked first
+    lib = N.lib
+    calls = [
+        lib.pire_gpu_run_batch(sc._h, fake, None, 32, 2, 3, fake, None, None, None),
+        lib.pire_gpu_run_batch_ordered(sc._h, fake, fake, fake, 2, 3, fake, None, None, None),
+        lib.pire_gpu_run_lines(sc._h, fake, fake, None, 2, 3, fake, None, None, None),
+        lib.pire_gpu_prefix_batch(sc._h, fake, None, 32, 2, 0, 0, fake, None),
+        lib.pire_gpu_suffix_batch(sc._h, fake, None, 32, 2, 0, 1, fake, None),
+        lib.pire_gpu_count_batch(sc._h, fake, None, 32, 2, 3, fake, None, None),
+        lib.pire_gpu_scanner_tune(sc._h, fake, None, 32, 2, 3, None),
+    ]
+    assert calls == [-4] * len(calls)
+    assert b"no CPU fallback" in lib.pire_gpu_last_error()
+    # the count mode is validated on the host
+    assert lib.pire_gpu_scanner_set_count_mode(sc._h, 3) == 0
+    assert lib.pire_gpu_scanner_set_count_mode(sc._h, 4) == -1
+
+
 def test_create_on_missing_device_fails_loudly():
     import torch
     if torch.cuda.is_available():
