@@ -108,14 +108,14 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
     }
 
     // Fused hot rows.
-    t.hot8.assign((size_t) (H + 1) * 256, (uint8_t) H);
+    t.hot8.assign(HotTableBytes(H), (uint8_t) H);
     t.noexit.assign(H + 1, 0);
     for (uint32_t h = 0; h < H; ++h) {
         const uint32_t* row = &dfa.next[(size_t) t.old_of_new[h] * dfa.letters];
         bool stays = true;
         for (uint32_t b = 0; b < 256; ++b) {
             uint32_t to = t.new_of_old[row[dfa.class_of[b]]];
-            t.hot8[(size_t) h * 256 + b] = (uint8_t) (to < H ? to : H);
+            t.hot8[(size_t) h * kHotStride + b] = (uint8_t) (to < H ? to : H);
             stays = stays && to == h;
         }
         t.noexit[h] = stays ? 1 : 0;    // same predicate as BuildShortcuts' NoExit, multi.h:477-514
@@ -140,7 +140,7 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
             for (uint32_t b = 0; b < 128; ++b) {
                 uint32_t to = sink;
                 if (r < real) {
-                    uint32_t h = t.hot8[(size_t) r * 256 + b];
+                    uint32_t h = t.hot8[(size_t) r * kHotStride + b];
                     if (h < real)
                         to = h;
                 }
@@ -151,11 +151,11 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
     {
         const uint32_t Hs = std::min<uint32_t>(H, kPrivHotRows);
         t.hot_small = Hs;
-        t.hot8_small.assign((size_t) (Hs + 1) * 256, (uint8_t) Hs);
+        t.hot8_small.assign(HotTableBytes(Hs), (uint8_t) Hs);
         for (uint32_t h = 0; h < Hs; ++h)
             for (uint32_t b = 0; b < 256; ++b) {
-                uint32_t to = t.hot8[(size_t) h * 256 + b];
-                t.hot8_small[(size_t) h * 256 + b] = (uint8_t) (to < Hs ? to : Hs);
+                uint32_t to = t.hot8[(size_t) h * kHotStride + b];
+                t.hot8_small[(size_t) h * kHotStride + b] = (uint8_t) (to < Hs ? to : Hs);
             }
     }
 

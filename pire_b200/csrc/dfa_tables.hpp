@@ -9,11 +9,12 @@
 //  * states are renumbered so that the H <= 255 most frequently visited ("hot")
 //    states get ids 0..H-1; id H is the "miss" marker;
 //  * hot8[(H+1) x 256]: fused byte-indexed rows for hot states, one u8 per
-//    (state, byte): the next hot id, or H when the target is a cold state.  Row
+//    (state, byte): the next hot id, or H when the target is a cold state; rows are
+//    kHotStride = 292 bytes apart (see below).  Row
 //    H maps every byte to H, so a lane that missed keeps running harmlessly to
 //    the end of its 16-byte chunk and is then replayed through the full table.
-//    The address of an entry is (id << 8) | byte -- one PRMT builds it from the
-//    input word and the state register;
+//    The address of an entry is ((id << 8) | byte) + 36 * id -- one PRMT builds the
+//    first term from the input word and the state register, one IMAD (FMA pipe) adds the second;
 //  * full[states x letters] (u16 when states <= 65536, else u32) + cls[256]:
 //    the complete class-indirect table in the new numbering, L2-resident, used
 //    only for replays, cold states and the unaligned head/tail bytes;
@@ -33,8 +34,15 @@
 namespace pire_b200 {
 
 constexpr uint32_t kMaxHot = 255;
+// Bytes from one fused hot row to the next: 256 entries + 36 bytes of padding, so that consecutive rows start
+// nine banks apart.  Lanes in different rows then spread over the banks instead of meeting in the 24 banks
+// the printable bytes of every row share (host model tools/analyze.cpp, glued ten: 2.44 -> 2.22 wavefronts per
+// step plain, 2.23 -> 2.05 with the exit filter).
+constexpr uint32_t kHotStride = 292;
+// rows are stored in multiples of four so that the table's size stays a multiple of 16 bytes (TMA bulk copy)
+inline size_t HotTableBytes(uint32_t hot) { return (size_t) ((hot + 1 + 3) / 4 * 4) * kHotStride; }
 constexpr uint32_t kMaxPrivRows = 48;     // lane-private rows incl. the sink (12 quads x 16 KB of shared memory)
-constexpr uint32_t kPrivHotRows = 135;    // shared second-tier rows that still fit beside them
+constexpr uint32_t kPrivHotRows = 115;    // shared second-tier rows that still fit beside them (116 x 292 B)
 
 struct FinEntry {
     uint32_t result;   // bit31 = Final(), bits 0..30 = StateIndex() in the reference's numbering
@@ -45,7 +53,7 @@ struct ScanTables {
     uint32_t states = 0, letters = 0, hot = 0;
     bool wide = false;                       // full table entries are u32
     std::vector<uint32_t> new_of_old, old_of_new;
-    std::vector<uint8_t> hot8;               // (hot + 1) * 256
+    std::vector<uint8_t> hot8;               // HotTableBytes(hot): entry of (id, byte) at id * kHotStride + byte
     std::vector<uint8_t> noexit;             // [hot + 1]: 1 = no byte leaves this hot state
     std::vector<uint16_t> cls;               // [256]
     std::vector<uint16_t> full16;
@@ -79,7 +87,7 @@ struct ScanTables {
     // The PRIV kernel's second tier: the same fused rows as hot8, cut to the first
     // hot_small ids (what fits in shared memory next to the private region).
     uint32_t hot_small = 0;
-    std::vector<uint8_t> hot8_small;         // (hot_small + 1) * 256
+    std::vector<uint8_t> hot8_small;         // HotTableBytes(hot_small), same layout
 };
 
 // Default hot order: breadth-first from the start states (states near the start

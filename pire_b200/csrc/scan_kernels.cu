@@ -141,7 +141,8 @@ struct SharedView {
     uint8_t* stage;      // generic kernel only: cp.async ring, kStageBytes
 };
 
-__host__ __device__ inline size_t HotBytes(uint32_t hot) { return (size_t) (hot + 1) * 256; }
+__host__ __device__ inline size_t HotBytes(uint32_t hot) { return (size_t) ((hot + 1 + 3) / 4 * 4) * kHotStride; }   // == HotTableBytes
+constexpr uint32_t kRowPad = kHotStride - 256;      // bytes a row is pushed beyond (id << 8): nine banks
 __host__ __device__ inline size_t PrivBytes(uint32_t priv_rows) { return (size_t) (priv_rows / 4) * 16384; }
 
 __device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot, uint32_t priv_rows = 0)
@@ -198,7 +199,7 @@ struct Tables {
 __device__ __forceinline__ uint32_t SlowStep(const Tables& t, uint32_t s, uint32_t b)
 {
     if (s < t.H) {
-        uint32_t h = t.hot[(s << 8) | b];
+        uint32_t h = t.hot[s * kHotStride + b];
         if (h != t.H)
             return h;
     }
@@ -227,7 +228,7 @@ __device__ __forceinline__ void SetFull(const Tables& t, LaneState& s, uint32_t 
 template <bool kPred>
 __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t w, uint32_t sel)
 {
-    // idx = (g << 8) | byte_k(w): byte address of the fused row entry.
+    // idx = (g << 8) | byte_k(w); the entry's byte address is idx + g * kRowPad (rows kHotStride apart).
     uint32_t idx = __byte_perm(w, g, sel);
     if (kPred) {
         // bit (byte & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
@@ -247,12 +248,13 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
             "setp.ne.u32 p, probe, 0;\n"
             "mov.u32 addr, pire_b200_smem;\n"          // hot rows start the dynamic array (kPred kernels)
             "add.u32 addr, addr, %1;\n"
+            "mad.lo.u32 addr, %0, %3, addr;\n"         // rows are kHotStride apart: + id * kRowPad (an IMAD, FMA pipe)
             "@p ld.shared.u8 %0, [addr];\n"
             "}\n"
             : "+r"(g)
-            : "r"(idx), "r"(t.m0));
+            : "r"(idx), "r"(t.m0), "n"(kRowPad));
     } else {
-        g = t.hot[idx];
+        g = t.hot[idx + g * kRowPad];
     }
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dfa_tables.hpp"
 #include "synth.h"
 
 namespace pire_b200 {
@@ -23,7 +24,7 @@ struct ScanArgs {
     unsigned int* work_counter;  // with `order`: units are claimed longest-first from this counter
     uint64_t fixed_len;          // used when offsets == nullptr
     uint64_t n;                  // strings
-    const uint8_t* hot8;         // (hot+1)*256 bytes, 16-byte aligned
+    const uint8_t* hot8;         // HotTableBytes(hot) bytes (rows kHotStride apart), 16-byte aligned
     const uint8_t* noexit;       // hot+1 bytes
     const uint16_t* cls;         // 256
     const void* full;            // states*letters, u16 or u32
@@ -35,7 +36,7 @@ struct ScanArgs {
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;
-    const uint8_t* hot8_small;   // PRIV variant's second tier: (hot_small+1)*256
+    const uint8_t* hot8_small;   // PRIV variant's second tier: HotTableBytes(hot_small)
     uint32_t hot_small;
     uint32_t* match_bits;        // may be null
     uint32_t* accept_masks;      // may be null

@@ -169,7 +169,8 @@ int main(int argc, char** argv)
             bitmap64 |= 1ull << (b & 63);
     std::printf("filter mode %d bitmap %08x\n", filter_mode, bitmap);
     const char* rotenv = std::getenv("ROT");
-    const int rot = rotenv ? std::atoi(rotenv) : -1;      // >= 0: lanes 16..31 use a second table copy rotated by `rot` banks
+    const int rot = rotenv ? std::atoi(rotenv) : -1;
+    const int rowrot = std::getenv("ROWROT") ? std::atoi(std::getenv("ROWROT")) : (int) (kHotStride - 256) / 4;      // >= 0: lanes 16..31 use a second table copy rotated by `rot` banks
     uint64_t steps = 0, wf_plain = 0, wf_pred = 0, active_pred = 0, lds_pred = 0;
     uint64_t chunks = 0, replay_lane_chunks = 0, replay_warp_chunks = 0;
     uint64_t hist_plain[8] = {0}, hist_pred[8] = {0};
@@ -190,7 +191,7 @@ int main(int argc, char** argv)
                 for (int l = 0; l < 32; ++l) {
                     uint8_t b = corpus[(base + l) * len + c + k];
                     uint32_t idx = (g[l] << 8) | b;
-                    uint32_t word = idx >> 2, bank = word & 31;
+                    uint32_t word = idx >> 2, bank = (word + g[l] * (uint32_t) rowrot) & 31;    // ROWROT: row stride 256 + 4 * rowrot bytes
                     if (rot >= 0 && l >= 16) {
                         bank = (bank + rot) & 31;
                         word |= 0x40000000u;            // a different copy: never the same word as copy A
@@ -217,7 +218,7 @@ int main(int argc, char** argv)
                         add(words_pred, cnt_pred);
                         ++act;
                     }
-                    g[l] = t.hot8[idx];
+                    g[l] = t.hot8[(size_t) g[l] * kHotStride + b];
                 }
                 int wp = 0, wq = 0;
                 for (int bnk = 0; bnk < 32; ++bnk) {
