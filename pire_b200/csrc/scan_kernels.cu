@@ -142,7 +142,7 @@ struct SharedView {
 };
 
 __host__ __device__ inline size_t HotBytes(uint32_t hot) { return (size_t) ((hot + 1 + 3) / 4 * 4) * kHotStride; }   // == HotTableBytes
-constexpr uint32_t kRowPad = kHotStride - 256;      // bytes a row is pushed beyond (id << 8): nine banks
+
 __host__ __device__ inline size_t PrivBytes(uint32_t priv_rows) { return (size_t) (priv_rows / 4) * 16384; }
 
 __device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot, uint32_t priv_rows = 0)
@@ -162,6 +162,8 @@ __device__ __forceinline__ SharedView CarveShared(uint8_t* smem, uint32_t hot, u
 __device__ __forceinline__ void StageTables(const ScanArgs& a, const SharedView& sv, const uint8_t* hot8, uint32_t hot)
 {
     const uint32_t total = (uint32_t) HotBytes(hot);
+    if ((SmemAddr(sv.hot) & 255u) != 0)
+        __trap();                          // FastStep builds base | byte with one PRMT
     if (threadIdx.x == 0) {
         MbarInit(sv.bar, 1);
         FenceBarrierInit();
@@ -193,6 +195,7 @@ struct Tables {
     uint32_t letters;
     uint32_t wide;
     uint32_t m0;              // 32-slot exit bitmap of hot id 0, slot = byte & 31
+    uint32_t base;            // shared-window address of the hot rows; 256-byte aligned (FastStep relies on it)
 };
 
 // One byte through the complete table (hot rows first: they are in shared memory).
@@ -228,13 +231,15 @@ __device__ __forceinline__ void SetFull(const Tables& t, LaneState& s, uint32_t 
 template <bool kPred>
 __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t w, uint32_t sel)
 {
-    // idx = (g << 8) | byte_k(w); the entry's byte address is idx + g * kRowPad (rows kHotStride apart).
-    uint32_t idx = __byte_perm(w, g, sel);
+    // Entry of (id g, byte b) sits at base + g * kHotStride + b.  `bb` = base | b comes from one PRMT (the
+    // base is 256-byte aligned, so its low byte is free) and does not depend on g: the dependent chain of a
+    // step is IMAD (FMA pipe) -> LDS, as short as the PRMT -> LDS of an unpadded table.
+    const uint32_t bb = __byte_perm(w, t.base, 0x7650u | (sel & 3u));
     if (kPred) {
         // bit (byte & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
         // Lanes resting in id 0 on a self-looping byte skip the load (fewer bank
         // conflicts).  Spelled in PTX so that it stays SHF, LOP3 -> predicate,
-        // @p LDS.  (Sharper filters -- a 64-slot bitmap probed with SHF.R.U64, or a
+        // IMAD, @p LDS.  (Sharper filters -- a 64-slot bitmap probed with SHF.R.U64, or a
         // slot of (byte >> 2) & 31 -- pass fewer lanes (2.12 / 2.14 vs 2.23 modelled
         // wavefronts) but measured 8 % slower: a fourth ALU-pipe instruction per byte,
         // issued at half rate, becomes the bound; DESIGN.md results log.)
@@ -242,19 +247,18 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
             "{\n"
             ".reg .pred p;\n"
             ".reg .b32 probe, addr;\n"
-            "shf.r.wrap.b32 probe, %2, 0, %1;\n"
+            "shf.r.wrap.b32 probe, %2, 0, %1;\n"        // the shift amount is bb & 31 == byte & 31
             "and.b32 probe, probe, 1;\n"
             "or.b32 probe, probe, %0;\n"
             "setp.ne.u32 p, probe, 0;\n"
-            "mov.u32 addr, pire_b200_smem;\n"          // hot rows start the dynamic array (kPred kernels)
-            "add.u32 addr, addr, %1;\n"
-            "mad.lo.u32 addr, %0, %3, addr;\n"         // rows are kHotStride apart: + id * kRowPad (an IMAD, FMA pipe)
+            "mad.lo.u32 addr, %0, %3, %1;\n"
             "@p ld.shared.u8 %0, [addr];\n"
             "}\n"
             : "+r"(g)
-            : "r"(idx), "r"(t.m0), "n"(kRowPad));
+            : "r"(bb), "r"(t.m0), "n"(kHotStride));
     } else {
-        g = t.hot[idx + g * kRowPad];
+        const uint32_t addr = g * kHotStride + bb;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(g) : "r"(addr));
     }
 }
 
@@ -275,6 +279,7 @@ __device__ __noinline__ uint32_t ReplayChunk(const uint8_t* hot, const uint16_t*
 {
     Tables t;
     t.hot = hot;
+    t.base = SmemAddr(hot);
     t.cls = cls;
     t.full = full;
     t.H = H;
@@ -356,6 +361,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 
     Tables t;
     t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot;
@@ -512,6 +518,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 
     Tables t;
     t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot;
@@ -656,6 +663,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
 
     Tables t;
     t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot;
@@ -822,6 +830,7 @@ __global__ void __launch_bounds__(kPrivBlock, 1) ScanUniformPrivKernel(const __g
 
     Tables t;
     t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot_small;          // the second tier seen by this kernel
@@ -1023,6 +1032,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
 
     Tables t;
     t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot;
@@ -1361,6 +1371,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
 
     Tables t;
     t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot;
