@@ -8,13 +8,13 @@
 //
 //  * states are renumbered so that the H <= 255 most frequently visited ("hot")
 //    states get ids 0..H-1; id H is the "miss" marker;
-//  * hot8[(H+1) x 256]: fused byte-indexed rows for hot states, one u8 per
-//    (state, byte): the next hot id, or H when the target is a cold state; rows are
-//    kHotStride = 292 bytes apart (see below).  Row
-//    H maps every byte to H, so a lane that missed keeps running harmlessly to
-//    the end of its 16-byte chunk and is then replayed through the full table.
-//    The address of an entry is ((id << 8) | byte) + 36 * id -- one PRMT builds the
-//    first term from the input word and the state register, one IMAD (FMA pipe) adds the second;
+//  * hot8[(H+1) rows, kHotStride = 292 bytes apart]: fused byte-indexed rows for hot
+//    states, one u8 per (state, byte): the next hot id, or H when the target is a cold
+//    state.  Row H maps every byte to H, so a lane that missed keeps running harmlessly
+//    to the end of its 16-byte chunk and is then replayed through the full table.
+//    The address of an entry is base + 292 * id + byte: one PRMT puts the byte into the
+//    low bits of the (256-byte aligned) base -- independent of the state -- and one IMAD
+//    (FMA pipe) adds the row, so a step's dependent chain is IMAD -> LDS;
 //  * full[states x letters] (u16 when states <= 65536, else u32) + cls[256]:
 //    the complete class-indirect table in the new numbering, L2-resident, used
 //    only for replays, cold states and the unaligned head/tail bytes;
