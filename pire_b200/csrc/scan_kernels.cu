@@ -36,8 +36,9 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
-// One dynamic shared-memory array for every kernel of this file, with an unmangled
-// PTX name so that inline PTX can address it as a link-time constant.
+// One dynamic shared-memory array for every kernel of this file.  The hot rows sit at its start (behind
+// the lane-private region in the PRIV kernel), 256-byte aligned: FastStep ORs the input byte into the
+// table's shared-window address with one PRMT (StageTables traps if the alignment ever fails).
 extern "C" {
 extern __shared__ __align__(128) uint8_t pire_b200_smem[];
 }
