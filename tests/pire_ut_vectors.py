@@ -61,6 +61,10 @@ VECTORS = [
     # SURVEY.md Appendix A answers for the headline regexp (Latin-1, case-sensitive)
     ("AppendixA", rb"hello\s+w.+d$", "",
      [b"hello world", b"hello  w..d", b"xx hello\tworld"], [b"Hello world", b"hello wd", b"hello world!", b""]),
+    # pire_ut.cpp:265-271 (the scanner of the reversed automaton) and :553-579 (the vectors every scanner type
+    # must still answer after Save/Load)
+    ("Reverse@265", b"abcdef", "r", [b"fedcba"], [b"abcdef"]),
+    ("Serialization@553", b"^regexp$", "", [b"regexp"], [b"regxp", b"regexp t"]),
 ]
 
 # Aligned@729: the same strings are also run at unaligned addresses there; the
