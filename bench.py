@@ -61,13 +61,30 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons during the timed region.
+
+    Two sources run side by side from before the warm-up: NVML polled every 4 ms from a thread (the same
+    counters nvidia-smi prints, exact timestamps), and the recipe's `nvidia-smi --query-gpu=... -lms 20`
+    line as a subprocess (its lines reach us through a pipe, so their arrival times are only approximate
+    and a short timed region can end before the first one arrives).  NVML samples are preferred."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.rows, self.proc = [], None
+        self.nvml_rows, self.nvml, self.nvml_max, self._halt = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.nvml_thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -77,31 +94,60 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv = self.nvml
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._halt:
+            try:
+                t = time.perf_counter()
+                sm = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                mask = int(reasons_fn(self._handle))
+                self.nvml_rows.append((t, sm, [name for bit, name in bits if mask & bit]))
+            except Exception:
+                break
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
+    @staticmethod
+    def _window(rows, t0, t1):
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        if inside:
+            return inside
+        near = [r for r in rows if t0 - 0.05 <= r[0] <= t1 + 0.05]     # region shorter than the sampling period
+        return near or rows[-3:]
+
     def stop(self, t0, t1):
+        if self.nvml:
+            self._halt = True
+            self.nvml_thread.join(timeout=1.0)
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        rows = self._window(self.nvml_rows, t0, t1) if self.nvml_rows else []
+        if rows:
+            reasons = sorted({name for _, _, names in rows for name in names})
+            return {"sm_mhz": statistics.median(sm for _, sm, _ in rows), "sm_max_mhz": self.nvml_max, "reasons": reasons,
+                    "samples": len(rows), "source": "nvml, polled every 4 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1]
-        if not rows:          # timed region shorter than the sampling period: nearest samples around it
-            rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for _, r in self.rows[-3:]]
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
+        rows = self._window(self.rows, t0, t1)
+        for _, r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
-                for name, v in zip(names, r[3:7]):
+                for name, v in zip(self.NAMES, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+                "reasons": sorted(reasons), "samples": len(rows), "source": "nvidia-smi -lms 20"}
 
 
 class PortScanner:
