@@ -83,6 +83,16 @@ int main(int argc, char** argv)
         matches += dfa.Final(dfa.Next(s, kEndMark));
     }
     std::vector<uint32_t> order = tuned ? HotOrderFromCounts(dfa, visits) : StaticHotOrder(dfa);
+    if (const char* sh = std::getenv("SHUFFLE")) {
+        // which id a hot row gets decides its bank rotation (9 * id mod 32): shuffle the ids of the hot rows
+        // (id 0 stays: the exit filter is built on it) to see how much the assignment matters
+        uint64_t x = std::strtoull(sh, nullptr, 10) * 0x9E3779B97F4A7C15ull + 1;
+        const size_t hot_n = std::min<size_t>(order.size(), kMaxHot);
+        for (size_t i = hot_n - 1; i > 1; --i) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            std::swap(order[i], order[1 + x % i]);
+        }
+    }
     ScanTables t;
     BuildScanTables(dfa, order, kMaxHot, &t);
 
