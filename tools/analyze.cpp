@@ -83,6 +83,13 @@ int main(int argc, char** argv)
         matches += dfa.Final(dfa.Next(s, kEndMark));
     }
     std::vector<uint32_t> order = tuned ? HotOrderFromCounts(dfa, visits) : StaticHotOrder(dfa);
+    if (std::getenv("SNAKE")) {
+        // rows whose ids differ by a multiple of 32 share a bank rotation: reverse every other block of 32 ranks
+        // so that a rotation class pairs a busy row of one block with a quiet row of the next
+        const size_t hot_n = std::min<size_t>(order.size(), kMaxHot);
+        for (size_t b = 32; b + 32 <= hot_n; b += 64)
+            std::reverse(order.begin() + b, order.begin() + b + 32);
+    }
     if (const char* sh = std::getenv("SHUFFLE")) {
         // which id a hot row gets decides its bank rotation (9 * id mod 32): shuffle the ids of the hot rows
         // (id 0 stays: the exit filter is built on it) to see how much the assignment matters
