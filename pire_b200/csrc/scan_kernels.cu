@@ -10,15 +10,21 @@
 //   * The table of hot rows (dfa_tables.hpp) is staged once per persistent CTA
 //     into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier).
 //   * A lane keeps its state as a hot id g in 0..H (H = "not in the table").
-//     One step is   idx = PRMT(word, g)  ->  g = LDS.U8 [idx] :  the PRMT places
-//     input byte k in bits 0..7 and g in bits 8..15, which is the byte address
-//     of the fused row entry.  No class lookup, no multiply, no branch.
+//     One step is   bb = PRMT(word, base)  (input byte k in the low bits of the table's
+//     256-byte aligned shared address; independent of g, so it runs ahead),
+//     addr = IMAD(g, 292, bb)  (rows are 292 bytes apart: consecutive rows start nine
+//     banks apart, which spreads the conflicts between lanes in different rows),
+//     g = LDS.U8 [addr].  No class lookup, no branch.
 //   * kPred variant: the LDS is predicated off while the lane sits in hot id 0
 //     and the byte cannot leave it (32-slot bitmap probed with a funnel shift),
 //     so fewer lanes hit the banks and the load costs fewer wavefronts.
-//   * Input bytes: each lane streams its own string with 32-byte (uniform
-//     kernel, LDG.256) or 16-byte (generic kernel) read-only vector loads that
-//     bypass L1 allocation, software-prefetched one iteration ahead.
+//   * Input bytes: each lane streams its own string: 32-byte read-only loads that
+//     bypass L1 allocation, one ahead in a register ping-pong (uniform kernel,
+//     LDG.256), or a four-deep cp.async ring of 16-byte chunks in shared memory
+//     (CSR kernels).  Lines of text have their own kernel: lanes pull lines one by one.
+//   * Prefix / suffix scans and HalfFinalScanner counting reuse the walk; final hot
+//     states carry the highest ids, so a running maximum per chunk says whether any
+//     step needs the per-byte work.
 //   * A lane whose walk leaves the hot rows reads H from then on (row H is a
 //     sink); after the chunk the lane is replayed byte by byte through the
 //     complete class-indirect table in global memory / L2.
