@@ -173,3 +173,65 @@ def test_oracle_suffix_scans_vs_reference_live(ref):
                     assert (want == sc.suffix(corpus, offs, shortest=shortest, through_end=te, through_begin=tb, variant=0)).all()
                     got = oracle_suffix(orc, corpus, offs, shortest=shortest, through_end=te, through_begin=tb)
                     assert (got == want).all(), (pat, opts, te, tb, shortest)
+
+
+def test_oracle_fuzz_vs_reference_live(ref):
+    """Differential fuzz on the CPU: random patterns (alternation, classes, repetition, anchors, UTF-8,
+    case-insensitive, reversed), singly and glued in threes -- run, prefix / suffix scans and (as
+    HalfFinalScanner) counting of the oracle port against the real reference."""
+    from refpire import oracle_count, oracle_prefix, oracle_suffix
+    from test_gpu_parity import _random_pattern
+    rng = np.random.default_rng(777)
+    alphabet = np.frombuffer(b"abcxABX 019\t." + "аб".encode(), np.uint8)
+    strings = [bytes(rng.choice(alphabet, size=int(n))) for n in rng.integers(0, 100, size=400)]
+    corpus, offs = csr(strings)
+    compiled = []
+    while len(compiled) < 40:
+        pat = _random_pattern(rng)
+        if rng.random() < 0.2:
+            pat = b"^" + pat
+        if rng.random() < 0.2:
+            pat = pat + b"$"
+        opts = "".join(o for o in "iunr" if rng.random() < 0.25)
+        try:
+            compiled.append((pat, opts, ref.compile(pat, opts)))
+        except ValueError:
+            continue
+    for k in range(0, 12, 3):
+        try:
+            g = ref.glue(ref.glue(compiled[k][2], compiled[k + 1][2]), compiled[k + 2][2])
+        except ValueError:
+            continue
+        if not g.empty:
+            compiled.append((b"glue", "", g))
+    for pat, opts, sc in compiled:
+        orc = Oracle(sc.save())
+        for begin, end in ((True, True), (False, False)):
+            f_ref, m_ref, s_ref = sc.run(corpus, offs, begin=begin, end=end, variant=0)
+            for shortcuts in (False, True):
+                f, m, s = orc.run(corpus, offs, begin=begin, end=end, shortcuts=shortcuts)
+                assert (f == f_ref).all() and (m == m_ref).all() and (s == s_ref).all(), (pat, opts, begin, end, shortcuts)
+        for shortest in (False, True):
+            for m1, m2 in ((False, False), (True, True)):
+                want = sc.prefix(corpus, offs, shortest=shortest, through_begin=m1, through_end=m2, variant=2)
+                assert (oracle_prefix(orc, corpus, offs, shortest=shortest, through_begin=m1, through_end=m2) == want).all(), (pat, opts)
+                want = sc.suffix(corpus, offs, shortest=shortest, through_end=m1, through_begin=m2, variant=2)
+                assert (oracle_suffix(orc, corpus, offs, shortest=shortest, through_end=m1, through_begin=m2) == want).all(), (pat, opts)
+    # the same patterns as HalfFinalScanners (mode 0) and as greedy / non-greedy counters
+    checked = 0
+    for pat, opts, _ in compiled[:24]:
+        if pat == b"glue":
+            continue
+        for mode in (0, 1, 4):
+            try:
+                hf = ref.compile_half_final(pat, opts.replace("r", ""), mode)
+            except ValueError:
+                continue
+            if hf.empty or hf.size > 4000:
+                continue
+            orc = Oracle(hf.save())
+            want, wfin = hf.count(corpus, offs)
+            got, gfin = oracle_count(orc, corpus, offs)
+            assert (got == want).all() and (gfin == wfin).all(), (pat, opts, mode)
+            checked += 1
+    assert checked >= 30
