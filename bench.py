@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
     ap.add_argument("--workload", default="glue10", choices=["glue10", "headline", "utf8mixed"])
     ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: 10 GB worth)")
-    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look"])
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -382,7 +382,7 @@ def main():
         return e0.elapsed_time(e1) / reps
 
     # kernel variant: measured on this batch by the library, not guessed
-    names = {N.VARIANT_PLAIN: "plain", N.VARIANT_PRED: "pred", N.VARIANT_PRIV: "priv"}
+    names = dict(N.VARIANT_NAMES)
     variant_ms = {}
     if args.variant == "auto":
         variant_ms = sc.AutoSelect(batch)

@@ -55,7 +55,11 @@ enum {
     PIRE_GPU_VARIANT_AUTO = 0,
     PIRE_GPU_VARIANT_PLAIN = 1,    /* one shared-memory load per byte, unconditional */
     PIRE_GPU_VARIANT_PRED = 2,     /* load predicated off while the resident state self-loops */
-    PIRE_GPU_VARIANT_PRIV = 3      /* hottest rows replicated per bank: conflict-free loads (fixed-length ASCII-heavy batches) */
+    PIRE_GPU_VARIANT_PRIV = 3,     /* hottest rows replicated per bank: conflict-free loads (fixed-length ASCII-heavy batches) */
+    PIRE_GPU_VARIANT_LOOK = 4,     /* PRED with one byte of look-ahead: a resting lane reads the table only when this byte and
+                                      the next can both matter (the device analogue of the ExitMasks skip loop,
+                                      multi.h:966-989); fixed-length batches, PRED otherwise */
+    PIRE_GPU_VARIANT_SLOTS = 8     /* length of per-variant arrays indexed by variant id */
 };
 
 typedef struct pire_gpu_info {
@@ -218,7 +222,7 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc,
 
 /* Times every kernel variant that can serve this batch shape (two launches each,
  * results discarded) and makes the fastest one the handle's AUTO choice for that
- * shape (fixed-length/aligned vs generic).  ms_out[4] (may be NULL) receives the
+ * shape (fixed-length/aligned vs generic).  ms_out[PIRE_GPU_VARIANT_SLOTS] (may be NULL) receives the
  * milliseconds per variant id, 0 for variants that do not apply.  Which variant
  * wins depends on the automaton and the text, so it is
  * measured rather than guessed.  Synchronises the device. */

@@ -7,6 +7,6 @@ Only what the path needs lives here:
     workloads.py  the BASELINE.json pattern sets and synthetic corpora
     dist.py       shard-by-string + the one bitmap all-reduce
 """
-from ._native import PireGpuError, RUN_BEGIN, RUN_END, VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV  # noqa: F401
+from ._native import PireGpuError, RUN_BEGIN, RUN_END, VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV, VARIANT_LOOK  # noqa: F401
 from .scanner import (Batch, BeginMark, EndMark, HalfFinalCount, HalfFinalResult, LongestPrefix, LongestSuffix, Matches, RunHelper, Runner, Scanner,  # noqa: F401
                       ShortestPrefix, ShortestSuffix)

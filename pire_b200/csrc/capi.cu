@@ -95,7 +95,7 @@ struct pire_gpu_scanner {
     uint32_t count_mode = 0;
     double final_share = 0.0;       // share of a tune sample's steps that ended in a final state
     std::vector<uint32_t> hot_order;
-    LaunchPlan plan[4][2];          // [variant][uniform]
+    LaunchPlan plan[kVariantSlots][2];          // [variant][uniform]
 
     // workspace of the host-buffer entry point
     std::mutex host_mutex;
@@ -114,8 +114,11 @@ namespace {
 
 uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform = true)
 {
-    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_PRIV)
+    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_LOOK) {
+        if (sc->variant == PIRE_GPU_VARIANT_LOOK && !sc->tab.look_ok)
+            return PIRE_GPU_VARIANT_PRED;       // an exit of the resting state is cold: no look-ahead set
         return sc->variant;
+    }
     if (sc->auto_choice[uniform ? 1 : 0])
         return sc->auto_choice[uniform ? 1 : 0];
     // AUTO: predication pays when lanes outside the resident state would
@@ -167,7 +170,7 @@ int Upload(pire_gpu_scanner* sc)
     if (!t.weights.empty())
         CUDA_TRY(cudaMemcpy(d.weights, t.weights.data(), t.weights.size() * 8, cudaMemcpyHostToDevice));
     sc->priv_ok = false;
-    for (int v = kVariantPlain; v <= kVariantPriv; ++v)
+    for (int v = kVariantPlain; v <= kVariantLook; ++v)
         for (int u = 0; u < 2; ++u) {
             cudaError_t pe = PlanScan(sc->device, t.hot, t.hot_small, t.priv_rows, v, u != 0, &sc->plan[v][u]);
             if (v == kVariantPriv && u == 1) {
@@ -213,6 +216,7 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->start = t.start[(flags & PIRE_GPU_RUN_BEGIN) ? 1 : 0];
     a->trim = (offsets && (flags & PIRE_GPU_RUN_LINES)) ? 1 : 0;
     a->exit_bitmap0 = t.exit_bitmap0;
+    a->look_bitmap = t.look_bitmap;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
     a->hot8_small = sc->dev.hot8_small;
@@ -311,7 +315,7 @@ int pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out)
 
 int pire_gpu_scanner_set_variant(pire_gpu_scanner* sc, uint32_t variant)
 {
-    if (!sc || variant > PIRE_GPU_VARIANT_PRIV)
+    if (!sc || variant > PIRE_GPU_VARIANT_LOOK)
         return Fail(PIRE_GPU_EINVAL, "bad variant");
     sc->variant = variant;
     return PIRE_GPU_OK;
@@ -674,7 +678,7 @@ int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     if (rc != PIRE_GPU_OK)
         return rc;
     if (ms_out)
-        for (int v = 0; v < 4; ++v)
+        for (int v = 0; v < PIRE_GPU_VARIANT_SLOTS; ++v)
             ms_out[v] = 0.f;
     if (n == 0)
         return PIRE_GPU_OK;
@@ -691,8 +695,10 @@ int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     const uint32_t saved = sc->variant;
     uint32_t best = 0;
     float best_ms = 0.f;
-    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_PRIV && ce == cudaSuccess; ++v) {
+    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_LOOK && ce == cudaSuccess; ++v) {
         if (v == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
+            continue;
+        if (v == PIRE_GPU_VARIANT_LOOK && !(uniform && sc->tab.look_ok))
             continue;
         sc->variant = v;
         float ms = 0.f;

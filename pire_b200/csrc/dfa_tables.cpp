@@ -127,6 +127,34 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
         if (t.hot8[b] != 0)
             t.exit_bitmap0 |= 1u << (b & 31);
 
+    // Look-ahead filter of the LOOK variant.  F1 = bytes that leave id 0; F = F1 plus every byte on which a state
+    // entered from id 0 goes anywhere but back to id 0.  If byte k+1 is outside F, then whatever byte k did to a lane
+    // resting in id 0, the lane is back in id 0 after byte k+1: both table reads can be skipped.
+    t.look_ok = true;
+    {
+        bool in_f[256];
+        for (uint32_t b = 0; b < 256; ++b)
+            in_f[b] = t.hot8[b] != 0;
+        for (uint32_t b = 0; b < 256; ++b) {
+            const uint32_t g1 = t.hot8[b];
+            if (g1 == 0)
+                continue;
+            if (g1 >= H) {
+                t.look_ok = false;
+                break;
+            }
+            for (uint32_t c = 0; c < 256; ++c)
+                if (t.hot8[(size_t) g1 * kHotStride + c] != 0)
+                    in_f[c] = true;
+        }
+        t.look_bitmap = 0;
+        for (uint32_t b = 0; b < 256; ++b)
+            if (in_f[b])
+                t.look_bitmap |= 1u << (b & 31);
+        if (!t.look_ok)
+            t.look_bitmap = ~0u;
+    }
+
     // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,
     // the last id being the sink.
     {

@@ -63,6 +63,12 @@ struct ScanTables {
     std::vector<uint8_t> flags_new;          // [new id]: bit0 Final, bit1 Dead (prefix scans test them per byte)
     uint32_t end_class = 0;                  // letter class of EndMark (prefix scans step it explicitly)
     uint32_t exit_bitmap0 = ~0u;             // bit (b & 31) set if byte b may leave hot id 0 (kPred filter)
+    // LOOK variant (two-byte look-ahead of the exit filter): bit (b & 31) set if byte b leaves hot id 0, or keeps a
+    // state entered from hot id 0 from falling back to it.  A lane resting in id 0 reads the table only when this
+    // byte AND the next one pass the filter; look_ok = 0 when an exit of id 0 leads to a cold state (the set is
+    // then unknown and the variant is not offered).
+    uint32_t look_bitmap = ~0u;
+    bool look_ok = false;
     // Counting (HalfFinalScanner, half_final.h:154-163): hot ids >= first_final_hot are final states
     // (== hot when none is); accept lists in the new numbering as CSR, ids repeated as the image has them.
     uint32_t first_final_hot = 0;

@@ -419,6 +419,160 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
     }
 }
 
+// ---------------------------------------------------------------- LOOK variant
+//
+// The reference leaves the table walk while a state cannot be left by the bytes ahead (ExitMasks skip loop,
+// multi.h:966-989).  The device analogue looks ONE byte further than the round-1 exit filter: a lane resting in
+// hot id 0 reads the table only if this byte AND the next one pass the filter F (dfa_tables.hpp: F holds the
+// bytes that leave id 0 and the bytes that keep a state entered from id 0 from falling straight back).  If the
+// next byte is outside F the lane is back in id 0 after it whatever this byte does, so both reads are skipped
+// and the lane never enters the one-step states at all: on random text the lanes outside id 0 drop from 7.4 to
+// 5.1 per warp and the active lanes per load from 19 to 12 (host model tools/model_look.cpp: 2.05 -> 1.72
+// shared-memory wavefronts per step with the same 32-slot filter; an exact filter would give 1.26).
+// A lane that skipped an exit byte is "virtually" in id 0; its true state differs only until the next byte,
+// which is outside F and returns it to id 0 on either path, so replays from the register state stay exact.
+// The last byte of a string has no successor: it is filtered by F alone.
+//
+// One step is six instructions, two of them on the dependent chain:
+//     bb  = IDP.4A(word, 1 << 8k, base)     byte k + table base, FMA pipe (PRMT in round 1, ALU pipe)
+//     pa  = SHF.R.W(F, bb)                  bit (byte & 31) of the filter in bit 0
+//     t   = LOP3(pa, pa_next, 1)            both bytes pass
+//     p   = LOP3((t | g) != 0)              ... or the lane is outside id 0            [chain]
+//     a   = IMAD(g, 292, bb)                                                          [chain]
+//     g   = @p LDS.U8 [a]
+__device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, uint32_t filter, uint32_t& bb, uint32_t& pa)
+{
+    bb = __dp4a(w, 0x00000001u, base);
+    pa = __funnelshift_r(filter, filter, bb);
+}
+
+__device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, uint32_t pa_next)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, addr;\n"
+        "lop3.b32 t, %1, %2, 1, 0x80;\n"
+        "or.b32 t, t, %0;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "mad.lo.u32 addr, %0, %4, %3;\n"
+        "@p ld.shared.u8 %0, [addr];\n"
+        "}\n"
+        : "+r"(g)
+        : "r"(pa), "r"(pa_next), "r"(bb), "n"(kHotStride));
+}
+
+// Four bytes.  (bb0, pa0) belong to byte 0 of `w` and were computed by the previous call; pan is the probe of the
+// byte that follows the word.
+__device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, uint32_t pa0, uint32_t pan, uint32_t base,
+                                         uint32_t filter)
+{
+    const uint32_t bb1 = __dp4a(w, 0x00000100u, base);
+    const uint32_t bb2 = __dp4a(w, 0x00010000u, base);
+    const uint32_t bb3 = __dp4a(w, 0x01000000u, base);
+    const uint32_t pa1 = __funnelshift_r(filter, filter, bb1);
+    const uint32_t pa2 = __funnelshift_r(filter, filter, bb2);
+    const uint32_t pa3 = __funnelshift_r(filter, filter, bb3);
+    LookStep(g, bb0, pa0, pa1);
+    LookStep(g, bb1, pa1, pa2);
+    LookStep(g, bb2, pa2, pa3);
+    LookStep(g, bb3, pa3, pan);
+}
+
+// Sixteen bytes; (bb0, pa0) enter as the probe of v's first byte and leave as (bbn, pan), the probe of the byte
+// after the chunk (pan = all ones at the end of the string).
+__device__ __forceinline__ void LookChunk16(const Tables& t, LaneState& s, uint4 v, uint32_t& bb0, uint32_t& pa0, uint32_t bbn,
+                                            uint32_t pan, uint32_t filter)
+{
+    const uint32_t before = s.g;
+    uint32_t g = s.g;
+    uint32_t b1, p1, b2, p2, b3, p3;
+    LookProbe(v.y, t.base, filter, b1, p1);
+    LookWord(g, v.x, bb0, pa0, p1, t.base, filter);
+    LookProbe(v.z, t.base, filter, b2, p2);
+    LookWord(g, v.y, b1, p1, p2, t.base, filter);
+    LookProbe(v.w, t.base, filter, b3, p3);
+    LookWord(g, v.z, b2, p2, p3, t.base, filter);
+    LookWord(g, v.w, b3, p3, pan, t.base, filter);
+    bb0 = bbn;
+    pa0 = pan;
+    s.g = g;
+    if (g == t.H) {
+        uint32_t from = before == t.H ? s.cold : before;
+        uint32_t full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, v);
+        SetFull(t, s, full);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.look_bitmap;
+    const uint32_t filter = a.look_bitmap;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    const uint32_t len = (uint32_t) a.fixed_len;
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
+
+        LaneState s;
+        SetFull(t, s, a.start);
+
+        if (len != 0) {
+            uint4 a0, a1, b0, b1;
+            uint32_t bb0, pa0, bbm, pam, bbn, pan;
+            LoadStream32(p, a0, a1);
+            LookProbe(a0.x, t.base, filter, bb0, pa0);
+            for (uint32_t off = 0;;) {
+                off += 32;
+                const bool more_b = off < len;
+                if (more_b)
+                    LoadStream32(p + off, b0, b1);
+                LookProbe(a1.x, t.base, filter, bbm, pam);
+                LookChunk16(t, s, a0, bb0, pa0, bbm, pam, filter);
+                bbn = 0;
+                pan = 0xffffffffu;
+                if (more_b)
+                    LookProbe(b0.x, t.base, filter, bbn, pan);
+                LookChunk16(t, s, a1, bb0, pa0, bbn, pan, filter);
+                if (!more_b)
+                    break;
+                off += 32;
+                const bool more_a = off < len;
+                if (more_a)
+                    LoadStream32(p + off, a0, a1);
+                LookProbe(b1.x, t.base, filter, bbm, pam);
+                LookChunk16(t, s, b0, bb0, pa0, bbm, pam, filter);
+                bbn = 0;
+                pan = 0xffffffffu;
+                if (more_a)
+                    LookProbe(a0.x, t.base, filter, bbn, pan);
+                LookChunk16(t, s, b1, bb0, pa0, bbn, pan, filter);
+                // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
+                if (!more_a || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
+                    break;
+            }
+        }
+        Report(a, t, s, unit, i, valid);
+    }
+}
+
 // Edge chunk of a string (its first or last, partially owned 16 bytes): loaded once, then
 // handed out byte by byte from registers.
 __device__ __forceinline__ uint4 LoadEdge16(const uint8_t* aligned)
@@ -1596,7 +1750,9 @@ const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
-    const bool pred = variant == kVariantPred;
+    if (variant == kVariantLook && uniform)
+        return reinterpret_cast<const void*>(&ScanUniformLookKernel);
+    const bool pred = variant == kVariantPred || variant == kVariantLook;      // CSR batches: LOOK falls back to the exit filter
     if (uniform)
         return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
     return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
@@ -1616,7 +1772,7 @@ cudaError_t PrepareScanKernels(int device)
     err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err != cudaSuccess)
         return err;
-    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv})
+    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook})
         for (bool uniform : {false, true}) {
             err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (err != cudaSuccess)

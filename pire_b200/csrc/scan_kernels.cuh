@@ -34,6 +34,7 @@ struct ScanArgs {
     uint32_t wide;               // full is u32
     uint32_t start;              // state after Initialize()[+Begin()], new numbering
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
+    uint32_t look_bitmap;        // LOOK variant: 32-slot look-ahead filter (dfa_tables.hpp), slot = byte & 31
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;
     const uint8_t* hot8_small;   // PRIV variant's second tier: HotTableBytes(hot_small)
@@ -68,7 +69,8 @@ struct LaunchPlan {
     size_t shared = 0;
 };
 
-enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3 };
+enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3, kVariantLook = 4 };
+constexpr int kVariantSlots = 8;      // size of per-variant arrays (variant ids are 1-based)
 
 size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows);
 cudaError_t PrepareScanKernels(int device);                       // raises the dynamic smem limit

@@ -196,12 +196,12 @@ class Scanner:
         flags = (N.RUN_BEGIN if begin else 0) | (N.RUN_END if end else 0) | (N.RUN_LINES if batch.trim else 0)
         torch = _torch()
         stream = torch.cuda.current_stream(batch.device).cuda_stream
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * N.VARIANT_SLOTS)()
         N.check(N.lib.pire_gpu_scanner_autoselect(self._h, batch.corpus.data_ptr(),
                                                   batch.offsets.data_ptr() if batch.offsets is not None else None,
                                                   batch.fixed_len, batch.n, flags, stream, ms),
                 "pire_gpu_scanner_autoselect")
-        return {name: float(ms[v]) for name, v in (("plain", 1), ("pred", 2), ("priv", 3)) if ms[v] > 0}
+        return {name: float(ms[v]) for v, name in N.VARIANT_NAMES.items() if ms[v] > 0}
 
     def run_batch(self, batch, flags, match_bits=None, accept_masks=None, state_idx=None, stream=None):
         """Thin wrapper of pire_gpu_run_batch: asynchronous on the current stream."""

@@ -34,7 +34,7 @@ def checker_run(image, strings, begin, end, ref_sc=None):
     return Oracle(image).run(corpus, offs, begin=begin, end=end)
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["plain", "pred"])
+@pytest.mark.parametrize("variant", [1, 2, 4], ids=["plain", "pred", "look"])
 @pytest.mark.parametrize("case", GOLDEN, ids=lambda c: c.name)
 def test_golden_vectors(case, variant, cuda_device):
     import pire_b200 as P
@@ -112,7 +112,7 @@ def random_text(rng, n, length, alphabet=None):
     return rng.choice(np.frombuffer(alphabet, np.uint8), size=(n, length))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3], ids=["plain", "pred", "priv"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["plain", "pred", "priv", "look"])
 def test_uniform_kernel_headline(variant, cuda_device, ref):
     """Fixed 1 KiB strings (the BASELINE configs' shape) through the uniform kernel,
     full comparison with the reference on 64 Ki strings, incl. StateIndex."""
@@ -163,7 +163,7 @@ def test_glued_ten_patterns(max_hot, tune, cuda_device, ref):
     host = spec.host_sample(0, n)
     f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=n, variant=1, threads=8)
     assert int((m_ref != 0).sum()) >= n // 8
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         sc.set_variant(variant)
         r = P.Runner(sc).Begin().Run(batch).End()
         assert (r.Matches().astype(np.uint8) == f_ref).all(), variant
@@ -197,7 +197,7 @@ def test_generic_kernel_mixed_lengths_utf8(cuda_device, ref):
     assert int(want[0].sum()) >= len(strings) // 5
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3], ids=["plain", "pred", "priv"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["plain", "pred", "priv", "look"])
 def test_uniform_kernel_binary_bytes(variant, cuda_device, ref):
     """Fixed-length strings over the whole byte range (UTF-8 pattern): the private-row
     kernel covers bytes < 128 only and must re-walk every word holding a byte >= 128."""
@@ -222,6 +222,52 @@ def test_uniform_kernel_binary_bytes(variant, cuda_device, ref):
     assert (r.Matches().astype(np.uint8) == f_ref).all()
     assert (r.States() == s_ref).all()
     assert int(f_ref.sum()) >= n // 3
+
+
+@pytest.mark.parametrize("length", [32, 64, 96, 480, 1024])
+def test_look_variant_dense_near_misses(length, cuda_device, ref):
+    """LOOK variant (one byte of look-ahead over the exit filter): text made almost only of the bytes that start
+    or continue the ten patterns, so that nearly every position is an exit byte followed by a continuing or a
+    non-continuing byte, strings that end on exit bytes and on half matches, every mark combination, static and
+    tuned hot rows.  Everything must equal the reference (and the plain kernel)."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    sc_ref = ref.glue_all(W.GLUE10)
+    sc = P.Scanner(W.load_image("glue10"), cuda_device)
+    rng = np.random.default_rng(length)
+    n = 4096 + 5
+    dense = b"(0123456789ABCXYZaefhilmorstuw)-: /GET"
+    sparse = bytes(range(0x20, 0x7F))
+    host = np.empty((n, length), np.uint8)
+    for i in range(n):
+        mix = rng.random()
+        alphabet = dense if mix < 0.6 else dense + sparse
+        row = rng.choice(np.frombuffer(alphabet, np.uint8), size=length)
+        if i % 7 == 0:
+            lit = W.GLUE10_PLANTS[(i // 7) % 10].lstrip(b"^$")
+            cut = int(rng.integers(1, len(lit) + 1))                  # whole literals and proper prefixes of them
+            at = int(rng.integers(0, max(1, length - cut))) if i % 14 else length - cut
+            row[at:at + cut] = np.frombuffer(lit[:cut], np.uint8)[:length - at]
+        host[i] = row
+    host = np.ascontiguousarray(host).reshape(-1)
+    dev = torch.from_numpy(host).to("cuda:0")
+    batch = P.Batch(dev, fixed_len=length, n=n)
+    for tuned in (False, True):
+        if tuned:
+            sc.Tune(batch, 2048)
+        for begin in (True, False):
+            for end in (True, False):
+                f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=length, n=n, begin=begin, end=end, variant=1, threads=8)
+                for variant in (1, 4):
+                    sc.set_variant(variant)
+                    r = P.Runner(sc)
+                    r = r.Begin() if begin else r
+                    r = r.Run(batch)
+                    r = r.End() if end else r
+                    assert (r.Matches().astype(np.uint8) == f_ref).all(), (variant, tuned, begin, end)
+                    assert (r.AcceptMasks() == m_ref).all(), (variant, tuned, begin, end)
+                    assert (r.States() == s_ref).all(), (variant, tuned, begin, end)
 
 
 def test_noexit_early_stop_is_exact(cuda_device, ref):
@@ -345,7 +391,7 @@ def test_autoselect_keeps_results(cuda_device, ref):
     sc.Tune(batch, 4096)
     ms = sc.AutoSelect(batch)
     assert set(ms) >= {"plain", "pred"} and all(v > 0 for v in ms.values())
-    assert sc.info().variant in (1, 2, 3)
+    assert sc.info().variant in (1, 2, 3, 4)
     r = P.Runner(sc).Begin().Run(batch).End()
     f_ref, m_ref, _ = sc_ref.run(spec.host_sample(0, n), fixed_len=1024, n=n, variant=1, threads=8)
     assert (r.Matches().astype(np.uint8) == f_ref).all() and (r.AcceptMasks() == m_ref).all()
@@ -456,7 +502,7 @@ def test_fuzz_random_patterns(cuda_device, ref):
         sc.Tune(batch, 512)
         want = sc_ref.run(corpus, offs, variant=0)
         want_fixed = sc_ref.run(fixed, fixed_len=64, n=2048, variant=0)
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4):
             sc.set_variant(variant)
             r = P.Runner(sc).Begin().Run(batch).End()
             ok = (r.Matches().astype(np.uint8) == want[0]).all() and (r.AcceptMasks() == want[1]).all()
