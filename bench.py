@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
     ap.add_argument("--workload", default="glue10", choices=["glue10", "headline", "utf8mixed"])
     ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: 10 GB worth)")
-    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look", "look64"])
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

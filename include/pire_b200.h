@@ -59,6 +59,7 @@ enum {
     PIRE_GPU_VARIANT_LOOK = 4,     /* PRED with one byte of look-ahead: a resting lane reads the table only when this byte and
                                       the next can both matter (the device analogue of the ExitMasks skip loop,
                                       multi.h:966-989); fixed-length batches, PRED otherwise */
+    PIRE_GPU_VARIANT_LOOK64 = 5,   /* LOOK with a 64-slot filter (one more FMA-pipe instruction per byte, fewer false passes) */
     PIRE_GPU_VARIANT_SLOTS = 8     /* length of per-variant arrays indexed by variant id */
 };
 

@@ -11,6 +11,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <string>
@@ -114,8 +115,8 @@ namespace {
 
 uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform = true)
 {
-    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_LOOK) {
-        if (sc->variant == PIRE_GPU_VARIANT_LOOK && !sc->tab.look_ok)
+    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_LOOK64) {
+        if (sc->variant >= PIRE_GPU_VARIANT_LOOK && !sc->tab.look_ok)
             return PIRE_GPU_VARIANT_PRED;       // an exit of the resting state is cold: no look-ahead set
         return sc->variant;
     }
@@ -170,7 +171,7 @@ int Upload(pire_gpu_scanner* sc)
     if (!t.weights.empty())
         CUDA_TRY(cudaMemcpy(d.weights, t.weights.data(), t.weights.size() * 8, cudaMemcpyHostToDevice));
     sc->priv_ok = false;
-    for (int v = kVariantPlain; v <= kVariantLook; ++v)
+    for (int v = kVariantPlain; v <= kVariantLook64; ++v)
         for (int u = 0; u < 2; ++u) {
             cudaError_t pe = PlanScan(sc->device, t.hot, t.hot_small, t.priv_rows, v, u != 0, &sc->plan[v][u]);
             if (v == kVariantPriv && u == 1) {
@@ -217,6 +218,7 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->trim = (offsets && (flags & PIRE_GPU_RUN_LINES)) ? 1 : 0;
     a->exit_bitmap0 = t.exit_bitmap0;
     a->look_bitmap = t.look_bitmap;
+    a->look_bitmap64 = t.look_bitmap64;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
     a->hot8_small = sc->dev.hot8_small;
@@ -244,7 +246,12 @@ int pire_gpu_scanner_create(const void* image, size_t size, int device, pire_gpu
     pire_gpu_scanner* sc = new (std::nothrow) pire_gpu_scanner;
     if (!sc)
         return Fail(PIRE_GPU_EINVAL, "out of memory");
-    std::string err = ParsePireImage(image, size, &sc->dfa);
+    std::string err;
+    try {
+        err = ParsePireImage(image, size, &sc->dfa);
+    } catch (const std::exception& e) {                 // bad_alloc / length_error on a huge (or lying) image
+        err = std::string("scanner image: ") + e.what();
+    }
     if (!err.empty()) {
         delete sc;
         return Fail(PIRE_GPU_EIMAGE, err);
@@ -265,8 +272,13 @@ int pire_gpu_scanner_create(const void* image, size_t size, int device, pire_gpu
         }
         sc->device = device;
     }
-    sc->hot_order = StaticHotOrder(sc->dfa);
-    Rebuild(sc);
+    try {
+        sc->hot_order = StaticHotOrder(sc->dfa);
+        Rebuild(sc);
+    } catch (const std::exception& e) {
+        delete sc;
+        return Fail(PIRE_GPU_EIMAGE, std::string("building the scan tables: ") + e.what());
+    }
     int rc = Upload(sc);
     if (rc != PIRE_GPU_OK) {
         pire_gpu_scanner_destroy(sc);
@@ -315,7 +327,7 @@ int pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out)
 
 int pire_gpu_scanner_set_variant(pire_gpu_scanner* sc, uint32_t variant)
 {
-    if (!sc || variant > PIRE_GPU_VARIANT_LOOK)
+    if (!sc || variant > PIRE_GPU_VARIANT_LOOK64)
         return Fail(PIRE_GPU_EINVAL, "bad variant");
     sc->variant = variant;
     return PIRE_GPU_OK;
@@ -326,7 +338,11 @@ int pire_gpu_scanner_set_max_hot(pire_gpu_scanner* sc, uint32_t max_hot_rows)
     if (!sc || max_hot_rows == 0)
         return Fail(PIRE_GPU_EINVAL, "bad max_hot_rows");
     sc->max_hot = max_hot_rows < kMaxHot ? max_hot_rows : kMaxHot;
-    Rebuild(sc);
+    try {
+        Rebuild(sc);
+    } catch (const std::exception& e) {
+        return Fail(PIRE_GPU_EINVAL, std::string("building the scan tables: ") + e.what());
+    }
     return Upload(sc);
 }
 
@@ -658,7 +674,11 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc, const uint8_t* d_corpus, const u
     std::vector<uint64_t> by_old(sc->dfa.states, 0);
     for (uint32_t ns = 0; ns < sc->tab.states; ++ns)
         by_old[sc->tab.old_of_new[ns]] = by_new[ns];
-    sc->hot_order = HotOrderFromCounts(sc->dfa, by_old);
+    try {
+        sc->hot_order = HotOrderFromCounts(sc->dfa, by_old);
+    } catch (const std::exception& e) {
+        return Fail(PIRE_GPU_EINVAL, std::string("pire_gpu_scanner_tune: ") + e.what());
+    }
     uint64_t steps = 0, in_final = 0;
     for (uint32_t s = 0; s < sc->dfa.states; ++s) {
         steps += by_old[s];
@@ -667,7 +687,11 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc, const uint8_t* d_corpus, const u
     }
     sc->final_share = steps ? (double) in_final / (double) steps : 0.0;
     sc->tuned = true;
-    Rebuild(sc);
+    try {
+        Rebuild(sc);
+    } catch (const std::exception& e) {
+        return Fail(PIRE_GPU_EINVAL, std::string("pire_gpu_scanner_tune: ") + e.what());
+    }
     return Upload(sc);
 }
 
@@ -695,10 +719,10 @@ int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     const uint32_t saved = sc->variant;
     uint32_t best = 0;
     float best_ms = 0.f;
-    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_LOOK && ce == cudaSuccess; ++v) {
+    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_LOOK64 && ce == cudaSuccess; ++v) {
         if (v == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
             continue;
-        if (v == PIRE_GPU_VARIANT_LOOK && !(uniform && sc->tab.look_ok))
+        if (v >= PIRE_GPU_VARIANT_LOOK && !(uniform && sc->tab.look_ok))
             continue;
         sc->variant = v;
         float ms = 0.f;

@@ -148,11 +148,16 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
                     in_f[c] = true;
         }
         t.look_bitmap = 0;
+        t.look_bitmap64 = 0;
         for (uint32_t b = 0; b < 256; ++b)
-            if (in_f[b])
+            if (in_f[b]) {
                 t.look_bitmap |= 1u << (b & 31);
-        if (!t.look_ok)
+                t.look_bitmap64 |= 1ull << (b & 63);
+            }
+        if (!t.look_ok) {
             t.look_bitmap = ~0u;
+            t.look_bitmap64 = ~0ull;
+        }
     }
 
     // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,

@@ -68,6 +68,7 @@ struct ScanTables {
     // byte AND the next one pass the filter; look_ok = 0 when an exit of id 0 leads to a cold state (the set is
     // then unknown and the variant is not offered).
     uint32_t look_bitmap = ~0u;
+    uint64_t look_bitmap64 = ~0ull;          // the same set with 64 slots (slot = b & 63): LOOK64 variant
     bool look_ok = false;
     // Counting (HalfFinalScanner, half_final.h:154-163): hot ids >= first_final_hot are final states
     // (== hot when none is); accept lists in the new numbering as CSR, ids repeated as the image has them.

@@ -82,11 +82,18 @@ std::string ParsePireImage(const void* data, size_t size, Dfa* out)
 
     if (m.states == 0 || m.letters == 0)
         return "scanner image has no states or letters";
+    // A scanner has at most MaxChar letter classes (defs.h:71) and Glue caps the states (multi.h:1100); an
+    // image that claims more is corrupt.  The bounds also keep the size arithmetic below inside 64 bits, so a
+    // crafted header cannot wrap BufSize() around the EOF check.
+    if (m.letters > kMaxChar)
+        return "scanner image: more letter classes than MaxChar";
     const size_t row_cells = RoundUp((size_t) m.letters + header_cells, 4);   // RowSize() :347
     const size_t row_bytes = row_cells * 4;
+    if ((size_t) m.states > size / row_bytes || (size_t) m.final_table_size > size / 8)
+        return "EOF reached while mapping Pire::Scanner";                    // :271-272 (tables larger than the image)
     const size_t buf = RoundUp((size_t) kMaxChar * 2 + (size_t) m.final_table_size * 8
                                + (size_t) m.states * 8 + row_bytes * m.states, 8);   // BufSize() :297-305
-    if (size < pos + buf)
+    if (size < pos || size - pos < buf)
         return "EOF reached while mapping Pire::Scanner";                    // :271-272
 
     // Markup(), :381-388.  The image may sit at any alignment in the caller's

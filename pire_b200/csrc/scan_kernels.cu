@@ -43,10 +43,11 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 // One dynamic shared-memory array for every kernel of this file.  The hot rows sit at its start (behind
-// the lane-private region in the PRIV kernel), 256-byte aligned: FastStep ORs the input byte into the
-// table's shared-window address with one PRMT (StageTables traps if the alignment ever fails).
+// the lane-private region in the PRIV kernel, a multiple of 16 KB), 256-byte aligned: FastStep ORs the input
+// byte into the table's shared-window address with one PRMT.  The array is declared with 1 KiB alignment so
+// that the alignment is a property of the build; StageTables keeps a trap as a backstop.
 extern "C" {
-extern __shared__ __align__(128) uint8_t pire_b200_smem[];
+extern __shared__ __align__(1024) uint8_t pire_b200_smem[];
 }
 
 namespace pire_b200 {
@@ -440,10 +441,25 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 //     p   = LOP3((t | g) != 0)              ... or the lane is outside id 0            [chain]
 //     a   = IMAD(g, 292, bb)                                                          [chain]
 //     g   = @p LDS.U8 [a]
-__device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, uint32_t filter, uint32_t& bb, uint32_t& pa)
+// k64 = false: 32-slot filter probed with the low five bits of bb (no extra instruction).
+// k64 = true : 64-slot filter (slot = byte & 63) probed with SHF.R.U64, which needs the slot alone in a register:
+//              one more IDP per byte on the word masked to six bits per byte (FMA pipe, and one LOP3 per word).
+//              Printable text folds 3:1 onto 32 slots but only 3:2 onto 64 (model: 1.72 -> 1.42 wavefronts per step).
+struct LookFilter {
+    uint32_t lo, hi;
+};
+
+template <bool k64, int kByte>
+__device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, const LookFilter& f, uint32_t& bb, uint32_t& pa)
 {
-    bb = __dp4a(w, 0x00000001u, base);
-    pa = __funnelshift_r(filter, filter, bb);
+    constexpr uint32_t sel = 1u << (8 * kByte);
+    bb = __dp4a(w, sel, base);
+    if (k64) {
+        const uint32_t slot = __dp4a(w & 0x3F3F3F3Fu, sel, 0u);
+        pa = (uint32_t) ((((uint64_t) f.hi << 32) | f.lo) >> slot);
+    } else {
+        pa = __funnelshift_r(f.lo, f.lo, bb);
+    }
 }
 
 __device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, uint32_t pa_next)
@@ -464,47 +480,70 @@ __device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, 
 
 // Four bytes.  (bb0, pa0) belong to byte 0 of `w` and were computed by the previous call; pan is the probe of the
 // byte that follows the word.
+template <bool k64>
 __device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, uint32_t pa0, uint32_t pan, uint32_t base,
-                                         uint32_t filter)
+                                         const LookFilter& f)
 {
-    const uint32_t bb1 = __dp4a(w, 0x00000100u, base);
-    const uint32_t bb2 = __dp4a(w, 0x00010000u, base);
-    const uint32_t bb3 = __dp4a(w, 0x01000000u, base);
-    const uint32_t pa1 = __funnelshift_r(filter, filter, bb1);
-    const uint32_t pa2 = __funnelshift_r(filter, filter, bb2);
-    const uint32_t pa3 = __funnelshift_r(filter, filter, bb3);
+    uint32_t bb1, bb2, bb3, pa1, pa2, pa3;
+    LookProbe<k64, 1>(w, base, f, bb1, pa1);
+    LookProbe<k64, 2>(w, base, f, bb2, pa2);
+    LookProbe<k64, 3>(w, base, f, bb3, pa3);
     LookStep(g, bb0, pa0, pa1);
     LookStep(g, bb1, pa1, pa2);
     LookStep(g, bb2, pa2, pa3);
     LookStep(g, bb3, pa3, pan);
 }
 
-// Sixteen bytes; (bb0, pa0) enter as the probe of v's first byte and leave as (bbn, pan), the probe of the byte
-// after the chunk (pan = all ones at the end of the string).
-__device__ __forceinline__ void LookChunk16(const Tables& t, LaneState& s, uint4 v, uint32_t& bb0, uint32_t& pa0, uint32_t bbn,
-                                            uint32_t pan, uint32_t filter)
+// Shared-window address of the dynamic shared memory array, as a link-time constant (a cvta of a generic pointer
+// costs an S2R + LEA wherever the compiler chooses to rematerialise it).
+__device__ __forceinline__ uint32_t SmemWindowBase()
+{
+    uint32_t v;
+    asm("mov.u32 %0, pire_b200_smem;" : "=r"(v));
+    return v;
+}
+
+// Thirty-two bytes (one LDG.256 per lane).  next0 = the word that follows the block (ignored when !more: the last
+// byte of a string is filtered alone).  A lane that left the hot rows reads the sink row from then on; one test
+// per block finds it and replays both 16-byte chunks through the complete table.
+template <bool k64>
+__device__ __forceinline__ void LookBlock32(const Tables& t, LaneState& s, const uint4& v0, const uint4& v1, uint32_t next0, bool more,
+                                            const LookFilter& f)
 {
     const uint32_t before = s.g;
     uint32_t g = s.g;
-    uint32_t b1, p1, b2, p2, b3, p3;
-    LookProbe(v.y, t.base, filter, b1, p1);
-    LookWord(g, v.x, bb0, pa0, p1, t.base, filter);
-    LookProbe(v.z, t.base, filter, b2, p2);
-    LookWord(g, v.y, b1, p1, p2, t.base, filter);
-    LookProbe(v.w, t.base, filter, b3, p3);
-    LookWord(g, v.z, b2, p2, p3, t.base, filter);
-    LookWord(g, v.w, b3, p3, pan, t.base, filter);
-    bb0 = bbn;
-    pa0 = pan;
+    uint32_t bb, pa, bn, pn;
+    LookProbe<k64, 0>(v0.x, t.base, f, bb, pa);
+    LookProbe<k64, 0>(v0.y, t.base, f, bn, pn);
+    LookWord<k64>(g, v0.x, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0>(v0.z, t.base, f, bb, pa);
+    LookWord<k64>(g, v0.y, bn, pn, pa, t.base, f);
+    LookProbe<k64, 0>(v0.w, t.base, f, bn, pn);
+    LookWord<k64>(g, v0.z, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0>(v1.x, t.base, f, bb, pa);
+    LookWord<k64>(g, v0.w, bn, pn, pa, t.base, f);
+    LookProbe<k64, 0>(v1.y, t.base, f, bn, pn);
+    LookWord<k64>(g, v1.x, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0>(v1.z, t.base, f, bb, pa);
+    LookWord<k64>(g, v1.y, bn, pn, pa, t.base, f);
+    LookProbe<k64, 0>(v1.w, t.base, f, bn, pn);
+    LookWord<k64>(g, v1.z, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0>(next0, t.base, f, bb, pa);
+    LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     s.g = g;
     if (g == t.H) {
-        uint32_t from = before == t.H ? s.cold : before;
-        uint32_t full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, v);
+        uint32_t full = before == t.H ? s.cold : before;
+        full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), full, v0);
+        full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), full, v1);
         SetFull(t, s, full);
     }
 }
 
-__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
+// 448 threads x 3 CTAs per SM: 48 registers per thread (512 x 3 leaves 40 and spills the string pointer into the loop)
+constexpr int kLookBlock = 448;
+
+template <bool k64>
+__global__ void __maxnreg__(48) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
@@ -512,22 +551,24 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformLookKernel
 
     Tables t;
     t.hot = sv.hot;
-    t.base = SmemAddr(sv.hot);
+    t.base = SmemWindowBase();          // the hot rows are the first thing in the array (CarveShared, no private region)
     t.cls = sv.cls;
     t.full = a.full;
     t.H = a.hot;
     t.letters = a.letters;
     t.wide = a.wide;
     t.m0 = a.look_bitmap;
-    const uint32_t filter = a.look_bitmap;
+    LookFilter f;
+    f.lo = k64 ? (uint32_t) a.look_bitmap64 : a.look_bitmap;
+    f.hi = (uint32_t) (a.look_bitmap64 >> 32);
 
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t units = (a.n + 31) / 32;
-    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    const uint32_t units = (uint32_t) ((a.n + 31) / 32);            // pire_gpu_run_batch keeps n <= 2^40 / 32 units below 2^32
+    const uint32_t warps = gridDim.x * (kLookBlock / 32);
     const uint32_t len = (uint32_t) a.fixed_len;
 
-    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
-        const uint64_t i = unit * 32 + lane;
+    for (uint32_t unit = blockIdx.x * (kLookBlock / 32) + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = (uint64_t) unit * 32 + lane;
         const bool valid = i < a.n;
         const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
 
@@ -536,34 +577,20 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformLookKernel
 
         if (len != 0) {
             uint4 a0, a1, b0, b1;
-            uint32_t bb0, pa0, bbm, pam, bbn, pan;
             LoadStream32(p, a0, a1);
-            LookProbe(a0.x, t.base, filter, bb0, pa0);
             for (uint32_t off = 0;;) {
                 off += 32;
                 const bool more_b = off < len;
                 if (more_b)
                     LoadStream32(p + off, b0, b1);
-                LookProbe(a1.x, t.base, filter, bbm, pam);
-                LookChunk16(t, s, a0, bb0, pa0, bbm, pam, filter);
-                bbn = 0;
-                pan = 0xffffffffu;
-                if (more_b)
-                    LookProbe(b0.x, t.base, filter, bbn, pan);
-                LookChunk16(t, s, a1, bb0, pa0, bbn, pan, filter);
+                LookBlock32<k64>(t, s, a0, a1, b0.x, more_b, f);
                 if (!more_b)
                     break;
                 off += 32;
                 const bool more_a = off < len;
                 if (more_a)
                     LoadStream32(p + off, a0, a1);
-                LookProbe(b1.x, t.base, filter, bbm, pam);
-                LookChunk16(t, s, b0, bb0, pa0, bbm, pam, filter);
-                bbn = 0;
-                pan = 0xffffffffu;
-                if (more_a)
-                    LookProbe(a0.x, t.base, filter, bbn, pan);
-                LookChunk16(t, s, b1, bb0, pa0, bbn, pan, filter);
+                LookBlock32<k64>(t, s, b0, b1, a0.x, more_a, f);
                 // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                 if (!more_a || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
                     break;
@@ -716,6 +743,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
             if (a.offsets) {
                 b = a.offsets[i];
                 e = a.offsets[i + 1] - a.trim;
+                e = e < b ? b : e;       // an empty entry of a trimmed (lines) batch, or caller offsets that step back
             } else {
                 b = i * a.fixed_len;
                 e = b + a.fixed_len;
@@ -862,7 +890,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
                     const uint64_t b = a.offsets[line];
                     const uint64_t e = a.offsets[line + 1] - a.trim;
                     const uint8_t* p = a.corpus + b;
-                    const uint32_t len = (uint32_t) (e - b);
+                    const uint32_t len = e > b ? (uint32_t) (e - b) : 0u;
                     mis = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
                     chunk = p - mis;
                     span = mis + len;
@@ -1216,6 +1244,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
             if (a.offsets) {
                 b = a.offsets[i];
                 e = a.offsets[i + 1] - a.trim;
+                e = e < b ? b : e;       // an empty entry of a trimmed (lines) batch, or caller offsets that step back
             } else {
                 b = i * a.fixed_len;
                 e = b + a.fixed_len;
@@ -1555,6 +1584,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
             if (a.offsets) {
                 b = a.offsets[i];
                 e = a.offsets[i + 1] - a.trim;
+                e = e < b ? b : e;       // an empty entry of a trimmed (lines) batch, or caller offsets that step back
             } else {
                 b = i * a.fixed_len;
                 e = b + a.fixed_len;
@@ -1661,6 +1691,7 @@ __global__ void __launch_bounds__(256) VisitCountKernel(const __grid_constant__ 
     if (a.offsets) {
         b = a.offsets[i];
         e = a.offsets[i + 1] - a.trim;
+        e = e < b ? b : e;
     } else {
         b = i * a.fixed_len;
         e = b + a.fixed_len;
@@ -1751,8 +1782,10 @@ const void* KernelFor(int variant, bool uniform)
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
     if (variant == kVariantLook && uniform)
-        return reinterpret_cast<const void*>(&ScanUniformLookKernel);
-    const bool pred = variant == kVariantPred || variant == kVariantLook;      // CSR batches: LOOK falls back to the exit filter
+        return reinterpret_cast<const void*>(&ScanUniformLookKernel<false>);
+    if (variant == kVariantLook64 && uniform)
+        return reinterpret_cast<const void*>(&ScanUniformLookKernel<true>);
+    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64;      // CSR batches: LOOK falls back to the exit filter
     if (uniform)
         return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
     return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
@@ -1772,7 +1805,7 @@ cudaError_t PrepareScanKernels(int device)
     err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err != cudaSuccess)
         return err;
-    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook})
+    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook, (int) kVariantLook64})
         for (bool uniform : {false, true}) {
             err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (err != cudaSuccess)
@@ -1784,7 +1817,7 @@ cudaError_t PrepareScanKernels(int device)
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
 {
     const bool priv = variant == kVariantPriv && uniform;
-    plan->block = priv ? kPrivBlock : kBlock;
+    plan->block = priv ? kPrivBlock : ((variant == kVariantLook || variant == kVariantLook64) && uniform) ? kLookBlock : kBlock;
     plan->shared = priv ? ScanSharedBytes(hot_small, priv_rows) : uniform ? ScanSharedBytes(hot, 0) : GenericSharedBytes(hot);
     int sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

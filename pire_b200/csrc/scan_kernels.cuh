@@ -35,6 +35,7 @@ struct ScanArgs {
     uint32_t start;              // state after Initialize()[+Begin()], new numbering
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     uint32_t look_bitmap;        // LOOK variant: 32-slot look-ahead filter (dfa_tables.hpp), slot = byte & 31
+    uint64_t look_bitmap64;      // LOOK64 variant: the same filter with 64 slots, slot = byte & 63
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;
     const uint8_t* hot8_small;   // PRIV variant's second tier: HotTableBytes(hot_small)
@@ -69,7 +70,7 @@ struct LaunchPlan {
     size_t shared = 0;
 };
 
-enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3, kVariantLook = 4 };
+enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3, kVariantLook = 4, kVariantLook64 = 5 };
 constexpr int kVariantSlots = 8;      // size of per-variant arrays (variant ids are 1-based)
 
 size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows);

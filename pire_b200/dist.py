@@ -19,8 +19,10 @@ def shard_bounds(n_strings, rank, world):
     """[lo, hi) of this rank: equal shares rounded up to 32 strings."""
     per = (n_strings + world - 1) // world
     per = (per + 31) // 32 * 32
-    lo = min(n_strings, rank * per)
-    hi = min(n_strings, lo + per)
+    # lo stays on the 32-string grid even for a rank whose shard is empty (n_strings < 32 * world):
+    # merge_match_bits places shards by lo // 32
+    lo = rank * per
+    hi = max(lo, min(n_strings, lo + per))
     return lo, hi
 
 
@@ -35,7 +37,8 @@ def merge_match_bits(local_bits, lo, n_total, group=None):
     assert lo % 32 == 0
     words = (n_total + 31) // 32
     full = torch.zeros(words, dtype=torch.int32, device=local_bits.device)
-    full[lo // 32: lo // 32 + local_bits.numel()] = local_bits
+    if local_bits.numel():                      # an empty shard contributes nothing but still joins the collective
+        full[lo // 32: lo // 32 + local_bits.numel()] = local_bits
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
     return full

@@ -108,8 +108,8 @@ class SynthSpec:
         """Contiguous string-index shard, boundaries aligned to 32 strings so bitmap words never straddle ranks."""
         per = (self.n_strings + world - 1) // world
         per = (per + 31) // 32 * 32
-        lo = min(self.n_strings, rank * per)
-        hi = min(self.n_strings, lo + per)
+        lo = rank * per                                  # stays on the 32-string grid even when the shard is empty
+        hi = max(lo, min(self.n_strings, lo + per))
         return SynthSpec(hi - lo, self.string_len, self.seed, self.plant_every, self.plants, self.first_string + lo), lo
 
 

@@ -112,7 +112,7 @@ def random_text(rng, n, length, alphabet=None):
     return rng.choice(np.frombuffer(alphabet, np.uint8), size=(n, length))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["plain", "pred", "priv", "look"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5], ids=["plain", "pred", "priv", "look", "look64"])
 def test_uniform_kernel_headline(variant, cuda_device, ref):
     """Fixed 1 KiB strings (the BASELINE configs' shape) through the uniform kernel,
     full comparison with the reference on 64 Ki strings, incl. StateIndex."""
@@ -163,7 +163,7 @@ def test_glued_ten_patterns(max_hot, tune, cuda_device, ref):
     host = spec.host_sample(0, n)
     f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=n, variant=1, threads=8)
     assert int((m_ref != 0).sum()) >= n // 8
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 3, 4, 5):
         sc.set_variant(variant)
         r = P.Runner(sc).Begin().Run(batch).End()
         assert (r.Matches().astype(np.uint8) == f_ref).all(), variant
@@ -197,7 +197,7 @@ def test_generic_kernel_mixed_lengths_utf8(cuda_device, ref):
     assert int(want[0].sum()) >= len(strings) // 5
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4], ids=["plain", "pred", "priv", "look"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5], ids=["plain", "pred", "priv", "look", "look64"])
 def test_uniform_kernel_binary_bytes(variant, cuda_device, ref):
     """Fixed-length strings over the whole byte range (UTF-8 pattern): the private-row
     kernel covers bytes < 128 only and must re-walk every word holding a byte >= 128."""
@@ -259,7 +259,7 @@ def test_look_variant_dense_near_misses(length, cuda_device, ref):
         for begin in (True, False):
             for end in (True, False):
                 f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=length, n=n, begin=begin, end=end, variant=1, threads=8)
-                for variant in (1, 4):
+                for variant in (1, 4, 5):
                     sc.set_variant(variant)
                     r = P.Runner(sc)
                     r = r.Begin() if begin else r
@@ -391,7 +391,7 @@ def test_autoselect_keeps_results(cuda_device, ref):
     sc.Tune(batch, 4096)
     ms = sc.AutoSelect(batch)
     assert set(ms) >= {"plain", "pred"} and all(v > 0 for v in ms.values())
-    assert sc.info().variant in (1, 2, 3, 4)
+    assert sc.info().variant in (1, 2, 3, 4, 5)
     r = P.Runner(sc).Begin().Run(batch).End()
     f_ref, m_ref, _ = sc_ref.run(spec.host_sample(0, n), fixed_len=1024, n=n, variant=1, threads=8)
     assert (r.Matches().astype(np.uint8) == f_ref).all() and (r.AcceptMasks() == m_ref).all()
@@ -502,7 +502,7 @@ def test_fuzz_random_patterns(cuda_device, ref):
         sc.Tune(batch, 512)
         want = sc_ref.run(corpus, offs, variant=0)
         want_fixed = sc_ref.run(fixed, fixed_len=64, n=2048, variant=0)
-        for variant in (1, 2, 3, 4):
+        for variant in (1, 2, 3, 4, 5):
             sc.set_variant(variant)
             r = P.Runner(sc).Begin().Run(batch).End()
             ok = (r.Matches().astype(np.uint8) == want[0]).all() and (r.AcceptMasks() == want[1]).all()

@@ -8,7 +8,7 @@ timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "look or 
 echo "pytest exit $?" >> $OUT/r2_pytest_look.log
 tail -5 $OUT/r2_pytest_look.log
 for wl in glue10 headline; do
-  for v in plain pred look; do
+  for v in pred look look64; do
     timeout 600 python bench.py --workload $wl --variant $v --steps 10 --warmup 3 --no-e2e --no-cpu > $OUT/r2_bench_${wl}_${v}.json 2> $OUT/r2_bench_${wl}_${v}.err
     python - <<PY
 import json
@@ -23,3 +23,5 @@ done
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniformLook -s 3 -c 1 -f -o $OUT/r2_prof_glue10_look \
     python bench.py --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant look > $OUT/r2_ncu_look.log 2>&1
 ls -la $OUT/*.ncu-rep | tail -3
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniformLook -s 3 -c 1 -f -o $OUT/r2_prof_glue10_look64 \
+    python bench.py --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --variant look64 > $OUT/r2_ncu_look64.log 2>&1
