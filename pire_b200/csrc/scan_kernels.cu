@@ -539,11 +539,15 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, LaneState& s, const
     }
 }
 
-// 448 threads x 3 CTAs per SM: 48 registers per thread (512 x 3 leaves 40 and spills the string pointer into the loop)
-constexpr int kLookBlock = 448;
+// Register budget.  The register file is split between the four warp schedulers (16 K registers each), so a
+// CTA's warps should be a multiple of four: 512 threads x 3 CTAs leaves 40 registers per thread (12 warps x 1280
+// per scheduler), 384 threads x 3 CTAs leaves 48 (9 warps x 1536).  Both instantiations exist; the launch plan picks
+// (PIRE_B200_LOOK_REGS=40|48 for experiments).
+constexpr int kLookBlock40 = 512;
+constexpr int kLookBlock48 = 384;
 
-template <bool k64>
-__global__ void __maxnreg__(48) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
+template <bool k64, int kRegs>
+__global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
@@ -564,10 +568,11 @@ __global__ void __maxnreg__(48) ScanUniformLookKernel(const __grid_constant__ Sc
 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t units = (uint32_t) ((a.n + 31) / 32);            // pire_gpu_run_batch keeps n <= 2^40 / 32 units below 2^32
-    const uint32_t warps = gridDim.x * (kLookBlock / 32);
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t warps = gridDim.x * warps_per_block;
     const uint32_t len = (uint32_t) a.fixed_len;
 
-    for (uint32_t unit = blockIdx.x * (kLookBlock / 32) + (threadIdx.x >> 5); unit < units; unit += warps) {
+    for (uint32_t unit = blockIdx.x * warps_per_block + (threadIdx.x >> 5); unit < units; unit += warps) {
         const uint64_t i = (uint64_t) unit * 32 + lane;
         const bool valid = i < a.n;
         const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
@@ -1777,14 +1782,25 @@ const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUnifo
 template <bool kPred>
 const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kPred>); }
 
+int LookRegs()
+{
+    static const int regs = [] {
+        const char* env = getenv("PIRE_B200_LOOK_REGS");
+        return env && atoi(env) == 40 ? 40 : 48;
+    }();
+    return regs;
+}
+
 const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
     if (variant == kVariantLook && uniform)
-        return reinterpret_cast<const void*>(&ScanUniformLookKernel<false>);
+        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48>)
+                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40>);
     if (variant == kVariantLook64 && uniform)
-        return reinterpret_cast<const void*>(&ScanUniformLookKernel<true>);
+        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48>)
+                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40>);
     const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64;      // CSR batches: LOOK falls back to the exit filter
     if (uniform)
         return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
@@ -1810,6 +1826,12 @@ cudaError_t PrepareScanKernels(int device)
             err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (err != cudaSuccess)
                 return err;
+            // three CTAs of ~75 KB each per SM: ask for the largest shared-memory carve-out (kernels without a
+            // blocks-per-SM launch bound would otherwise get a smaller one and run two CTAs)
+            err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared);
+            if (err != cudaSuccess)
+                return err;
         }
     return cudaSuccess;
 }
@@ -1817,7 +1839,7 @@ cudaError_t PrepareScanKernels(int device)
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
 {
     const bool priv = variant == kVariantPriv && uniform;
-    plan->block = priv ? kPrivBlock : ((variant == kVariantLook || variant == kVariantLook64) && uniform) ? kLookBlock : kBlock;
+    plan->block = priv ? kPrivBlock : ((variant == kVariantLook || variant == kVariantLook64) && uniform) ? (LookRegs() == 48 ? kLookBlock48 : kLookBlock40) : kBlock;
     plan->shared = priv ? ScanSharedBytes(hot_small, priv_rows) : uniform ? ScanSharedBytes(hot, 0) : GenericSharedBytes(hot);
     int sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

@@ -150,12 +150,15 @@ def test_synth_corpus_is_deterministic_and_planted():
 
 
 def test_shards_tile_the_batch():
-    for n in (0, 1, 31, 32, 33, 1000, 10_000_000, 78_125_000):
+    """Non-empty shards tile [0, n) in rank order; every shard starts on the 32-string grid (bitmap words never
+    straddle ranks), also the empty shards of a batch smaller than 32 * world strings."""
+    for n in (0, 1, 31, 32, 33, 100, 1000, 10_000_000, 78_125_000):
         for world in (1, 2, 4, 8):
-            prev = 0
+            covered = 0
             for r in range(world):
                 lo, hi = shard_bounds(n, r, world)
-                assert lo == prev and lo % 32 == 0 or lo == n
-                assert hi >= lo
-                prev = hi
-            assert prev == n
+                assert lo % 32 == 0 and hi >= lo
+                if hi > lo:
+                    assert lo == covered
+                    covered = hi
+            assert covered == n
