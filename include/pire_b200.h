@@ -205,9 +205,19 @@ int pire_gpu_run_lines(const pire_gpu_scanner* sc, const uint8_t* d_text, const 
                        const uint32_t* d_order, uint64_t n_lines, uint32_t flags,
                        uint32_t* d_match_bits, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream);
 
-/* Same call with HOST buffers (what a Pire user holds: const char* ranges):
- * copies corpus (+offsets) to the device, runs, copies the requested results
- * back and synchronises.  corpus_bytes = total bytes of the corpus buffer. */
+/* Same call with HOST buffers -- what a Pire user holds: Run(const char* begin, const char* end) takes pageable
+ * memory (run.h:271-275; samples/pigrep/pigrep.cpp:38-45).  The corpus is cut into chunks of whole 32-string
+ * units (about 64 MiB; PIRE_B200_HOST_CHUNK_MB) and streamed through a ring of three device slots: the
+ * host->device copy of chunk k+1 overlaps the scan of chunk k and the device->host copy of its results.
+ * Pageable input is staged through the library's own pinned buffers by a few copy threads
+ * (PIRE_B200_HOST_THREADS, default min(8, cores / 4)); pinned or cudaHostRegister-ed input is DMA-ed straight
+ * from the caller's buffer.  The device never holds more than the ring, so corpora larger than HBM stream through.
+ * CSR batches are length-binned per chunk (pire_gpu_length_order).  Results are those of pire_gpu_run_batch on
+ * the resident corpus.  Returns after everything has landed in the caller's arrays.
+ * corpus_bytes = size of the corpus buffer; offsets (if any) must ascend and end within it, n * fixed_len
+ * must fit in it (PIRE_GPU_EINVAL otherwise).
+ * Concurrency: calls on one handle from several threads run concurrently, each with its own workspace
+ * (streams, slots, staging); workspaces are kept with the handle and freed by pire_gpu_scanner_destroy. */
 int pire_gpu_run_batch_host(const pire_gpu_scanner* sc,
                             const uint8_t* corpus, uint64_t corpus_bytes, const uint64_t* offsets,
                             uint64_t fixed_len, uint64_t n, uint32_t flags,
@@ -230,6 +240,17 @@ int pire_gpu_scanner_tune(pire_gpu_scanner* sc,
 int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc,
                                 const uint8_t* d_corpus, const uint64_t* d_offsets,
                                 uint64_t fixed_len, uint64_t n, uint32_t flags, void* stream, float* ms_out);
+
+/* AcceptedRegexps for scanners with MORE than 32 regexps (multi.h:149-158 returns a list of any length; Glue only
+ * caps the states, multi.h:1092-1103).  The scan entry points' d_accept_masks holds ids 0..31; the complete answer
+ * comes from the state each string stopped in: run with d_state_idx, then
+ *     pire_gpu_accept_sets(sc, d_state_idx, n, d_sets, stream)
+ * writes n rows of pire_gpu_accept_words(sc) = ceil(max(1, RegexpsCount()) / 32) words, bit (r % 32) of word
+ * r / 32 of row i set iff regexp r is in AcceptedRegexps of string i's last state (after End() when the run
+ * stepped it).  A state index outside the scanner yields an empty set. */
+uint32_t pire_gpu_accept_words(const pire_gpu_scanner* sc);
+int pire_gpu_accept_sets(const pire_gpu_scanner* sc, const uint32_t* d_state_idx, uint64_t n,
+                         uint32_t* d_accept_sets, void* stream);
 
 /* Number of kernels this library has launched in the calling process. */
 uint64_t pire_gpu_launch_count(void);
@@ -269,6 +290,8 @@ typedef struct pire_gpu_synth {
 
 int pire_gpu_synth_fill_device(const pire_gpu_synth* spec, uint8_t* d_corpus, int device, void* stream);
 int pire_gpu_synth_fill_host(const pire_gpu_synth* spec, uint8_t* corpus, uint64_t first, uint64_t count);
+/* strings indices[0..count) of the corpus (relative to spec->first_string), back to back: stratified parity samples */
+int pire_gpu_synth_fill_host_indexed(const pire_gpu_synth* spec, uint8_t* corpus, const uint64_t* indices, uint64_t count);
 
 /* kind 1: mixed-length UTF-8 corpus (BASELINE config 4): lengths log-uniform in
  * [16, 65536), multiples of 4; ASCII / 2-byte Cyrillic / 3-byte code points; every

@@ -30,6 +30,7 @@ SYMBOLS = [
     "pire_gpu_synth_fill_device", "pire_gpu_synth_fill_host", "pire_gpu_synth_mixed_lengths_device",
     "pire_gpu_synth_mixed_lengths_host", "pire_gpu_synth_mixed_fill_device", "pire_gpu_synth_mixed_fill_host",
     "pire_gpu_last_error", "pire_gpu_version",
+    "pire_gpu_accept_words", "pire_gpu_accept_sets", "pire_gpu_synth_fill_host_indexed",
 ]
 
 
@@ -88,6 +89,10 @@ def _load():
     lib.pire_gpu_synth_mixed_fill_host.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, vp, vp]
     lib.pire_gpu_last_error.restype = C.c_char_p
     lib.pire_gpu_version.restype = C.c_char_p
+    lib.pire_gpu_accept_words.argtypes = [vp]
+    lib.pire_gpu_accept_words.restype = C.c_uint32
+    lib.pire_gpu_accept_sets.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    lib.pire_gpu_synth_fill_host_indexed.argtypes = [C.POINTER(Synth), vp, vp, C.c_uint64]
     return lib
 
 

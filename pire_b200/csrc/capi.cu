@@ -5,28 +5,22 @@
 // the sm_100a kernels (scan_kernels.cu).  There is deliberately no CPU scan
 // here: without a CUDA device every run entry point fails with
 // PIRE_GPU_ENODEVICE.
-#include "../../include/pire_b200.h"
-
-#include <cuda_runtime.h>
+#include "capi_internal.hpp"
 
 #include <cstdlib>
 #include <cstring>
 #include <exception>
-#include <mutex>
 #include <new>
-#include <string>
-#include <vector>
 
-#include "dfa_tables.hpp"
-#include "pire_image.hpp"
-#include "scan_kernels.cuh"
 #include "synth.h"
 
 using namespace pire_b200;
 
-namespace {
+namespace pire_b200 {
 
+namespace {
 thread_local std::string g_error;
+}
 
 int Fail(int code, const std::string& what)
 {
@@ -40,80 +34,25 @@ int FailCuda(cudaError_t err, const char* where)
     return PIRE_GPU_ECUDA;
 }
 
-#define CUDA_TRY(expr)                                   \
-    do {                                                 \
-        cudaError_t err__ = (expr);                      \
-        if (err__ != cudaSuccess)                        \
-            return FailCuda(err__, #expr);               \
-    } while (0)
+void DeviceTables::Free()
+{
+    cudaFree(hot8);
+    cudaFree(noexit);
+    cudaFree(cls);
+    cudaFree(full);
+    cudaFree(fin[0]);
+    cudaFree(fin[1]);
+    cudaFree(priv_packed);
+    cudaFree(hot8_small);
+    cudaFree(flags);
+    cudaFree(acc_begin);
+    cudaFree(acc_ids);
+    cudaFree(weights);
+    cudaFree(accept_wide);
+    *this = DeviceTables();
+}
 
-struct DeviceTables {
-    uint8_t* hot8 = nullptr;
-    uint8_t* noexit = nullptr;
-    uint16_t* cls = nullptr;
-    void* full = nullptr;
-    DeviceFin* fin[2] = {nullptr, nullptr};
-    uint32_t* priv_packed = nullptr;
-    uint8_t* hot8_small = nullptr;
-    uint8_t* flags = nullptr;
-    uint32_t* acc_begin = nullptr;
-    uint32_t* acc_ids = nullptr;
-    uint64_t* weights = nullptr;
-    size_t full_bytes = 0;
-
-    void Free()
-    {
-        cudaFree(hot8);
-        cudaFree(noexit);
-        cudaFree(cls);
-        cudaFree(full);
-        cudaFree(fin[0]);
-        cudaFree(fin[1]);
-        cudaFree(priv_packed);
-        cudaFree(hot8_small);
-        cudaFree(flags);
-        cudaFree(acc_begin);
-        cudaFree(acc_ids);
-        cudaFree(weights);
-        *this = DeviceTables();
-    }
-};
-
-} // namespace
-
-struct pire_gpu_scanner {
-    Dfa dfa;
-    ScanTables tab;
-    DeviceTables dev;
-    int device = -1;
-    uint32_t variant = PIRE_GPU_VARIANT_AUTO;
-    uint32_t auto_choice[2] = {0, 0};   // [uniform]: measured by pire_gpu_scanner_autoselect, 0 = heuristic
-    uint32_t max_hot = kMaxHot;
-    bool tuned = false;
-    bool priv_ok = false;
-    // counting kernel: 0 = automatic, 1 = accept lists, 2 = packed increments behind the look-ahead pass,
-    // 3 = packed increments on every chunk (pire_gpu_scanner_set_count_mode; for tests and experiments)
-    uint32_t count_mode = 0;
-    double final_share = 0.0;       // share of a tune sample's steps that ended in a final state
-    std::vector<uint32_t> hot_order;
-    LaunchPlan plan[kVariantSlots][2];          // [variant][uniform]
-
-    // workspace of the host-buffer entry point
-    std::mutex host_mutex;
-    uint8_t* ws_corpus = nullptr;
-    size_t ws_corpus_bytes = 0;
-    uint64_t* ws_offsets = nullptr;
-    size_t ws_offsets_bytes = 0;
-    uint32_t* ws_out = nullptr;
-    size_t ws_out_bytes = 0;
-    uint32_t* ws_order = nullptr;
-    size_t ws_order_bytes = 0;
-    cudaStream_t ws_stream = nullptr;
-};
-
-namespace {
-
-uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform = true)
+uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform)
 {
     if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_LOOK64) {
         if (sc->variant >= PIRE_GPU_VARIANT_LOOK && !sc->tab.look_ok)
@@ -131,6 +70,8 @@ uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform = true)
         return PIRE_GPU_VARIANT_PLAIN;
     return sc->tab.states > 64 ? PIRE_GPU_VARIANT_PRED : PIRE_GPU_VARIANT_PLAIN;
 }
+
+namespace {
 
 int Upload(pire_gpu_scanner* sc)
 {
@@ -170,6 +111,21 @@ int Upload(pire_gpu_scanner* sc)
     CUDA_TRY(cudaMalloc(&d.weights, t.weights.size() * 8 + 8));
     if (!t.weights.empty())
         CUDA_TRY(cudaMemcpy(d.weights, t.weights.data(), t.weights.size() * 8, cudaMemcpyHostToDevice));
+    // AcceptedRegexps as a bit set per state (reference numbering), for automata with more than 32 regexps:
+    // pire_gpu_accept_sets gathers rows of this table by StateIndex
+    {
+        const uint32_t regs = sc->dfa.regexps ? sc->dfa.regexps : 1;
+        sc->accept_words = (regs + 31) / 32;
+        std::vector<uint32_t> wide((size_t) sc->dfa.states * sc->accept_words, 0);
+        for (uint32_t st = 0; st < sc->dfa.states; ++st)
+            for (uint32_t k = sc->dfa.acc_begin[st]; k < sc->dfa.acc_begin[st + 1]; ++k) {
+                const uint32_t id = sc->dfa.acc_ids[k];
+                if (id < regs)
+                    wide[(size_t) st * sc->accept_words + id / 32] |= 1u << (id % 32);
+            }
+        CUDA_TRY(cudaMalloc(&d.accept_wide, wide.size() * 4));
+        CUDA_TRY(cudaMemcpy(d.accept_wide, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
+    }
     sc->priv_ok = false;
     for (int v = kVariantPlain; v <= kVariantLook64; ++v)
         for (int u = 0; u < 2; ++u) {
@@ -190,6 +146,8 @@ void Rebuild(pire_gpu_scanner* sc)
 {
     BuildScanTables(sc->dfa, sc->hot_order, sc->max_hot, &sc->tab);
 }
+
+} // namespace
 
 bool IsUniform(const uint8_t* corpus, const uint64_t* offsets, uint64_t fixed_len)
 {
@@ -234,7 +192,7 @@ int CheckRunnable(const pire_gpu_scanner* sc)
     return PIRE_GPU_OK;
 }
 
-} // namespace
+} // namespace pire_b200
 
 extern "C" {
 
@@ -295,12 +253,7 @@ void pire_gpu_scanner_destroy(pire_gpu_scanner* sc)
     if (sc->device >= 0) {
         cudaSetDevice(sc->device);
         sc->dev.Free();
-        cudaFree(sc->ws_corpus);
-        cudaFree(sc->ws_offsets);
-        cudaFree(sc->ws_out);
-        cudaFree(sc->ws_order);
-        if (sc->ws_stream)
-            cudaStreamDestroy(sc->ws_stream);
+        FreeHostWorkspaces(sc);
     }
     delete sc;
 }
@@ -464,6 +417,23 @@ int pire_gpu_count_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, co
     return PIRE_GPU_OK;
 }
 
+uint32_t pire_gpu_accept_words(const pire_gpu_scanner* sc) { return sc ? sc->accept_words : 0; }
+
+int pire_gpu_accept_sets(const pire_gpu_scanner* sc, const uint32_t* d_state_idx, uint64_t n, uint32_t* d_accept_sets, void* stream)
+{
+    int rc = CheckRunnable(sc);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (n == 0)
+        return PIRE_GPU_OK;
+    if (!d_state_idx || !d_accept_sets)
+        return Fail(PIRE_GPU_EINVAL, "null state indices or output");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    CUDA_TRY(LaunchAcceptGather(sc->dev.accept_wide, sc->dfa.states, sc->accept_words, d_state_idx, n, d_accept_sets,
+                                static_cast<cudaStream_t>(stream)));
+    return PIRE_GPU_OK;
+}
+
 int pire_gpu_length_order(const uint64_t* d_offsets, uint64_t n, uint32_t* d_order, int device, void* stream)
 {
     if (n && (!d_offsets || !d_order))
@@ -564,83 +534,6 @@ static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uin
         cudaFreeAsync(counter, st);
     if (ce != cudaSuccess)
         return FailCuda(ce, "pire_gpu_run_batch (CSR)");
-    return PIRE_GPU_OK;
-}
-
-int pire_gpu_run_batch_host(const pire_gpu_scanner* csc, const uint8_t* corpus, uint64_t corpus_bytes,
-                            const uint64_t* offsets, uint64_t fixed_len, uint64_t n, uint32_t flags,
-                            uint32_t* match_bits, uint32_t* accept_masks, uint32_t* state_idx)
-{
-    int rc = CheckRunnable(csc);
-    if (rc != PIRE_GPU_OK)
-        return rc;
-    if (n == 0)
-        return PIRE_GPU_OK;
-    pire_gpu_scanner* sc = const_cast<pire_gpu_scanner*>(csc);
-    std::lock_guard<std::mutex> lock(sc->host_mutex);
-    CUDA_TRY(cudaSetDevice(sc->device));
-    if (!sc->ws_stream)
-        CUDA_TRY(cudaStreamCreateWithFlags(&sc->ws_stream, cudaStreamNonBlocking));
-    cudaStream_t st = sc->ws_stream;
-
-    const size_t need_corpus = (size_t) corpus_bytes + 64;
-    if (sc->ws_corpus_bytes < need_corpus) {
-        cudaFree(sc->ws_corpus);
-        sc->ws_corpus = nullptr;
-        sc->ws_corpus_bytes = 0;
-        CUDA_TRY(cudaMalloc(&sc->ws_corpus, need_corpus));
-        sc->ws_corpus_bytes = need_corpus;
-    }
-    const size_t need_off = offsets ? (size_t) (n + 1) * 8 : 0;
-    if (sc->ws_offsets_bytes < need_off) {
-        cudaFree(sc->ws_offsets);
-        sc->ws_offsets = nullptr;
-        sc->ws_offsets_bytes = 0;
-        CUDA_TRY(cudaMalloc(&sc->ws_offsets, need_off));
-        sc->ws_offsets_bytes = need_off;
-    }
-    const size_t words = (size_t) ((n + 31) / 32);
-    const size_t need_out = (words + 2 * (size_t) n) * 4;
-    if (sc->ws_out_bytes < need_out) {
-        cudaFree(sc->ws_out);
-        sc->ws_out = nullptr;
-        sc->ws_out_bytes = 0;
-        CUDA_TRY(cudaMalloc(&sc->ws_out, need_out));
-        sc->ws_out_bytes = need_out;
-    }
-    uint32_t* d_bits = match_bits ? sc->ws_out : nullptr;
-    uint32_t* d_masks = accept_masks ? sc->ws_out + words : nullptr;
-    uint32_t* d_states = state_idx ? sc->ws_out + words + n : nullptr;
-    const bool binned = offsets != nullptr && n >= 64 && n < (1ull << 31);
-    if (binned && sc->ws_order_bytes < (size_t) n * 4) {
-        cudaFree(sc->ws_order);
-        sc->ws_order = nullptr;
-        sc->ws_order_bytes = 0;
-        CUDA_TRY(cudaMalloc(&sc->ws_order, (size_t) n * 4));
-        sc->ws_order_bytes = (size_t) n * 4;
-    }
-
-    if (corpus_bytes)
-        CUDA_TRY(cudaMemcpyAsync(sc->ws_corpus, corpus, corpus_bytes, cudaMemcpyHostToDevice, st));
-    if (offsets)
-        CUDA_TRY(cudaMemcpyAsync(sc->ws_offsets, offsets, need_off, cudaMemcpyHostToDevice, st));
-    if (binned) {
-        // strings of unknown, unequal lengths: bin them so that a warp's lanes finish together
-        CUDA_TRY(LengthOrder(sc->ws_offsets, n, sc->ws_order, st));
-        rc = pire_gpu_run_batch_ordered(sc, sc->ws_corpus, sc->ws_offsets, sc->ws_order, n, flags, d_bits, d_masks, d_states, st);
-    } else {
-        rc = pire_gpu_run_batch(sc, sc->ws_corpus, offsets ? sc->ws_offsets : nullptr, fixed_len, n, flags,
-                                d_bits, d_masks, d_states, st);
-    }
-    if (rc != PIRE_GPU_OK)
-        return rc;
-    if (match_bits)
-        CUDA_TRY(cudaMemcpyAsync(match_bits, d_bits, words * 4, cudaMemcpyDeviceToHost, st));
-    if (accept_masks)
-        CUDA_TRY(cudaMemcpyAsync(accept_masks, d_masks, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-    if (state_idx)
-        CUDA_TRY(cudaMemcpyAsync(state_idx, d_states, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     return PIRE_GPU_OK;
 }
 
@@ -873,6 +766,34 @@ int pire_gpu_synth_fill_host(const pire_gpu_synth* spec, uint8_t* corpus, uint64
     const uint32_t words = p.string_len / 8;
     for (uint64_t k = 0; k < count; ++k) {
         const uint64_t gi = p.first_string + first + k;
+        uint8_t* dst = corpus + k * (uint64_t) p.string_len;
+        for (uint32_t w = 0; w < words; ++w) {
+            uint64_t v = SynthWord(p.seed, gi, w, words);
+            std::memcpy(dst + (size_t) w * 8, &v, 8);
+        }
+        uint32_t off = 0;
+        int id = SynthPlant(p, gi, &off);
+        if (id >= 0) {
+            std::memcpy(dst + off, packed.data() + p.plant_off[id], p.plant_off[id + 1] - p.plant_off[id]);
+            if (p.tail && p.plant_mode[id] == 0)
+                dst[p.string_len - 1] = (uint8_t) p.tail;
+        }
+    }
+    return PIRE_GPU_OK;
+}
+
+int pire_gpu_synth_fill_host_indexed(const pire_gpu_synth* spec, uint8_t* corpus, const uint64_t* indices, uint64_t count)
+{
+    SynthParams p;
+    int rc = FillSynthParams(spec, &p);
+    if (rc != PIRE_GPU_OK)
+        return rc;
+    if (count && (!corpus || !indices))
+        return Fail(PIRE_GPU_EINVAL, "null corpus or indices");
+    std::string packed = PackPlants(spec);
+    const uint32_t words = p.string_len / 8;
+    for (uint64_t k = 0; k < count; ++k) {
+        const uint64_t gi = p.first_string + indices[k];
         uint8_t* dst = corpus + k * (uint64_t) p.string_len;
         for (uint32_t w = 0; w < words; ++w) {
             uint64_t v = SynthWord(p.seed, gi, w, words);

@@ -128,6 +128,21 @@ __device__ __forceinline__ uint4 LoadShared16(uint32_t shared_addr)
 
 // Streaming read-only load of the corpus (uniform kernels): 32 bytes = one full sector per
 // lane per request, never re-used by this SM.
+// L2 prefetch of the 128-byte line at p: no destination registers, so nothing tempts the scheduler to delay it.
+__device__ __forceinline__ void PrefetchL2(const uint8_t* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// The same load with a 256-byte L2 prefetch: the first touch of a 256-byte region of a string brings all of it
+// into L2, so the following seven 32-byte loads of the lane are L2 hits.
+__device__ __forceinline__ void LoadStream32P(const uint8_t* p, uint4& a, uint4& b)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+
 __device__ __forceinline__ void LoadStream32(const uint8_t* p, uint4& a, uint4& b)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -528,7 +543,12 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, LaneState& s, const
     LookWord<k64>(g, v1.y, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v1.w, t.base, f, bn, pn);
     LookWord<k64>(g, v1.z, bb, pa, pn, t.base, f);
-    LookProbe<k64, 0>(next0, t.base, f, bb, pa);
+    // The word after the block was requested from HBM when this block began: its probe must stay down here (an
+    // ordinary intrinsic is hoisted to the top of the block by the compiler, where it waits for the whole DRAM
+    // latency -- ncu: 10 % of all stall samples on that one IDP).  asm volatile keeps it behind the steps above.
+    uint32_t late;
+    asm volatile("mov.b32 %0, %1;" : "=r"(late) : "r"(next0));
+    LookProbe<k64, 0>(late, t.base, f, bb, pa);
     LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     s.g = g;
     if (g == t.H) {
@@ -581,20 +601,32 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
         SetFull(t, s, a.start);
 
         if (len != 0) {
+            // The scheduler sinks the 32-byte loads towards their first use to save registers (seen in SASS: a dozen
+            // steps ahead instead of thirty-two), which would expose most of a DRAM round trip per block.  So HBM
+            // latency is covered one level up: every 128 bytes a lane prefetches the line 512 bytes ahead into L2
+            // (no destination registers -- nothing to sink), and the loads themselves only have to cover an L2 hit.
             uint4 a0, a1, b0, b1;
-            LoadStream32(p, a0, a1);
+            if (len > 128)
+                PrefetchL2(p + 128);
+            if (len > 256)
+                PrefetchL2(p + 256);
+            if (len > 384)
+                PrefetchL2(p + 384);
+            LoadStream32P(p, a0, a1);
             for (uint32_t off = 0;;) {
+                if ((off & 64) == 0 && off + 512 < len)
+                    PrefetchL2(p + off + 512);
                 off += 32;
                 const bool more_b = off < len;
                 if (more_b)
-                    LoadStream32(p + off, b0, b1);
+                    LoadStream32P(p + off, b0, b1);
                 LookBlock32<k64>(t, s, a0, a1, b0.x, more_b, f);
                 if (!more_b)
                     break;
                 off += 32;
                 const bool more_a = off < len;
                 if (more_a)
-                    LoadStream32(p + off, a0, a1);
+                    LoadStream32P(p + off, a0, a1);
                 LookBlock32<k64>(t, s, b0, b1, a0.x, more_a, f);
                 // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                 if (!more_a || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
@@ -2193,6 +2225,34 @@ cudaError_t LaunchSynthMixedFill(uint64_t seed, uint32_t plant_every, uint64_t f
     uint64_t blocks = (n + 7) / 8;
     SynthMixedFillKernel<<<(unsigned) (blocks < 148ull * 32 ? blocks : 148ull * 32), 256, 0, stream>>>(seed, plant_every, first, n,
                                                                                                    d_offsets, d_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+namespace {
+// AcceptedRegexps of the state every string stopped in, as a bit set of `words` 32-bit words (multi.h:149-158 for
+// scanners with more than 32 regexps; the scan kernels' accept mask holds ids 0..31 only).
+__global__ void __launch_bounds__(256) AcceptGatherKernel(const uint32_t* __restrict__ table, uint32_t states, uint32_t words,
+                                                          const uint32_t* __restrict__ state_idx, uint64_t n, uint32_t* __restrict__ out)
+{
+    const uint64_t total = n * words;
+    for (uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (uint64_t) gridDim.x * blockDim.x) {
+        const uint64_t i = k / words;
+        const uint32_t w = (uint32_t) (k % words);
+        const uint32_t st = state_idx[i];
+        out[k] = st < states ? __ldg(table + (size_t) st * words + w) : 0u;
+    }
+}
+} // namespace
+
+cudaError_t LaunchAcceptGather(const uint32_t* d_table, uint32_t states, uint32_t words, const uint32_t* d_state_idx, uint64_t n,
+                               uint32_t* d_out, cudaStream_t stream)
+{
+    if (n == 0 || words == 0)
+        return cudaSuccess;
+    const uint64_t total = n * words;
+    const uint64_t blocks = (total + 255) / 256;
+    AcceptGatherKernel<<<(unsigned) (blocks < 148ull * 32 ? blocks : 148ull * 32), 256, 0, stream>>>(d_table, states, words, d_state_idx, n, d_out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -98,6 +98,10 @@ cudaError_t LaunchSynthMixedLengths(uint64_t seed, uint64_t first, uint64_t n, u
 cudaError_t LaunchSynthMixedFill(uint64_t seed, uint32_t plant_every, uint64_t first, uint64_t n, const uint64_t* d_offsets,
                                  uint8_t* d_out, cudaStream_t stream);
 
+// out[i * words + w] = table[state_idx[i] * words + w] (a state index outside the table yields zeros)
+cudaError_t LaunchAcceptGather(const uint32_t* d_table, uint32_t states, uint32_t words, const uint32_t* d_state_idx, uint64_t n,
+                               uint32_t* d_out, cudaStream_t stream);
+
 uint64_t KernelLaunchCount();
 
 } // namespace pire_b200
