@@ -9,15 +9,15 @@ NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall 
 
 CSRC      := pire_b200/csrc
 LIB       := pire_b200/libpire_b200.so
-LIB_SRC   := $(CSRC)/pire_image.cpp $(CSRC)/dfa_tables.cpp $(CSRC)/scan_kernels.cu $(CSRC)/capi.cu $(CSRC)/capi_host.cu
+LIB_SRC   := $(CSRC)/pire_image.cpp $(CSRC)/dfa_tables.cpp $(CSRC)/scan_kernels.cu $(CSRC)/capi.cu $(CSRC)/capi_host.cu $(CSRC)/capi_dist.cu
 LIB_HDR   := $(CSRC)/capi_internal.hpp $(CSRC)/pire_image.hpp $(CSRC)/dfa_tables.hpp $(CSRC)/scan_kernels.cuh $(CSRC)/synth.h include/pire_b200.h
 
 ORACLE    := oracle/libpire_oracle.so
 
 all: $(LIB) $(ORACLE)
 
-$(LIB): $(LIB_SRC) $(LIB_HDR)
-	$(NVCC) $(NVCCFLAGS) -shared $(LIB_SRC) -o $@ 2> build/ptxas_$(notdir $@).log || (cat build/ptxas_$(notdir $@).log; false)
+$(LIB): $(LIB_SRC) $(LIB_HDR) Makefile
+	$(NVCC) $(NVCCFLAGS) -shared $(LIB_SRC) -o $@ -ldl 2> build/ptxas_$(notdir $@).log || (cat build/ptxas_$(notdir $@).log; false)
 	@grep -E "registers|spill" build/ptxas_$(notdir $@).log | sort | uniq -c | sort -rn | head -20 || true
 
 $(ORACLE): oracle/pire_oracle.c oracle/pire_oracle.h

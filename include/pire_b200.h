@@ -223,6 +223,44 @@ int pire_gpu_run_batch_host(const pire_gpu_scanner* sc,
                             uint64_t fixed_len, uint64_t n, uint32_t flags,
                             uint32_t* match_bits, uint32_t* accept_masks, uint32_t* state_idx);
 
+/* ---- several GPUs of one box ---------------------------------------------------
+ * The path shards by string: rank r of `world` scans the contiguous shard
+ * pire_gpu_shard_bounds(n_global, world, r) -- boundaries on multiples of 32 strings, so bitmap words never straddle
+ * ranks -- straight into its slot of the full-length match bitmap, and one in-place ncclAllGather of the equal-sized
+ * slots completes the bitmap on every rank (1/world of the bytes of an all-reduce of a zeroed bitmap and no zeroing;
+ * the shards are disjoint and word aligned, so the result is the same OR).  The reference's callers are C++
+ * (tools/bench/bench.cpp:241-254, samples/pigrep/pigrep.cpp:38-45): this is their multi-GPU entry, no Python or
+ * PyTorch involved.  NCCL is bound at run time (libnccl.so.2 of the process, else the system's); single-GPU users carry
+ * no NCCL dependency, and these calls return PIRE_GPU_EUNSUPPORTED where NCCL is absent.
+ *
+ * One communicator per rank (process or thread; one GPU each):
+ *   rank 0: pire_gpu_comm_get_id(id)  -> ship the PIRE_GPU_COMM_ID_BYTES bytes to every rank by any means
+ *   every rank: pire_gpu_comm_create(id, world, rank, device, &comm)      (collective, like ncclCommInitRank)
+ *   or pire_gpu_comm_adopt(ncclComm_t, device, &comm) around a communicator the caller already owns.
+ * pire_gpu_run_sharded: d_corpus / d_offsets / d_accept_masks / d_state_idx describe THIS RANK's shard only (string
+ *   0 of the buffers is string lo of the batch); d_match_bits_all has pire_gpu_sharded_words(n_global, world) words
+ *   (>= ceil(n_global / 32); bits past n_global are zero) and is identical on every rank afterwards.  The scan runs
+ *   on `stream`, the exchange on the communicator's own stream behind it.  Default: `stream` then waits for the
+ *   exchange (stream-ordered, like any other call).  With PIRE_GPU_RUN_ASYNC_EXCHANGE the exchange is left running so
+ *   that the caller's next work on `stream` (the next batch's scan into ANOTHER bitmap buffer) overlaps it;
+ *   pire_gpu_comm_wait(comm, stream) makes `stream` wait for the last exchange before the bitmap is read.
+ *   A later run_sharded on the same communicator orders itself after the pending exchange. */
+#define PIRE_GPU_COMM_ID_BYTES 128
+#define PIRE_GPU_RUN_ASYNC_EXCHANGE 8u
+typedef struct pire_gpu_comm pire_gpu_comm;
+void     pire_gpu_shard_bounds(uint64_t n_global, int world, int rank, uint64_t* lo, uint64_t* hi);
+uint64_t pire_gpu_sharded_words(uint64_t n_global, int world);
+int  pire_gpu_comm_get_id(void* id_out);
+int  pire_gpu_comm_create(const void* id, int world, int rank, int device, pire_gpu_comm** out);
+int  pire_gpu_comm_adopt(void* nccl_comm, int device, pire_gpu_comm** out);
+void pire_gpu_comm_destroy(pire_gpu_comm* comm);
+int  pire_gpu_comm_info(const pire_gpu_comm* comm, int* world, int* rank);
+int  pire_gpu_comm_wait(pire_gpu_comm* comm, void* stream);
+int  pire_gpu_run_sharded(const pire_gpu_scanner* sc, pire_gpu_comm* comm,
+                          const uint8_t* d_corpus, const uint64_t* d_offsets, uint64_t fixed_len,
+                          uint64_t n_global, uint32_t flags,
+                          uint32_t* d_match_bits_all, uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream);
+
 /* Re-selects the shared-memory hot rows from the states a device-resident
  * sample of the workload actually visits (the reference has no counterpart; it
  * relies on the CPU cache to keep hot rows close).  Only speed depends on it.

@@ -31,6 +31,8 @@ SYMBOLS = [
     "pire_gpu_synth_mixed_lengths_host", "pire_gpu_synth_mixed_fill_device", "pire_gpu_synth_mixed_fill_host",
     "pire_gpu_last_error", "pire_gpu_version",
     "pire_gpu_accept_words", "pire_gpu_accept_sets", "pire_gpu_synth_fill_host_indexed",
+    "pire_gpu_shard_bounds", "pire_gpu_sharded_words", "pire_gpu_comm_get_id", "pire_gpu_comm_create",
+    "pire_gpu_comm_adopt", "pire_gpu_comm_destroy", "pire_gpu_comm_info", "pire_gpu_comm_wait", "pire_gpu_run_sharded",
 ]
 
 
@@ -93,6 +95,18 @@ def _load():
     lib.pire_gpu_accept_words.restype = C.c_uint32
     lib.pire_gpu_accept_sets.argtypes = [vp, vp, C.c_uint64, vp, vp]
     lib.pire_gpu_synth_fill_host_indexed.argtypes = [C.POINTER(Synth), vp, vp, C.c_uint64]
+    lib.pire_gpu_shard_bounds.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.pire_gpu_shard_bounds.restype = None
+    lib.pire_gpu_sharded_words.argtypes = [C.c_uint64, C.c_int]
+    lib.pire_gpu_sharded_words.restype = C.c_uint64
+    lib.pire_gpu_comm_get_id.argtypes = [vp]
+    lib.pire_gpu_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pire_gpu_comm_adopt.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    lib.pire_gpu_comm_destroy.argtypes = [vp]
+    lib.pire_gpu_comm_destroy.restype = None
+    lib.pire_gpu_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pire_gpu_comm_wait.argtypes = [vp, vp]
+    lib.pire_gpu_run_sharded.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp, vp]
     return lib
 
 
