@@ -256,6 +256,9 @@ int  pire_gpu_comm_adopt(void* nccl_comm, int device, pire_gpu_comm** out);
 void pire_gpu_comm_destroy(pire_gpu_comm* comm);
 int  pire_gpu_comm_info(const pire_gpu_comm* comm, int* world, int* rank);
 int  pire_gpu_comm_wait(pire_gpu_comm* comm, void* stream);
+/* the exchange alone, for a slot filled some other way (e.g. uploaded after pire_gpu_run_batch_host); flags: 0 or
+ * PIRE_GPU_RUN_ASYNC_EXCHANGE */
+int  pire_gpu_comm_gather_bits(pire_gpu_comm* comm, uint64_t n_global, uint32_t* d_match_bits_all, uint32_t flags, void* stream);
 int  pire_gpu_run_sharded(const pire_gpu_scanner* sc, pire_gpu_comm* comm,
                           const uint8_t* d_corpus, const uint64_t* d_offsets, uint64_t fixed_len,
                           uint64_t n_global, uint32_t flags,

@@ -14,6 +14,8 @@ u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
 
+RUN_ASYNC_EXCHANGE = 8
+COMM_ID_BYTES = 128
 RUN_BEGIN = 1
 RUN_END = 2
 RUN_LINES = 4
@@ -32,7 +34,7 @@ SYMBOLS = [
     "pire_gpu_last_error", "pire_gpu_version",
     "pire_gpu_accept_words", "pire_gpu_accept_sets", "pire_gpu_synth_fill_host_indexed",
     "pire_gpu_shard_bounds", "pire_gpu_sharded_words", "pire_gpu_comm_get_id", "pire_gpu_comm_create",
-    "pire_gpu_comm_adopt", "pire_gpu_comm_destroy", "pire_gpu_comm_info", "pire_gpu_comm_wait", "pire_gpu_run_sharded",
+    "pire_gpu_comm_adopt", "pire_gpu_comm_destroy", "pire_gpu_comm_info", "pire_gpu_comm_wait", "pire_gpu_run_sharded", "pire_gpu_comm_gather_bits",
 ]
 
 
@@ -106,6 +108,7 @@ def _load():
     lib.pire_gpu_comm_destroy.restype = None
     lib.pire_gpu_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pire_gpu_comm_wait.argtypes = [vp, vp]
+    lib.pire_gpu_comm_gather_bits.argtypes = [vp, C.c_uint64, vp, C.c_uint32, vp]
     lib.pire_gpu_run_sharded.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp, vp, vp]
     return lib
 

@@ -231,6 +231,28 @@ int pire_gpu_comm_wait(pire_gpu_comm* c, void* stream)
     return PIRE_GPU_OK;
 }
 
+// The exchange alone: this rank's slot of d_match_bits_all has been written on `stream` (by whatever means, e.g.
+// uploaded after pire_gpu_run_batch_host); gather every rank's slot.
+int pire_gpu_comm_gather_bits(pire_gpu_comm* c, uint64_t n_global, uint32_t* d_match_bits_all, uint32_t flags, void* stream)
+{
+    if (!c || !d_match_bits_all)
+        return Fail(PIRE_GPU_EINVAL, "null communicator or bitmap");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->world <= 1)
+        return PIRE_GPU_OK;
+    const uint64_t words_per = pire_gpu_sharded_words(n_global, c->world) / (uint64_t) c->world;
+    uint32_t* slot = d_match_bits_all + (size_t) c->rank * words_per;
+    CUDA_TRY(cudaEventRecord(c->scanned, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->scanned, 0));
+    NCCL_TRY(Nccl().AllGather(slot, d_match_bits_all, (size_t) words_per, ncclUint32, c->comm, c->stream));
+    CUDA_TRY(cudaEventRecord(c->exchanged, c->stream));
+    c->pending = true;
+    if (!(flags & PIRE_GPU_RUN_ASYNC_EXCHANGE))
+        CUDA_TRY(cudaStreamWaitEvent(st, c->exchanged, 0));
+    return PIRE_GPU_OK;
+}
+
 int pire_gpu_run_sharded(const pire_gpu_scanner* sc, pire_gpu_comm* c, const uint8_t* d_corpus, const uint64_t* d_offsets,
                          uint64_t fixed_len, uint64_t n_global, uint32_t flags, uint32_t* d_match_bits_all,
                          uint32_t* d_accept_masks, uint32_t* d_state_idx, void* stream)

@@ -601,32 +601,26 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
         SetFull(t, s, a.start);
 
         if (len != 0) {
-            // The scheduler sinks the 32-byte loads towards their first use to save registers (seen in SASS: a dozen
-            // steps ahead instead of thirty-two), which would expose most of a DRAM round trip per block.  So HBM
-            // latency is covered one level up: every 128 bytes a lane prefetches the line 512 bytes ahead into L2
-            // (no destination registers -- nothing to sink), and the loads themselves only have to cover an L2 hit.
             uint4 a0, a1, b0, b1;
-            if (len > 128)
-                PrefetchL2(p + 128);
-            if (len > 256)
-                PrefetchL2(p + 256);
-            if (len > 384)
-                PrefetchL2(p + 384);
-            LoadStream32P(p, a0, a1);
+            LoadStream32(p, a0, a1);
             for (uint32_t off = 0;;) {
-                if ((off & 64) == 0 && off + 512 < len)
-                    PrefetchL2(p + off + 512);
                 off += 32;
                 const bool more_b = off < len;
                 if (more_b)
-                    LoadStream32P(p + off, b0, b1);
+                    LoadStream32(p + off, b0, b1);
+                __syncwarp();          // see below
                 LookBlock32<k64>(t, s, a0, a1, b0.x, more_b, f);
                 if (!more_b)
                     break;
                 off += 32;
                 const bool more_a = off < len;
                 if (more_a)
-                    LoadStream32P(p + off, a0, a1);
+                    LoadStream32(p + off, a0, a1);
+                // The warp barrier pins the load HERE.  Left alone, the scheduler sinks the LDG.256 towards its first
+                // use to lend its eight destination registers to the steps in between (SASS: issued 7 steps before
+                // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
+                // stall samples were long-scoreboard waits on the first use of the loaded word).
+                __syncwarp();
                 LookBlock32<k64>(t, s, b0, b1, a0.x, more_a, f);
                 // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                 if (!more_a || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
