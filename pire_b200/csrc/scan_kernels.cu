@@ -521,12 +521,13 @@ __device__ __forceinline__ uint32_t SmemWindowBase()
 // Thirty-two bytes (one LDG.256 per lane).  next0 = the word that follows the block (ignored when !more: the last
 // byte of a string is filtered alone).  A lane that left the hot rows reads the sink row from then on; one test
 // per block finds it and replays both 16-byte chunks through the complete table.
+// Lane state in two registers: g (hot id, H = outside the hot rows) and prev = the complete state the lane had when
+// the block began (its cold state while g == H, else g itself) -- exactly what a replay starts from.
 template <bool k64>
-__device__ __forceinline__ void LookBlock32(const Tables& t, LaneState& s, const uint4& v0, const uint4& v1, uint32_t next0, bool more,
-                                            const LookFilter& f)
+__device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32_t& prev, const uint4& v0, const uint4& v1,
+                                            uint32_t next0, bool more, const LookFilter& f)
 {
-    const uint32_t before = s.g;
-    uint32_t g = s.g;
+    prev = g == t.H ? prev : g;
     uint32_t bb, pa, bn, pn;
     LookProbe<k64, 0>(v0.x, t.base, f, bb, pa);
     LookProbe<k64, 0>(v0.y, t.base, f, bn, pn);
@@ -550,12 +551,11 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, LaneState& s, const
     asm volatile("mov.b32 %0, %1;" : "=r"(late) : "r"(next0));
     LookProbe<k64, 0>(late, t.base, f, bb, pa);
     LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
-    s.g = g;
     if (g == t.H) {
-        uint32_t full = before == t.H ? s.cold : before;
-        full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), full, v0);
+        uint32_t full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), prev, v0);
         full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), full, v1);
-        SetFull(t, s, full);
+        prev = full;
+        g = full < t.H ? full : t.H;
     }
 }
 
@@ -586,48 +586,54 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
     f.lo = k64 ? (uint32_t) a.look_bitmap64 : a.look_bitmap;
     f.hi = (uint32_t) (a.look_bitmap64 >> 32);
 
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t units = (uint32_t) ((a.n + 31) / 32);            // pire_gpu_run_batch keeps n <= 2^40 / 32 units below 2^32
+    const uint32_t units = (uint32_t) ((a.n + 31) / 32);            // pire_gpu_run_batch keeps n <= 2^40: units below 2^32
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t warps = gridDim.x * warps_per_block;
     const uint32_t len = (uint32_t) a.fixed_len;
+    const uint32_t blocks = len >> 5;                               // 32-byte blocks per string (uniform)
 
     for (uint32_t unit = blockIdx.x * warps_per_block + (threadIdx.x >> 5); unit < units; unit += warps) {
-        const uint64_t i = (uint64_t) unit * 32 + lane;
-        const bool valid = i < a.n;
-        const uint8_t* p = a.corpus + (valid ? i : a.n - 1) * (uint64_t) len;
-
-        LaneState s;
-        SetFull(t, s, a.start);
-
-        if (len != 0) {
-            uint4 a0, a1, b0, b1;
-            LoadStream32(p, a0, a1);
-            for (uint32_t off = 0;;) {
-                off += 32;
-                const bool more_b = off < len;
-                if (more_b)
-                    LoadStream32(p + off, b0, b1);
-                __syncwarp();          // see below
-                LookBlock32<k64>(t, s, a0, a1, b0.x, more_b, f);
-                if (!more_b)
-                    break;
-                off += 32;
-                const bool more_a = off < len;
-                if (more_a)
-                    LoadStream32(p + off, a0, a1);
-                // The warp barrier pins the load HERE.  Left alone, the scheduler sinks the LDG.256 towards its first
-                // use to lend its eight destination registers to the steps in between (SASS: issued 7 steps before
-                // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
-                // stall samples were long-scoreboard waits on the first use of the loaded word).
-                __syncwarp();
-                LookBlock32<k64>(t, s, b0, b1, a0.x, more_a, f);
-                // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
-                if (!more_a || __all_sync(0xffffffffu, sv.noexit[s.g] != 0))
-                    break;
+        uint32_t g, prev;
+        {
+            const uint64_t i = (uint64_t) unit * 32 + (threadIdx.x & 31);
+            const uint8_t* p = a.corpus + (i < a.n ? i : a.n - 1) * (uint64_t) len;
+            prev = a.start;
+            g = a.start < t.H ? a.start : t.H;
+            if (blocks != 0) {
+                uint4 a0, a1, b0, b1;
+                LoadStream32(p, a0, a1);
+                for (uint32_t left = blocks;;) {
+                    // `left` counts the blocks not yet walked, the one in the a-set included
+                    const bool more_b = left > 1;
+                    p += 32;
+                    if (more_b)
+                        LoadStream32(p, b0, b1);
+                    __syncwarp();          // see below
+                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f);
+                    if (!more_b)
+                        break;
+                    const bool more_a = left > 2;
+                    p += 32;
+                    if (more_a)
+                        LoadStream32(p, a0, a1);
+                    // The warp barrier pins the load HERE.  Left alone, the scheduler sinks the LDG.256 towards its first
+                    // use to lend its eight destination registers to the steps in between (SASS: issued 7 steps before
+                    // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
+                    // stall samples were long-scoreboard waits on the first use of the loaded word).
+                    __syncwarp();
+                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f);
+                    left -= 2;
+                    // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
+                    if (!more_a || __all_sync(0xffffffffu, sv.noexit[g] != 0))
+                        break;
+                }
             }
         }
-        Report(a, t, s, unit, i, valid);
+        const uint64_t i = (uint64_t) unit * 32 + (threadIdx.x & 31);
+        LaneState s;
+        s.g = t.H;              // Report reads the complete state
+        s.cold = g == t.H ? prev : g;
+        Report(a, t, s, unit, i, i < a.n);
     }
 }
 
