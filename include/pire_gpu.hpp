@@ -62,12 +62,13 @@ public:
     typedef uint32_t Action;
     typedef unsigned short Char;     // Pire::Char, pire/defs.h:59
 
-    Scanner() : Handle(nullptr) {}
+    Scanner() : Handle(nullptr), AcceptBegin(1, 0) {}
 
     // From a Scanner::Save() stream (multi.h:557-573).  device = -1: host only.
     Scanner(const void* image, size_t size, int device = 0) : Handle(nullptr)
     {
         Check(pire_gpu_scanner_create(image, size, device, &Handle), "pire_gpu_scanner_create");
+        BuildAcceptCache();
     }
 
     // From any Pire scanner type whose Save() writes the multi-Scanner format
@@ -79,16 +80,23 @@ public:
         sc.Save(&out);
         const std::string image = out.str();
         Check(pire_gpu_scanner_create(image.data(), image.size(), device, &Handle), "pire_gpu_scanner_create");
+        BuildAcceptCache();
     }
 
-    Scanner(Scanner&& o) noexcept : Handle(o.Handle), AcceptCache(std::move(o.AcceptCache)) { o.Handle = nullptr; }
+    Scanner(Scanner&& o) noexcept : Handle(o.Handle), AcceptBegin(std::move(o.AcceptBegin)), AcceptIds(std::move(o.AcceptIds))
+    {
+        o.Handle = nullptr;
+        o.AcceptBegin.assign(1, 0);
+    }
     Scanner& operator=(Scanner&& o) noexcept
     {
         if (this != &o) {
             pire_gpu_scanner_destroy(Handle);
             Handle = o.Handle;
-            AcceptCache = std::move(o.AcceptCache);
+            AcceptBegin = std::move(o.AcceptBegin);
+            AcceptIds = std::move(o.AcceptIds);
             o.Handle = nullptr;
+            o.AcceptBegin.assign(1, 0);
         }
         return *this;
     }
@@ -108,26 +116,13 @@ public:
     bool Dead(const State& st) const { return pire_gpu_dead(Handle, st) != 0; }               // multi.h:147
     size_t StateIndex(State st) const { return st; }                                          // multi.h:281-284
 
-    // multi.h:149-158.  The returned range stays valid for the scanner's lifetime.
+    // multi.h:149-158.  The returned range stays valid for the scanner's lifetime.  The lists are built once in the
+    // constructor, so this is a pure read: like a const Pire::Scanner, one object may be shared between threads.
     std::pair<const size_t*, const size_t*> AcceptedRegexps(const State& st) const
     {
-        if (AcceptCache.size() <= st)
-            AcceptCache.resize((size_t) st + 1);
-        std::vector<size_t>& slot = AcceptCache[st];
-        if (slot.empty()) {
-            uint32_t ids[64];
-            size_t k = pire_gpu_accepted_regexps(Handle, st, ids, 64);
-            std::vector<uint32_t> big;
-            const uint32_t* src = ids;
-            if (k > 64) {
-                big.resize(k);
-                pire_gpu_accepted_regexps(Handle, st, big.data(), k);
-                src = big.data();
-            }
-            slot.assign(src, src + k);
-            slot.push_back(static_cast<size_t>(-1));     // keep a terminator like m_final does
-        }
-        return std::make_pair(slot.data(), slot.data() + slot.size() - 1);
+        if (st >= AcceptBegin.size() - 1)
+            return std::make_pair(AcceptIds.data(), AcceptIds.data());
+        return std::make_pair(AcceptIds.data() + AcceptBegin[st], AcceptIds.data() + AcceptBegin[st + 1] - 1);
     }
 
     // ---- device ----------------------------------------------------------------
@@ -147,8 +142,29 @@ public:
     pire_gpu_scanner* Raw() const { return Handle; }
 
 private:
+    // every state's accept list, each followed by a terminator like m_final's (multi.h:96)
+    void BuildAcceptCache()
+    {
+        const size_t states = Info().states;
+        AcceptBegin.assign(states + 1, 0);
+        AcceptIds.clear();
+        std::vector<uint32_t> ids(64);
+        for (size_t st = 0; st < states; ++st) {
+            AcceptBegin[st] = AcceptIds.size();
+            size_t k = pire_gpu_accepted_regexps(Handle, (uint32_t) st, ids.data(), ids.size());
+            if (k > ids.size()) {
+                ids.resize(k);
+                k = pire_gpu_accepted_regexps(Handle, (uint32_t) st, ids.data(), ids.size());
+            }
+            AcceptIds.insert(AcceptIds.end(), ids.begin(), ids.begin() + k);
+            AcceptIds.push_back(static_cast<size_t>(-1));
+        }
+        AcceptBegin[states] = AcceptIds.size();
+    }
+
     pire_gpu_scanner* Handle;
-    mutable std::vector<std::vector<size_t>> AcceptCache;
+    std::vector<size_t> AcceptBegin;      // [states + 1] into AcceptIds
+    std::vector<size_t> AcceptIds;
 };
 
 // Counterpart of Pire::RunHelper (run.h:365-386) for a device batch.  Results are
@@ -180,6 +196,56 @@ private:
 };
 
 inline BatchRunner Runner(const Scanner& sc) { return BatchRunner(sc); }     // run.h:388-389
+
+// AcceptedRegexps for scanners with more than 32 regexps: rows of AcceptWords(sc) words, bit r of row i set iff
+// regexp r is accepted by the state string i stopped in (d_state_idx from BatchRunner::Launch).
+inline uint32_t AcceptWords(const Scanner& sc) { return pire_gpu_accept_words(sc.Raw()); }
+inline void AcceptSets(const Scanner& sc, const uint32_t* d_state_idx, uint64_t n, uint32_t* d_sets, void* stream = nullptr)
+{
+    Check(pire_gpu_accept_sets(sc.Raw(), d_state_idx, n, d_sets, stream), "pire_gpu_accept_sets");
+}
+
+// One rank of a multi-GPU run (one GPU per process or thread): the communicator of pire_gpu_run_sharded.
+//     rank 0:  unsigned char id[PIRE_GPU_COMM_ID_BYTES]; Comm::MakeId(id);  ... ship id to every rank ...
+//     all:     Comm comm(id, world, rank, device);
+//              comm.RunSharded(gsc, shard, n_global, flags, d_bits_all, d_masks, nullptr, stream);
+class Comm {
+public:
+    static void MakeId(void* id) { Check(pire_gpu_comm_get_id(id), "pire_gpu_comm_get_id"); }
+    Comm(const void* id, int world, int rank, int device) : Handle(nullptr)
+    {
+        Check(pire_gpu_comm_create(id, world, rank, device, &Handle), "pire_gpu_comm_create");
+    }
+    // around an ncclComm_t the caller owns (not destroyed here)
+    Comm(void* ncclComm, int device) : Handle(nullptr) { Check(pire_gpu_comm_adopt(ncclComm, device, &Handle), "pire_gpu_comm_adopt"); }
+    Comm(const Comm&) = delete;
+    Comm& operator=(const Comm&) = delete;
+    ~Comm() { pire_gpu_comm_destroy(Handle); }
+
+    int World() const { int w = 1; pire_gpu_comm_info(Handle, &w, nullptr); return w; }
+    int Rank() const { int r = 0; pire_gpu_comm_info(Handle, nullptr, &r); return r; }
+    // [lo, hi) of this rank's shard and the words of the gathered bitmap
+    std::pair<uint64_t, uint64_t> Bounds(uint64_t n_global) const
+    {
+        uint64_t lo = 0, hi = 0;
+        pire_gpu_shard_bounds(n_global, World(), Rank(), &lo, &hi);
+        return std::make_pair(lo, hi);
+    }
+    uint64_t Words(uint64_t n_global) const { return pire_gpu_sharded_words(n_global, World()); }
+
+    // `shard` describes this rank's strings only (Count is ignored: the shard is Bounds(n_global)).
+    void RunSharded(const Scanner& sc, const Batch& shard, uint64_t n_global, unsigned flags, uint32_t* d_match_bits_all,
+                    uint32_t* d_accept_masks = nullptr, uint32_t* d_state_idx = nullptr, void* stream = nullptr)
+    {
+        Check(pire_gpu_run_sharded(sc.Raw(), Handle, shard.Corpus, shard.Offsets, shard.FixedLen, n_global, flags, d_match_bits_all,
+                                   d_accept_masks, d_state_idx, stream), "pire_gpu_run_sharded");
+    }
+    void Wait(void* stream = nullptr) { Check(pire_gpu_comm_wait(Handle, stream), "pire_gpu_comm_wait"); }
+    pire_gpu_comm* Raw() const { return Handle; }
+
+private:
+    pire_gpu_comm* Handle;
+};
 
 // Batch counterparts of Pire::LongestPrefix / Pire::ShortestPrefix (run.h:277-311): one prefix
 // length per string into d_prefix_len (PIRE_GPU_NO_PREFIX where the reference returns null).

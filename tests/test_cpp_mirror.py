@@ -26,3 +26,26 @@ def test_reference_templates_run_on_gpu_scanner(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "0 mismatches" in out.stdout
+
+
+@pytest.mark.gpu
+def test_sharded_entry_from_cpp(tmp_path, cuda_device):
+    """The multi-GPU entry of the C ABI from plain C++ (no Python in the data path): tests/cpp/sharded_check.cpp through
+    include/pire_gpu.hpp's Comm, one rank per visible GPU up to two; the gathered bitmap must equal a single-GPU run."""
+    import shutil
+    import torch
+    from pire_b200 import workloads as W
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not present")
+    exe = str(tmp_path / "sharded_check")
+    lib_dir = os.path.join(ROOT, "pire_b200")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "sharded_check.cpp"),
+                    os.path.join(lib_dir, "libpire_b200.so"), "-o", exe, "-Xlinker", "-rpath=" + lib_dir], check=True)
+    image = tmp_path / "glue10.pire"
+    image.write_bytes(W.load_image("glue10"))
+    for world in sorted({1, min(2, torch.cuda.device_count())}):
+        for n in (100_000, 70):                        # 70 strings: rank 1 of 2 holds 6, the slack words must be zero
+            out = subprocess.run([exe, str(image), str(n), str(world)], capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, out.stdout + out.stderr
+            assert ": 0 mismatches" in out.stdout

@@ -21,3 +21,5 @@ for regs in 40 48; do
 PIRE_B200_LOOK_REGS=$regs timeout 900 ncu --set full --clock-control none --import-source on -k regex:ScanUniformLook -s 3 -c 1 -f -o $OUT/r2_prof_glue10_look_r$regs \
     python bench.py --strings 2000000 --steps 2 --warmup 1 --no-e2e --no-cpu --no-parity --no-configs --no-next --variant look > $OUT/r2_ncu_look.log 2>&1
 done
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/r2_pytest_gpu_full.log 2>&1; echo "pytest exit $?" >> $OUT/r2_pytest_gpu_full.log; tail -4 $OUT/r2_pytest_gpu_full.log
+timeout 900 python bench.py > $OUT/r2_bench_default.json 2> $OUT/r2_bench_default.err; echo "bench exit $?"; head -c 6000 $OUT/r2_bench_default.json; tail -5 $OUT/r2_bench_default.err
