@@ -525,7 +525,7 @@ __device__ __forceinline__ uint32_t SmemWindowBase()
 // the block began (its cold state while g == H, else g itself) -- exactly what a replay starts from.
 template <bool k64>
 __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32_t& prev, const uint4& v0, const uint4& v1,
-                                            uint32_t next0, bool more, const LookFilter& f)
+                                            uint32_t next0, bool more, const LookFilter& f, uint32_t opaque_zero)
 {
     prev = g == t.H ? prev : g;
     uint32_t bb, pa, bn, pn;
@@ -546,9 +546,10 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     LookWord<k64>(g, v1.z, bb, pa, pn, t.base, f);
     // The word after the block was requested from HBM when this block began: its probe must stay down here (an
     // ordinary intrinsic is hoisted to the top of the block by the compiler, where it waits for the whole DRAM
-    // latency -- ncu: 10 % of all stall samples on that one IDP).  asm volatile keeps it behind the steps above.
-    uint32_t late;
-    asm volatile("mov.b32 %0, %1;" : "=r"(late) : "r"(next0));
+    // latency -- ncu: 10 % of all stall samples on that one IDP).
+    // (a volatile mov is not enough: ptxas schedules across it.  The word is made to depend on the walk itself --
+    // plus g times a kernel argument that is always zero -- which costs one IMAD per block.)
+    const uint32_t late = next0 + g * opaque_zero;
     LookProbe<k64, 0>(late, t.base, f, bb, pa);
     LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     if (g == t.H) {
@@ -609,7 +610,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     if (more_b)
                         LoadStream32(p, b0, b1);
                     __syncwarp();          // see below
-                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f);
+                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero);
                     if (!more_b)
                         break;
                     const bool more_a = left > 2;
@@ -621,7 +622,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
                     // stall samples were long-scoreboard waits on the first use of the loaded word).
                     __syncwarp();
-                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f);
+                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero);
                     left -= 2;
                     // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                     if (!more_a || __all_sync(0xffffffffu, sv.noexit[g] != 0))

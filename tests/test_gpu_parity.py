@@ -706,3 +706,152 @@ def test_suffix_scans_vs_reference(cuda_device, ref):
     for shortest in (False, True):
         got = (P.ShortestSuffix if shortest else P.LongestSuffix)(sc, batch)
         assert (got == sc_ref.suffix(host, fixed_len=72, n=5000, shortest=shortest, variant=2)).all()
+
+
+def test_longest_prefix_vs_default_scanner_enumerated(cuda_device, ref):
+    """run.h:277-292 through the default Scanner's skip loop (multi.h:966-989): the ExitMasks fast-forward does not
+    call the predicate over the 16-byte words it jumps, so LongestPrefix comes out SHORT exactly when the string ends
+    on a 16-byte boundary of the host address space after at least one whole aligned word walked in a final state
+    with at most two exit bytes -- it then reports only the unaligned head.  The device (like the NoMask scanners)
+    has no such artefact.  This test pins WHERE the two reference scanners differ, for every start alignment and
+    length, and that the device agrees with the byte-by-byte answer everywhere."""
+    import pire_b200 as P
+
+    def aligned(nbytes):
+        raw = np.zeros(nbytes + 64, np.uint8)
+        off = (-raw.ctypes.data) % 64
+        return raw[off:off + nbytes]
+
+    cases = [(rb"[^x]*", b"a", True), (rb"a*b?", b"a", False), (rb"(ab)*", b"ab", False), (rb"[a-c]+x?", b"abc", False)]
+    for pat, fill, has_artefact in cases:
+        sc_ref = ref.compile(pat, "n")
+        sc = P.Scanner(sc_ref.save(), cuda_device)
+        strings, shifts = [], []
+        differing = set()
+        for shift in range(16):
+            for ln in range(0, 70):
+                buf = aligned(256)
+                buf[:] = ord("z")
+                text = (fill * 100)[:ln]
+                if ln:
+                    buf[shift:shift + ln] = np.frombuffer(text, np.uint8)
+                offs = np.array([shift, shift + ln], np.uint64)
+                default = int(sc_ref.prefix(buf, offs, variant=0)[0])
+                nomask = int(sc_ref.prefix(buf, offs, variant=2)[0])
+                if default != nomask:
+                    differing.add((shift, ln))
+                    head = (-shift) % 16
+                    assert default == (head if head else 0) and default < nomask      # only the unaligned head is seen
+                strings.append(text)
+                shifts.append((shift, ln, nomask))
+        predicted = set()
+        for shift in range(16):
+            for ln in range(0, 70):
+                end, first = shift + ln, (shift + 15) // 16 * 16
+                if has_artefact and end % 16 == 0 and end >= first + 16:
+                    predicted.add((shift, ln))
+        assert differing == predicted, (pat, sorted(differing ^ predicted)[:8])
+        # the device: every string at every device alignment (CSR, back to back) equals the byte-by-byte reference
+        got = P.LongestPrefix(sc, P.Batch.from_strings(strings))
+        assert got.tolist() == [w for _, _, w in shifts], pat
+
+
+def test_accept_sets_beyond_32_regexps(cuda_device, ref):
+    """multi.h:149-158 returns accept lists of any length; the scan kernels' mask holds ids 0..31.  Forty end-anchored
+    literals glued into one scanner: every id, also 32..39, must come back through pire_gpu_accept_sets."""
+    import ctypes as C
+    import torch
+    import pire_b200 as P
+    from pire_b200 import _native as N
+    pats = [(("w%02d$" % k).encode(), "") for k in range(40)]
+    sc_ref = ref.glue_all(pats)
+    sc = P.Scanner(sc_ref.save(), cuda_device)
+    assert sc.RegexpsCount() == 40 and N.lib.pire_gpu_accept_words(sc._h) == 2
+    rng = np.random.default_rng(40)
+    n, length = 4096, 64
+    host = rng.integers(0x61, 0x7B, size=(n, length), dtype=np.uint8)
+    want_ids = []
+    for i in range(n):
+        if i % 3:
+            k = int(rng.integers(0, 40))
+            host[i, -3:] = np.frombuffer(b"w%02d" % k, np.uint8)
+            want_ids.append([k])
+        else:
+            host[i, -1] = ord("!")
+            want_ids.append([])
+    dev = torch.from_numpy(np.ascontiguousarray(host).reshape(-1)).to("cuda:0")
+    batch = P.Batch(dev, fixed_len=length, n=n)
+    for variant in (1, 2, 4, 5):
+        sc.set_variant(variant)
+        r = P.Runner(sc).Begin().Run(batch).End()
+        states = torch.from_numpy(r.States().astype(np.int32)).to("cuda:0")
+        sets = torch.zeros((n, 2), dtype=torch.int32, device="cuda:0")
+        N.check(N.lib.pire_gpu_accept_sets(sc._h, states.data_ptr(), n, sets.data_ptr(), None), "pire_gpu_accept_sets")
+        sets = sets.cpu().numpy().view(np.uint32)
+        masks = r.AcceptMasks()
+        for i in range(n):
+            ids = [k for k in range(40) if (int(sets[i, k // 32]) >> (k % 32)) & 1]
+            assert ids == want_ids[i], (variant, i, ids, want_ids[i])
+            assert int(masks[i]) == int(sets[i, 0])                              # the 32-bit mask is the first word
+            assert ids == sc.AcceptedRegexps(int(r.States()[i]))                 # and the host accessor agrees
+        assert (r.Matches() == np.array([bool(w) for w in want_ids])).all()
+    # a state index outside the scanner yields an empty set
+    bad = torch.tensor([sc.Size() + 5], dtype=torch.int32, device="cuda:0")
+    out = torch.full((1, 2), -1, dtype=torch.int32, device="cuda:0")
+    N.check(N.lib.pire_gpu_accept_sets(sc._h, bad.data_ptr(), 1, out.data_ptr(), None), "pire_gpu_accept_sets")
+    assert out.cpu().tolist() == [[0, 0]]
+
+
+def test_host_entry_streams_chunks(cuda_device, ref, monkeypatch):
+    """pire_gpu_run_batch_host with pageable buffers (numpy): chunks of 1 MiB force a dozen trips round the three-slot
+    ring for a fixed-length and a ragged CSR batch; two threads on one handle run concurrently; bad offsets are
+    refused.  Results equal the reference."""
+    import threading
+    import pire_b200 as P
+    from pire_b200 import _native as N
+    from pire_b200 import workloads as W
+    monkeypatch.setenv("PIRE_B200_HOST_CHUNK_MB", "1")
+    sc_ref = ref.glue_all(W.GLUE10)
+    sc = P.Scanner(W.load_image("glue10"), cuda_device)
+    n = 12 * 1024 + 37
+    spec = W.SynthSpec(n, 1024, plants=W.GLUE10_PLANTS)
+    host = spec.host_sample(0, n)                                  # pageable
+    f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=1024, n=n, threads=8)
+    bits, masks, states = sc.run_batch_host(host, fixed_len=1024, n=n, want_masks=True, want_states=True)
+    assert (np.unpackbits(bits.view(np.uint8), bitorder="little")[:n] == f_ref).all()
+    assert (masks == m_ref).all() and (states == s_ref).all()
+    # ragged CSR incl. empty strings, a string longer than a chunk, lengths not multiples of anything
+    rng = np.random.default_rng(8)
+    lens = np.concatenate([rng.integers(0, 3000, size=5000), [0, 0, 3 << 20, 1, 17]])
+    rng.shuffle(lens)
+    total = int(lens.sum())
+    corpus = rng.integers(0x20, 0x7F, size=total, dtype=np.uint8)
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    for k in range(0, len(lens), 7):                               # plant a few hits
+        if lens[k] >= 8:
+            corpus[int(offs[k + 1]) - 5:int(offs[k + 1])] = np.frombuffer(b"error", np.uint8)
+    f2, m2, s2 = sc_ref.run(corpus, offs, threads=8)
+    bits, masks, states = sc.run_batch_host(corpus, offsets=offs, want_masks=True, want_states=True)
+    assert (np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(lens)] == f2).all()
+    assert (masks == m2).all() and (states == s2).all()
+    assert int(f2.sum()) > 100
+    # two threads, one handle
+    results = [None, None]
+
+    def work(k):
+        results[k] = sc.run_batch_host(host, fixed_len=1024, n=n, want_masks=True)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for b, m, _ in results:
+        assert (np.unpackbits(b.view(np.uint8), bitorder="little")[:n] == f_ref).all() and (m == m_ref).all()
+    # refused: offsets that step back, offsets past the buffer, n * fixed_len past the buffer
+    bad = offs.copy()
+    bad[10], bad[11] = bad[11], bad[10]
+    with pytest.raises(P.PireGpuError):
+        sc.run_batch_host(corpus, offsets=bad)
+    with pytest.raises(P.PireGpuError):
+        sc.run_batch_host(corpus[: total // 2], offsets=offs)
+    with pytest.raises(P.PireGpuError):
+        sc.run_batch_host(host[:4096], fixed_len=1024, n=5)
