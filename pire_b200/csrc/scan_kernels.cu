@@ -257,7 +257,7 @@ __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t 
     // Entry of (id g, byte b) sits at base + g * kHotStride + b.  `bb` = base | b comes from one PRMT (the
     // base is 256-byte aligned, so its low byte is free) and does not depend on g: the dependent chain of a
     // step is IMAD (FMA pipe) -> LDS, as short as the PRMT -> LDS of an unpadded table.
-    const uint32_t bb = __byte_perm(w, t.base, 0x7650u | (sel & 3u));
+    const uint32_t bb = __dp4a(w, 1u << (8 * (sel & 3u)), t.base);      // IDP.4A: byte sel + base on the FMA pipe (PRMT: ALU pipe)
     if (kPred) {
         // bit (byte & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
         // Lanes resting in id 0 on a self-looping byte skip the load (fewer bank
