@@ -364,6 +364,7 @@ static int PrefixOrSuffix(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     a.end_class = reverse ? sc->tab.begin_class : sc->tab.end_class;
     a.prefix_len = d_len;
     a.first_final_hot = sc->tab.first_final_hot;
+    a.uniform = (!reverse && IsUniform(d_corpus, d_offsets, fixed_len) && !getenv("PIRE_B200_NO_UNIFORM_BODY")) ? 1 : 0;
     CUDA_TRY(LaunchPrefix(a, shortest != 0, reverse, sc->device, static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
 }
@@ -412,6 +413,7 @@ int pire_gpu_count_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, co
     a.weights = sc->dev.weights;
     a.count_words = sc->count_mode == 1 ? 0 : sc->tab.count_words;
     a.count_always = (sc->count_mode == 3 || (sc->count_mode == 0 && sc->final_share > 0.025)) ? 1 : 0;
+    a.uniform = (IsUniform(d_corpus, d_offsets, fixed_len) && !getenv("PIRE_B200_NO_UNIFORM_BODY")) ? 1 : 0;
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t) n * a.regexps * 4, st));
     CUDA_TRY(LaunchCount(a, sc->device, st));
     return PIRE_GPU_OK;

@@ -251,13 +251,16 @@ __device__ __forceinline__ void SetFull(const Tables& t, LaneState& s, uint32_t 
     }
 }
 
-template <bool kPred>
+template <bool kPred, bool kIdp = true>
 __device__ __forceinline__ void FastStep(const Tables& t, uint32_t& g, uint32_t w, uint32_t sel)
 {
     // Entry of (id g, byte b) sits at base + g * kHotStride + b.  `bb` = base | b comes from one PRMT (the
     // base is 256-byte aligned, so its low byte is free) and does not depend on g: the dependent chain of a
     // step is IMAD (FMA pipe) -> LDS, as short as the PRMT -> LDS of an unpadded table.
-    const uint32_t bb = __dp4a(w, 1u << (8 * (sel & 3u)), t.base);      // IDP.4A: byte sel + base on the FMA pipe (PRMT: ALU pipe)
+    // byte `sel` + base: IDP.4A on the FMA pipe (round 2: +0.6 % on the exit-filter scan, +1-2 % on the CSR and counting
+    // kernels, which are short of ALU slots), or PRMT on the ALU pipe for the prefix kernels, whose look-ahead pass keeps
+    // the FMA side busy (IDP there measured 17 % slower)
+    const uint32_t bb = kIdp ? __dp4a(w, 1u << (8 * (sel & 3u)), t.base) : __byte_perm(w, t.base, 0x7650u | (sel & 3u));
     if (kPred) {
         // bit (byte & 31) of the 32-slot exit bitmap: may this byte leave hot id 0?
         // Lanes resting in id 0 on a self-looping byte skip the load (fewer bank
@@ -523,9 +526,19 @@ __device__ __forceinline__ uint32_t SmemWindowBase()
 // per block finds it and replays both 16-byte chunks through the complete table.
 // Lane state in two registers: g (hot id, H = outside the hot rows) and prev = the complete state the lane had when
 // the block began (its cold state while g == H, else g itself) -- exactly what a replay starts from.
+// The replay of a whole 32-byte block for the LOOK kernels: out of line, and with every table pointer read from the
+// kernel's parameter block in here, so that the walk loop around the (rare) call carries no argument set-up.
+__device__ __noinline__ uint32_t ReplayBlock32(const ScanArgs* a, uint32_t from, uint4 v0, uint4 v1)
+{
+    const SharedView sv = CarveShared(pire_b200_smem, a->hot);
+    const uint32_t letters_wide = a->letters | (a->wide << 31);
+    const uint32_t mid = ReplayChunk(sv.hot, sv.cls, a->full, a->hot, letters_wide, from, v0);
+    return ReplayChunk(sv.hot, sv.cls, a->full, a->hot, letters_wide, mid, v1);
+}
+
 template <bool k64>
 __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32_t& prev, const uint4& v0, const uint4& v1,
-                                            uint32_t next0, bool more, const LookFilter& f, uint32_t opaque_zero)
+                                            uint32_t next0, bool more, const LookFilter& f, uint32_t opaque_zero, const ScanArgs* args)
 {
     prev = g == t.H ? prev : g;
     uint32_t bb, pa, bn, pn;
@@ -553,10 +566,8 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     LookProbe<k64, 0>(late, t.base, f, bb, pa);
     LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     if (g == t.H) {
-        uint32_t full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), prev, v0);
-        full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), full, v1);
-        prev = full;
-        g = full < t.H ? full : t.H;
+        prev = ReplayBlock32(args, prev, v0, v1);
+        g = prev < t.H ? prev : t.H;
     }
 }
 
@@ -610,7 +621,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     if (more_b)
                         LoadStream32(p, b0, b1);
                     __syncwarp();          // see below
-                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero);
+                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
                     if (!more_b)
                         break;
                     const bool more_a = left > 2;
@@ -622,7 +633,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
                     // stall samples were long-scoreboard waits on the first use of the loaded word).
                     __syncwarp();
-                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero);
+                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
                     left -= 2;
                     // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                     if (!more_a || __all_sync(0xffffffffu, sv.noexit[g] != 0))
@@ -1186,7 +1197,7 @@ __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t
         const uint32_t word = at == 0 ? v.x : at == 1 ? v.y : at == 2 ? v.z : v.w;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            FastStep<false>(t, g, word, 0x5540 + (kReverse ? 3 - b : b));
+            FastStep<false, false>(t, g, word, 0x5540 + (kReverse ? 3 - b : b));
             top = max(top, g);
         }
     }
@@ -1209,7 +1220,7 @@ __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t
             const uint32_t word = at == 0 ? v.x : at == 1 ? v.y : at == 2 ? v.z : v.w;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                FastStep<false>(t, h, word, 0x5540 + (kReverse ? 3 - b : b));
+                FastStep<false, false>(t, h, word, 0x5540 + (kReverse ? 3 - b : b));
                 const bool final = h >= a.first_final_hot;
                 if (kShortest)
                     mark = final && mark == 0 ? (uint32_t) (4 * w + b + 1) : mark;
@@ -1343,6 +1354,45 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
         }
         LaneState s;
         SetFull(t, s, full);
+        if (!kReverse && a.uniform) {
+            // Fixed-length, 32-byte aligned batch (the BASELINE configs' shape): no edge bytes, and the strings stream
+            // through registers like in the uniform scan kernel -- one LDG.256 per lane per 32 bytes, prefetched one
+            // block ahead -- instead of the cp.async ring, whose shared-memory round trip costs half a wavefront per
+            // step on the pipe that bounds the walk.
+            if (len != 0) {
+                uint4 a0, a1, b0, b1;
+                LoadStream32(first, a0, a1);
+                for (uint32_t off = 0;;) {
+                    off += 32;
+                    const bool more_b = off < len;
+                    if (more_b)
+                        LoadStream32(first + off, b0, b1);
+                    if (!l.stop)
+                        PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, a0, l);
+                    if (!l.stop)
+                        PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, a1, l);
+                    if (!more_b)
+                        break;
+                    off += 32;
+                    const bool more_a = off < len;
+                    if (more_a)
+                        LoadStream32(first + off, a0, a1);
+                    if (!l.stop)
+                        PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, b0, l);
+                    if (!l.stop)
+                        PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, b1, l);
+                    // a dead state only leads to dead states: stop the lane once it is noticed (every 64 bytes)
+                    if (!l.stop) {
+                        const uint32_t at = FullState(t, s);
+                        if ((at < t.H ? hot_flags[at] : __ldg(a.flags + at)) & 2u)
+                            l.stop = true;
+                    }
+                    if (!more_a || __all_sync(0xffffffffu, l.stop))
+                        break;
+                }
+            }
+            p = end;
+        }
         // body: whole 16-byte chunks; chunk c is at p + 16c (forward) or p - 16(c+1) (reverse)
         const uint32_t chunks = (uint32_t) ((kReverse ? p - first : end - p) >> 4);
 #pragma unroll
@@ -1666,6 +1716,33 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
         }
         LaneState s;
         SetFull(t, s, full);
+        if (a.uniform) {
+            // fixed-length, 32-byte aligned batch: LDG.256 ping-pong through registers, no staging ring (see PrefixKernel)
+            const uint32_t len = (uint32_t) (end - p);
+            if (len != 0) {
+                uint4 a0, a1, b0, b1;
+                LoadStream32(p, a0, a1);
+                for (uint32_t off = 0;;) {
+                    off += 32;
+                    const bool more_b = off < len;
+                    if (more_b)
+                        LoadStream32(p + off, b0, b1);
+                    CountChunk16<kWords, kAlways>(a, t, s, a0, c);
+                    CountChunk16<kWords, kAlways>(a, t, s, a1, c);
+                    if (!more_b)
+                        break;
+                    off += 32;
+                    const bool more_a = off < len;
+                    if (more_a)
+                        LoadStream32(p + off, a0, a1);
+                    CountChunk16<kWords, kAlways>(a, t, s, b0, c);
+                    CountChunk16<kWords, kAlways>(a, t, s, b1, c);
+                    if (!more_a)
+                        break;
+                }
+            }
+            p = end;
+        }
         const uint32_t chunks = (uint32_t) ((end - p) >> 4);
 #pragma unroll
         for (int j = 0; j < kStageSlots; ++j) {

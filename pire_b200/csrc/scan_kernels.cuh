@@ -36,6 +36,7 @@ struct ScanArgs {
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     uint32_t look_bitmap;        // LOOK variant: 32-slot look-ahead filter (dfa_tables.hpp), slot = byte & 31
     uint64_t look_bitmap64;      // LOOK64 variant: the same filter with 64 slots, slot = byte & 63
+    uint32_t uniform;            // prefix / count kernels: fixed length, a multiple of 32 bytes, corpus 32-byte aligned
     uint32_t opaque_zero;        // always 0; the LOOK kernels multiply by it to pin an instruction behind the walk
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
     uint32_t priv_rows;

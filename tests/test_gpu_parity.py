@@ -781,9 +781,12 @@ def test_accept_sets_beyond_32_regexps(cuda_device, ref):
             want_ids.append([])
     dev = torch.from_numpy(np.ascontiguousarray(host).reshape(-1)).to("cuda:0")
     batch = P.Batch(dev, fixed_len=length, n=n)
+    f_ref, m_ref, s_ref = sc_ref.run(np.ascontiguousarray(host).reshape(-1), fixed_len=length, n=n, begin=False, end=False)
+    assert [sc_ref.accepted(int(st)) for st in s_ref[:64]] == want_ids[:64]      # the reference agrees with the construction
     for variant in (1, 2, 4, 5):
         sc.set_variant(variant)
-        r = P.Runner(sc).Begin().Run(batch).End()
+        r = P.Runner(sc).Run(batch)              # patterns without Surround() do not consume the marks (run.h:396-400)
+        assert (r.States() == s_ref).all() and (r.AcceptMasks() == m_ref).all()
         states = torch.from_numpy(r.States().astype(np.int32)).to("cuda:0")
         sets = torch.zeros((n, 2), dtype=torch.int32, device="cuda:0")
         N.check(N.lib.pire_gpu_accept_sets(sc._h, states.data_ptr(), n, sets.data_ptr(), None), "pire_gpu_accept_sets")
@@ -855,3 +858,43 @@ def test_host_entry_streams_chunks(cuda_device, ref, monkeypatch):
         sc.run_batch_host(corpus[: total // 2], offsets=offs)
     with pytest.raises(P.PireGpuError):
         sc.run_batch_host(host[:4096], fixed_len=1024, n=5)
+
+
+@pytest.mark.parametrize("length", [32, 160, 1024])
+def test_uniform_bodies_of_prefix_and_count(length, cuda_device, ref, monkeypatch):
+    """Fixed-length, 32-byte aligned batches take the register-streaming bodies of PrefixKernel / CountKernel (no
+    staging ring).  Every mark combination, longest and shortest, a pattern with dead states, all counting modes:
+    equal to the reference and to the ring path on the same bytes."""
+    import torch
+    import pire_b200 as P
+    rng = np.random.default_rng(1000 + length)
+    n = 3000 + 11
+    host = rng.choice(np.frombuffer(b"abcx 01.", np.uint8), size=(n, length))
+    host[::5, : min(length, 24)] = np.frombuffer((b"ab" * 12)[: min(length, 24)], np.uint8)
+    host = np.ascontiguousarray(host).reshape(-1)
+    dev = torch.from_numpy(host).to("cuda:0")
+    batch = P.Batch(dev, fixed_len=length, n=n)
+    for pat, opts in [(b"(ab)*c?", "n"), (b"a+b", ""), (rb"[0-9]+\.[0-9]+", ""), (b"[^x]*", "n")]:
+        sc_ref = ref.compile(pat, opts)
+        sc = P.Scanner(sc_ref.save(), cuda_device)
+        for tb in (False, True):
+            for te in (False, True):
+                for shortest in (False, True):
+                    fn = P.ShortestPrefix if shortest else P.LongestPrefix
+                    want = sc_ref.prefix(host, fixed_len=length, n=n, shortest=shortest, through_begin=tb, through_end=te, variant=2)
+                    monkeypatch.delenv("PIRE_B200_NO_UNIFORM_BODY", raising=False)
+                    got = fn(sc, batch, throughBeginMark=tb, throughEndMark=te)
+                    monkeypatch.setenv("PIRE_B200_NO_UNIFORM_BODY", "1")
+                    ring = fn(sc, batch, throughBeginMark=tb, throughEndMark=te)
+                    assert (got == want).all() and (ring == want).all(), (pat, tb, te, shortest)
+    monkeypatch.delenv("PIRE_B200_NO_UNIFORM_BODY", raising=False)
+    for pat in (b"ab", b"[ab]+", b"a.*b|c"):
+        hf = ref.compile_half_final(pat, "n", 0)
+        sc = P.Scanner(hf.save(), cuda_device)
+        for begin in (True, False):
+            for end in (True, False):
+                want, wfin = hf.count(host, fixed_len=length, n=n, begin=begin, end=end)
+                for mode in (1, 2, 3):
+                    sc.set_count_mode(mode)
+                    res = P.HalfFinalCount(sc, batch, begin=begin, end=end)
+                    assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all(), (pat, begin, end, mode)
