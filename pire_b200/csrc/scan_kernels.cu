@@ -746,9 +746,38 @@ __device__ __forceinline__ uint4 LoadChunk16(const uint8_t* aligned, uintptr_t b
 // Generic batch: CSR offsets or arbitrary fixed length / alignment.  Head and
 // tail bytes (to 16-byte alignment) take the slow step, like run.h:186-226 does
 // with its word-aligned body.
-template <bool kPred>
+// The look-ahead filter of the LOOK variant (see LookStep) inside one 16-byte chunk of a CSR string: byte k reads the
+// table only if bytes k and k+1 both pass; the chunk's last byte is filtered alone, so the lane's state is exact at
+// every chunk boundary (edges, replays and the NoExit test see true states).
+__device__ __forceinline__ void Chunk16Look(const Tables& t, LaneState& s, uint4 v, const LookFilter& f)
+{
+    const uint32_t before = s.g;
+    uint32_t g = s.g;
+    uint32_t bb, pa, bn, pn;
+    LookProbe<false, 0>(v.x, t.base, f, bb, pa);
+    LookProbe<false, 0>(v.y, t.base, f, bn, pn);
+    LookWord<false>(g, v.x, bb, pa, pn, t.base, f);
+    LookProbe<false, 0>(v.z, t.base, f, bb, pa);
+    LookWord<false>(g, v.y, bn, pn, pa, t.base, f);
+    LookProbe<false, 0>(v.w, t.base, f, bn, pn);
+    LookWord<false>(g, v.z, bb, pa, pn, t.base, f);
+    LookWord<false>(g, v.w, bn, pn, 0xffffffffu, t.base, f);
+    s.g = g;
+    if (g == t.H) {
+        uint32_t from = before == t.H ? s.cold : before;
+        uint32_t full = ReplayChunk(t.hot, t.cls, t.full, t.H, t.letters | (t.wide << 31), from, v);
+        SetFull(t, s, full);
+    }
+}
+
+// kMode: 0 plain, 1 exit filter (PRED), 2 exit filter with one byte of look-ahead (LOOK) in the 16-byte body chunks
+template <int kMode>
 __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
 {
+    constexpr bool kPred = kMode != 0;
+    LookFilter look;
+    look.lo = a.look_bitmap;
+    look.hi = 0;
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv, a.hot8, a.hot);
@@ -844,8 +873,12 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
                 if (k + kStageSlots + j < chunks)
                     CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
                 CopyAsyncCommit();
-                if (k + j < chunks)
-                    Chunk16<kPred>(t, s, v);
+                if (k + j < chunks) {
+                    if (kMode == 2)
+                        Chunk16Look(t, s, v, look);
+                    else
+                        Chunk16<kPred>(t, s, v);
+                }
             }
             // multi.h:955-958,:979-982: a NoExit state cannot be left by any byte.
             const bool live = k + kStageSlots < chunks;
@@ -1359,14 +1392,18 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
             // through registers like in the uniform scan kernel -- one LDG.256 per lane per 32 bytes, prefetched one
             // block ahead -- instead of the cp.async ring, whose shared-memory round trip costs half a wavefront per
             // step on the pipe that bounds the walk.
-            if (len != 0) {
+            // every lane of the warp walks the loop (its control flow holds a warp vote), also the lanes past the end
+            // of the batch: they are stopped from the start and read string 0
+            const uint32_t ulen = (uint32_t) a.fixed_len;
+            const uint8_t* const src = valid ? first : a.corpus;
+            if (ulen != 0) {
                 uint4 a0, a1, b0, b1;
-                LoadStream32(first, a0, a1);
+                LoadStream32(src, a0, a1);
                 for (uint32_t off = 0;;) {
                     off += 32;
-                    const bool more_b = off < len;
+                    const bool more_b = off < ulen;
                     if (more_b)
-                        LoadStream32(first + off, b0, b1);
+                        LoadStream32(src + off, b0, b1);
                     if (!l.stop)
                         PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, a0, l);
                     if (!l.stop)
@@ -1374,9 +1411,9 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
                     if (!more_b)
                         break;
                     off += 32;
-                    const bool more_a = off < len;
+                    const bool more_a = off < ulen;
                     if (more_a)
-                        LoadStream32(first + off, a0, a1);
+                        LoadStream32(src + off, a0, a1);
                     if (!l.stop)
                         PrefixChunk16<kShortest, kReverse>(a, t, hot_flags, s, b0, l);
                     if (!l.stop)
@@ -1889,8 +1926,8 @@ __global__ void __launch_bounds__(256) SynthMixedFillKernel(uint64_t seed, uint3
 
 template <bool kPred>
 const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUniformKernel<kPred>); }
-template <bool kPred>
-const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kPred>); }
+template <int kMode>
+const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kMode>); }
 
 int LookRegs()
 {
@@ -1911,10 +1948,11 @@ const void* KernelFor(int variant, bool uniform)
     if (variant == kVariantLook64 && uniform)
         return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48>)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40>);
-    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64;      // CSR batches: LOOK falls back to the exit filter
     if (uniform)
-        return pred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
-    return pred ? GenericKernelPtr<true>() : GenericKernelPtr<false>();
+        return variant == kVariantPred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
+    if (variant == kVariantLook || variant == kVariantLook64)      // CSR batches: one look-ahead kernel (32-slot filter)
+        return GenericKernelPtr<2>();
+    return variant == kVariantPred ? GenericKernelPtr<1>() : GenericKernelPtr<0>();
 }
 
 } // namespace

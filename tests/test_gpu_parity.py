@@ -69,11 +69,13 @@ def test_alignment_and_ragged_lengths(cuda_device):
         junk = [bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8)) for n in rng.integers(0, 70, size=50)]
         strings += junk
         expect += [None] * len(junk)
-        final, mask, state = gpu_run(sc, strings)
         f2, m2, s2 = checker_run(case.image, strings, True, True)
-        assert (final == f2).all() and (mask == m2).all() and (state == s2).all(), case.name
-        for got, want in zip(final.tolist(), expect):
-            assert want is None or got == want
+        for variant in (0, 2, 4):                    # AUTO (plain for CSR), exit filter, look-ahead filter
+            sc.set_variant(variant)
+            final, mask, state = gpu_run(sc, strings)
+            assert (final == f2).all() and (mask == m2).all() and (state == s2).all(), (case.name, variant)
+            for got, want in zip(final.tolist(), expect):
+                assert want is None or got == want
 
 
 def test_mark_flag_combinations(cuda_device, ref):
@@ -367,7 +369,7 @@ def test_length_binned_launch_mixed_utf8(cuda_device, ref):
             assert (np.diff(bucket) <= 0).all()                          # longest bucket first, corpus order inside
             same = np.diff(bucket) == 0
             assert (np.diff(order)[same] > 0).all()
-        for variant in (1, 2):
+        for variant in (1, 2, 4):
             sc.set_variant(variant)
             r = P.Runner(sc).Begin().Run(batch).End()
             assert (r.Matches().astype(np.uint8) == f_ref).all(), (binned, variant)

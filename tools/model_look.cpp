@@ -79,7 +79,13 @@ int main(int argc, char** argv)
     sp.plant_off[sp.n_plants] = (uint32_t) packed.size();
 
     std::vector<uint8_t> corpus(n * len);
-    for (uint64_t i = 0; i < n; ++i) {
+    const bool mixed = std::getenv("MIXED") != nullptr;       // BASELINE configs[3] text (synth.h SynthMixedCell), fixed length here
+    for (uint64_t i = 0; i < n && mixed; ++i)
+        for (uint32_t c = 0; c < len / 4; ++c) {
+            uint32_t v = SynthMixedCellPlanted(42, 8, i, len, c);
+            std::memcpy(&corpus[i * len + 4 * c], &v, 4);
+        }
+    for (uint64_t i = 0; i < n && !mixed; ++i) {
         uint8_t* dst = &corpus[i * len];
         for (uint32_t w = 0; w < len / 8; ++w) {
             uint64_t v = SynthWord(sp.seed, i, w, len / 8);
