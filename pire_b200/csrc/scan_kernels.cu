@@ -496,9 +496,28 @@ __device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, 
         : "r"(pa), "r"(pa_next), "r"(bb), "n"(kHotStride));
 }
 
+// The same step with the byte's own filter only (the round-1 exit filter over F): one LOP3 less.
+__device__ __forceinline__ void LookStepOwn(uint32_t& g, uint32_t bb, uint32_t pa)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, addr;\n"
+        "and.b32 t, %1, 1;\n"
+        "or.b32 t, t, %0;\n"
+        "setp.ne.u32 p, t, 0;\n"
+        "mad.lo.u32 addr, %0, %3, %2;\n"
+        "@p ld.shared.u8 %0, [addr];\n"
+        "}\n"
+        : "+r"(g)
+        : "r"(pa), "r"(bb), "n"(kHotStride));
+}
+
 // Four bytes.  (bb0, pa0) belong to byte 0 of `w` and were computed by the previous call; pan is the probe of the
-// byte that follows the word.
-template <bool k64>
+// byte that follows the word.  kAlt: look ahead from the even bytes only -- a lane that
+// skipped an exit byte there is back in id 0 after the odd byte, which its own filter then skips too -- trading
+// wavefronts (model: 1.72 -> 1.91 per step) for half a LOP3 per byte.
+template <bool k64, bool kAlt = false>
 __device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, uint32_t pa0, uint32_t pan, uint32_t base,
                                          const LookFilter& f)
 {
@@ -507,9 +526,15 @@ __device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, 
     LookProbe<k64, 2>(w, base, f, bb2, pa2);
     LookProbe<k64, 3>(w, base, f, bb3, pa3);
     LookStep(g, bb0, pa0, pa1);
-    LookStep(g, bb1, pa1, pa2);
+    if (kAlt)
+        LookStepOwn(g, bb1, pa1);
+    else
+        LookStep(g, bb1, pa1, pa2);
     LookStep(g, bb2, pa2, pa3);
-    LookStep(g, bb3, pa3, pan);
+    if (kAlt)
+        LookStepOwn(g, bb3, pa3);
+    else
+        LookStep(g, bb3, pa3, pan);
 }
 
 // Shared-window address of the dynamic shared memory array, as a link-time constant (a cvta of a generic pointer
@@ -536,7 +561,7 @@ __device__ __noinline__ uint32_t ReplayBlock32(const ScanArgs* a, uint32_t from,
     return ReplayChunk(sv.hot, sv.cls, a->full, a->hot, letters_wide, mid, v1);
 }
 
-template <bool k64>
+template <bool k64, bool kAlt>
 __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32_t& prev, const uint4& v0, const uint4& v1,
                                             uint32_t next0, bool more, const LookFilter& f, uint32_t opaque_zero, const ScanArgs* args)
 {
@@ -544,19 +569,19 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     uint32_t bb, pa, bn, pn;
     LookProbe<k64, 0>(v0.x, t.base, f, bb, pa);
     LookProbe<k64, 0>(v0.y, t.base, f, bn, pn);
-    LookWord<k64>(g, v0.x, bb, pa, pn, t.base, f);
+    LookWord<k64, kAlt>(g, v0.x, bb, pa, pn, t.base, f);
     LookProbe<k64, 0>(v0.z, t.base, f, bb, pa);
-    LookWord<k64>(g, v0.y, bn, pn, pa, t.base, f);
+    LookWord<k64, kAlt>(g, v0.y, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v0.w, t.base, f, bn, pn);
-    LookWord<k64>(g, v0.z, bb, pa, pn, t.base, f);
+    LookWord<k64, kAlt>(g, v0.z, bb, pa, pn, t.base, f);
     LookProbe<k64, 0>(v1.x, t.base, f, bb, pa);
-    LookWord<k64>(g, v0.w, bn, pn, pa, t.base, f);
+    LookWord<k64, kAlt>(g, v0.w, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v1.y, t.base, f, bn, pn);
-    LookWord<k64>(g, v1.x, bb, pa, pn, t.base, f);
+    LookWord<k64, kAlt>(g, v1.x, bb, pa, pn, t.base, f);
     LookProbe<k64, 0>(v1.z, t.base, f, bb, pa);
-    LookWord<k64>(g, v1.y, bn, pn, pa, t.base, f);
+    LookWord<k64, kAlt>(g, v1.y, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v1.w, t.base, f, bn, pn);
-    LookWord<k64>(g, v1.z, bb, pa, pn, t.base, f);
+    LookWord<k64, kAlt>(g, v1.z, bb, pa, pn, t.base, f);
     // The word after the block was requested from HBM when this block began: its probe must stay down here (an
     // ordinary intrinsic is hoisted to the top of the block by the compiler, where it waits for the whole DRAM
     // latency -- ncu: 10 % of all stall samples on that one IDP).
@@ -564,7 +589,7 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     // plus g times a kernel argument that is always zero -- which costs one IMAD per block.)
     const uint32_t late = next0 + g * opaque_zero;
     LookProbe<k64, 0>(late, t.base, f, bb, pa);
-    LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
+    LookWord<k64, kAlt>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     if (g == t.H) {
         prev = ReplayBlock32(args, prev, v0, v1);
         g = prev < t.H ? prev : t.H;
@@ -578,7 +603,7 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
 constexpr int kLookBlock40 = 512;
 constexpr int kLookBlock48 = 384;
 
-template <bool k64, int kRegs>
+template <bool k64, int kRegs, bool kAlt>
 __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
@@ -621,7 +646,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     if (more_b)
                         LoadStream32(p, b0, b1);
                     __syncwarp();          // see below
-                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
+                    LookBlock32<k64, kAlt>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
                     if (!more_b)
                         break;
                     const bool more_a = left > 2;
@@ -633,7 +658,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
                     // stall samples were long-scoreboard waits on the first use of the loaded word).
                     __syncwarp();
-                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
+                    LookBlock32<k64, kAlt>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
                     left -= 2;
                     // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                     if (!more_a || __all_sync(0xffffffffu, sv.noexit[g] != 0))
@@ -1938,16 +1963,32 @@ int LookRegs()
     return regs;
 }
 
+bool LookAlt()
+{
+    static const bool alt = [] {
+        const char* env = getenv("PIRE_B200_LOOK_ALT");
+        return env && env[0] == '1';
+    }();
+    return alt;
+}
+
 const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
-    if (variant == kVariantLook && uniform)
-        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48>)
-                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40>);
-    if (variant == kVariantLook64 && uniform)
-        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48>)
-                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40>);
+    if ((variant == kVariantLook || variant == kVariantLook64) && uniform) {
+        const int key = (variant == kVariantLook64 ? 4 : 0) + (LookRegs() == 48 ? 2 : 0) + (LookAlt() ? 1 : 0);
+        switch (key) {
+        case 0: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, false>);
+        case 1: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, true>);
+        case 2: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, false>);
+        case 3: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, true>);
+        case 4: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40, false>);
+        case 5: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40, true>);
+        case 6: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48, false>);
+        default: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48, true>);
+        }
+    }
     if (uniform)
         return variant == kVariantPred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
     if (variant == kVariantLook || variant == kVariantLook64)      // CSR batches: one look-ahead kernel (32-slot filter)

@@ -61,6 +61,7 @@ int main(int argc, char** argv)
     const uint64_t n = std::strtoull(argv[2], nullptr, 10);
     const uint32_t len = (uint32_t) std::atoi(argv[3]);
     const uint32_t stride = std::getenv("STRIDE") ? std::atoi(std::getenv("STRIDE")) : 292;
+    const bool alt = std::getenv("ALT") != nullptr;           // look-ahead on even positions only
 
     SynthParams sp;
     std::memset(&sp, 0, sizeof(sp));
@@ -236,6 +237,8 @@ int main(int argc, char** argv)
                         bool need;
                         if (mode == 0)
                             need = gg != 0 || f1[h.slot(b)];
+                        else if (alt && (k & 1))
+                            need = gg != 0 || ff[h.slot(b)];            // ALT: odd positions use the byte's own filter only
                         else
                             need = gg != 0 || (ff[h.slot(b)] && (last || !look_ok || ff[h.slot(nb)]));
                         nonzero[mode] += gg != 0;

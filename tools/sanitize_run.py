@@ -19,7 +19,7 @@ dev = "cuda:0"
 
 def check(sc, orc, batch, corpus_host, offsets_host, fixed_len, n, tag):
     f, m, s = orc.run(corpus_host, offsets_host, fixed_len=fixed_len, n=n, shortcuts=True)
-    for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED, N.VARIANT_PRIV):
+    for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED, N.VARIANT_PRIV, N.VARIANT_LOOK, N.VARIANT_LOOK64):
         sc.set_variant(variant)
         r = P.Runner(sc).Begin().Run(batch).End()
         assert (r.Matches().astype(np.uint8) == f).all() and (r.AcceptMasks() == m).all() and (r.States() == s).all(), (tag, variant)
@@ -95,7 +95,7 @@ for name in ("headline", "glue10"):
     for max_hot in (255, 2):
         sc = P.Scanner(image, 0)
         sc.set_max_hot(max_hot)
-        for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED):
+        for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED, N.VARIANT_LOOK):
             sc.set_variant(variant)
             r = P.Runner(sc).Begin().Run(lb).End()
             assert (r.Matches().astype(np.uint8) == f).all() and (r.AcceptMasks() == m).all() and (r.States() == s_).all(), (name, max_hot, variant)
@@ -146,5 +146,46 @@ for name in ("hf_glue10", "count_words5"):
     res = P.HalfFinalCount(sc, fbatch)
     assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all(), name
     print("ok counting", name, flush=True)
+# round 2: register-streaming bodies of the prefix / counting kernels (fixed length, multiple of 32, partial last warp),
+# accept sets, the streaming host entry point (1 MiB chunks, pageable input), the one-rank sharded call
+image = W.load_image("headline")
+orc = Oracle(image)
+sc = P.Scanner(image, 0)
+spec = W.SynthSpec(1024 + 7, 160, plants=W.HEADLINE_PLANTS)
+d = torch.empty(spec.total_bytes(), dtype=torch.uint8, device=dev)
+spec.fill_device(d)
+host = spec.host_sample(0, 1024 + 7)
+fbatch = P.Batch(d, fixed_len=160, n=1024 + 7)
+for shortest in (False, True):
+    got = (P.ShortestPrefix if shortest else P.LongestPrefix)(sc, fbatch, throughBeginMark=True, throughEndMark=True)
+    assert (got == oracle_prefix(orc, host, fixed_len=160, n=1024 + 7, shortest=shortest, through_begin=True, through_end=True)).all()
+image = W.load_image("hf_glue10")
+sc_hf = P.Scanner(image, 0)
+want, wfin = oracle_count(Oracle(image), host, fixed_len=160, n=1024 + 7)
+for mode in (1, 2, 3):
+    sc_hf.set_count_mode(mode)
+    res = P.HalfFinalCount(sc_hf, fbatch)
+    assert (res.counts == want).all(), mode
+print("ok uniform bodies", flush=True)
+import ctypes as C
+r = P.Runner(sc).Begin().Run(fbatch).End()
+states = torch.from_numpy(r.States().astype(np.int32)).to(dev)
+sets = torch.zeros(1024 + 7, dtype=torch.int32, device=dev)
+N.check(N.lib.pire_gpu_accept_sets(sc._h, states.data_ptr(), 1024 + 7, sets.data_ptr(), None), "accept sets")
+assert (sets.cpu().numpy().view(np.uint32) == r.AcceptMasks()).all()
+os.environ["PIRE_B200_HOST_CHUNK_MB"] = "1"
+big = W.SynthSpec(6000, 1024, plants=W.HEADLINE_PLANTS)
+hbig = big.host_sample(0, 6000)
+bits, masks, _ = sc.run_batch_host(hbig, fixed_len=1024, n=6000, want_masks=True)
+f, m, _ = orc.run(hbig, fixed_len=1024, n=6000)
+assert (np.unpackbits(bits.view(np.uint8), bitorder="little")[:6000] == f).all() and (masks == m).all()
+from pire_b200.dist import Comm
+comm = Comm(0, rank=0, world=1)
+ball = torch.full((comm.words(1024 + 7),), -1, dtype=torch.int32, device=dev)
+comm.run_sharded(sc, fbatch, 1024 + 7, N.RUN_BEGIN | N.RUN_END, ball)
+torch.cuda.synchronize()
+assert (np.unpackbits(ball.cpu().numpy().view(np.uint8), bitorder="little")[:1024 + 7] == r.Matches().astype(np.uint8)).all()
+comm.close()
+print("ok accept sets, host streaming, sharded(1)", flush=True)
 torch.cuda.synchronize()
 print("sanitize_run done, launches:", N.lib.pire_gpu_launch_count())
