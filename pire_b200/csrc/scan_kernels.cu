@@ -796,8 +796,8 @@ __device__ __forceinline__ void Chunk16Look(const Tables& t, LaneState& s, uint4
 }
 
 // kMode: 0 plain, 1 exit filter (PRED), 2 exit filter with one byte of look-ahead (LOOK) in the 16-byte body chunks
-template <int kMode>
-__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
+template <int kMode, int kCtas = kGenericBlocksPerSM>
+__global__ void __launch_bounds__(kBlock, kCtas) ScanGenericKernel(const __grid_constant__ ScanArgs a)
 {
     constexpr bool kPred = kMode != 0;
     LookFilter look;
@@ -1951,8 +1951,21 @@ __global__ void __launch_bounds__(256) SynthMixedFillKernel(uint64_t seed, uint3
 
 template <bool kPred>
 const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUniformKernel<kPred>); }
+int GenericCtas()
+{
+    static const int ctas = [] {
+        const char* env = getenv("PIRE_B200_GENERIC_CTAS");       // experiments: resident CTAs per SM of the CSR kernel
+        return env && atoi(env) == 3 ? 3 : kGenericBlocksPerSM;
+    }();
+    return ctas;
+}
+
 template <int kMode>
-const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kMode>); }
+const void* GenericKernelPtr()
+{
+    return GenericCtas() == 3 ? reinterpret_cast<const void*>(&ScanGenericKernel<kMode, 3>)
+                              : reinterpret_cast<const void*>(&ScanGenericKernel<kMode, kGenericBlocksPerSM>);
+}
 
 int LookRegs()
 {
@@ -2040,9 +2053,7 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
     if (per_sm < 1)
         return cudaErrorLaunchOutOfResources;
     if (!uniform) {
-        int cap = kGenericBlocksPerSM;
-        if (const char* env = getenv("PIRE_B200_GENERIC_CTAS"))       // experiments: resident CTAs per SM
-            cap = atoi(env) > 0 ? atoi(env) : cap;
+        const int cap = GenericCtas();
         per_sm = per_sm < cap ? per_sm : cap;
     }
     plan->grid = sms * per_sm;     // persistent: every SM holds its full share of CTAs
