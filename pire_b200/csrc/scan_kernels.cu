@@ -115,6 +115,16 @@ __device__ __forceinline__ void CopyAsync16(uint32_t dst_shared, const uint8_t* 
 {
     asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
 }
+// The same copy through L1 (.ca): a lane's next 16 bytes are the other half of the 32-byte sector it has just
+// fetched, so with room in L1 (small automata leave most of the 228 KB to it) the second request hits there
+// instead of going back to L2.
+__device__ __forceinline__ void CopyAsync16(uint32_t dst_shared, const uint8_t* src, bool through_l1)
+{
+    if (through_l1)
+        asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+    else
+        CopyAsync16(dst_shared, src);
+}
 __device__ __forceinline__ void CopyAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void CopyAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
@@ -496,28 +506,10 @@ __device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, 
         : "r"(pa), "r"(pa_next), "r"(bb), "n"(kHotStride));
 }
 
-// The same step with the byte's own filter only (the round-1 exit filter over F): one LOP3 less.
-__device__ __forceinline__ void LookStepOwn(uint32_t& g, uint32_t bb, uint32_t pa)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b32 t, addr;\n"
-        "and.b32 t, %1, 1;\n"
-        "or.b32 t, t, %0;\n"
-        "setp.ne.u32 p, t, 0;\n"
-        "mad.lo.u32 addr, %0, %3, %2;\n"
-        "@p ld.shared.u8 %0, [addr];\n"
-        "}\n"
-        : "+r"(g)
-        : "r"(pa), "r"(bb), "n"(kHotStride));
-}
-
 // Four bytes.  (bb0, pa0) belong to byte 0 of `w` and were computed by the previous call; pan is the probe of the
-// byte that follows the word.  kAlt: look ahead from the even bytes only -- a lane that
-// skipped an exit byte there is back in id 0 after the odd byte, which its own filter then skips too -- trading
-// wavefronts (model: 1.72 -> 1.91 per step) for half a LOP3 per byte.
-template <bool k64, bool kAlt = false>
+// byte that follows the word.  (Looking ahead from the even bytes only -- half a LOP3 less per byte, 1.91 instead of
+// 1.72 wavefronts per step in the model -- measured slower, 2.67 vs 2.63 ms: profiles/r02_experiments_notes.txt.)
+template <bool k64>
 __device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, uint32_t pa0, uint32_t pan, uint32_t base,
                                          const LookFilter& f)
 {
@@ -526,15 +518,9 @@ __device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, 
     LookProbe<k64, 2>(w, base, f, bb2, pa2);
     LookProbe<k64, 3>(w, base, f, bb3, pa3);
     LookStep(g, bb0, pa0, pa1);
-    if (kAlt)
-        LookStepOwn(g, bb1, pa1);
-    else
-        LookStep(g, bb1, pa1, pa2);
+    LookStep(g, bb1, pa1, pa2);
     LookStep(g, bb2, pa2, pa3);
-    if (kAlt)
-        LookStepOwn(g, bb3, pa3);
-    else
-        LookStep(g, bb3, pa3, pan);
+    LookStep(g, bb3, pa3, pan);
 }
 
 // Shared-window address of the dynamic shared memory array, as a link-time constant (a cvta of a generic pointer
@@ -561,7 +547,7 @@ __device__ __noinline__ uint32_t ReplayBlock32(const ScanArgs* a, uint32_t from,
     return ReplayChunk(sv.hot, sv.cls, a->full, a->hot, letters_wide, mid, v1);
 }
 
-template <bool k64, bool kAlt>
+template <bool k64>
 __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32_t& prev, const uint4& v0, const uint4& v1,
                                             uint32_t next0, bool more, const LookFilter& f, uint32_t opaque_zero, const ScanArgs* args)
 {
@@ -569,19 +555,19 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     uint32_t bb, pa, bn, pn;
     LookProbe<k64, 0>(v0.x, t.base, f, bb, pa);
     LookProbe<k64, 0>(v0.y, t.base, f, bn, pn);
-    LookWord<k64, kAlt>(g, v0.x, bb, pa, pn, t.base, f);
+    LookWord<k64>(g, v0.x, bb, pa, pn, t.base, f);
     LookProbe<k64, 0>(v0.z, t.base, f, bb, pa);
-    LookWord<k64, kAlt>(g, v0.y, bn, pn, pa, t.base, f);
+    LookWord<k64>(g, v0.y, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v0.w, t.base, f, bn, pn);
-    LookWord<k64, kAlt>(g, v0.z, bb, pa, pn, t.base, f);
+    LookWord<k64>(g, v0.z, bb, pa, pn, t.base, f);
     LookProbe<k64, 0>(v1.x, t.base, f, bb, pa);
-    LookWord<k64, kAlt>(g, v0.w, bn, pn, pa, t.base, f);
+    LookWord<k64>(g, v0.w, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v1.y, t.base, f, bn, pn);
-    LookWord<k64, kAlt>(g, v1.x, bb, pa, pn, t.base, f);
+    LookWord<k64>(g, v1.x, bb, pa, pn, t.base, f);
     LookProbe<k64, 0>(v1.z, t.base, f, bb, pa);
-    LookWord<k64, kAlt>(g, v1.y, bn, pn, pa, t.base, f);
+    LookWord<k64>(g, v1.y, bn, pn, pa, t.base, f);
     LookProbe<k64, 0>(v1.w, t.base, f, bn, pn);
-    LookWord<k64, kAlt>(g, v1.z, bb, pa, pn, t.base, f);
+    LookWord<k64>(g, v1.z, bb, pa, pn, t.base, f);
     // The word after the block was requested from HBM when this block began: its probe must stay down here (an
     // ordinary intrinsic is hoisted to the top of the block by the compiler, where it waits for the whole DRAM
     // latency -- ncu: 10 % of all stall samples on that one IDP).
@@ -589,7 +575,7 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     // plus g times a kernel argument that is always zero -- which costs one IMAD per block.)
     const uint32_t late = next0 + g * opaque_zero;
     LookProbe<k64, 0>(late, t.base, f, bb, pa);
-    LookWord<k64, kAlt>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
+    LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     if (g == t.H) {
         prev = ReplayBlock32(args, prev, v0, v1);
         g = prev < t.H ? prev : t.H;
@@ -603,7 +589,7 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
 constexpr int kLookBlock40 = 512;
 constexpr int kLookBlock48 = 384;
 
-template <bool k64, int kRegs, bool kAlt>
+template <bool k64, int kRegs>
 __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
@@ -646,7 +632,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     if (more_b)
                         LoadStream32(p, b0, b1);
                     __syncwarp();          // see below
-                    LookBlock32<k64, kAlt>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
+                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
                     if (!more_b)
                         break;
                     const bool more_a = left > 2;
@@ -658,7 +644,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
                     // stall samples were long-scoreboard waits on the first use of the loaded word).
                     __syncwarp();
-                    LookBlock32<k64, kAlt>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
+                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
                     left -= 2;
                     // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                     if (!more_a || __all_sync(0xffffffffu, sv.noexit[g] != 0))
@@ -796,8 +782,8 @@ __device__ __forceinline__ void Chunk16Look(const Tables& t, LaneState& s, uint4
 }
 
 // kMode: 0 plain, 1 exit filter (PRED), 2 exit filter with one byte of look-ahead (LOOK) in the 16-byte body chunks
-template <int kMode, int kCtas = kGenericBlocksPerSM>
-__global__ void __launch_bounds__(kBlock, kCtas) ScanGenericKernel(const __grid_constant__ ScanArgs a)
+template <int kMode>
+__global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel(const __grid_constant__ ScanArgs a)
 {
     constexpr bool kPred = kMode != 0;
     LookFilter look;
@@ -887,7 +873,7 @@ __global__ void __launch_bounds__(kBlock, kCtas) ScanGenericKernel(const __grid_
 #pragma unroll
         for (int j = 0; j < kStageSlots; ++j) {
             if ((uint32_t) j < chunks)
-                CopyAsync16(stage + j * 512, p + 16 * j);
+                CopyAsync16(stage + j * 512, p + 16 * j, a.ring_l1 != 0);
             CopyAsyncCommit();
         }
         for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += kStageSlots) {
@@ -896,7 +882,7 @@ __global__ void __launch_bounds__(kBlock, kCtas) ScanGenericKernel(const __grid_
                 CopyAsyncWait<kStageSlots - 1>();                 // chunk k + j has landed
                 const uint4 v = LoadShared16(stage + j * 512);
                 if (k + kStageSlots + j < chunks)
-                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
+                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j), a.ring_l1 != 0);
                 CopyAsyncCommit();
                 if (k + j < chunks) {
                     if (kMode == 2)
@@ -1951,21 +1937,8 @@ __global__ void __launch_bounds__(256) SynthMixedFillKernel(uint64_t seed, uint3
 
 template <bool kPred>
 const void* UniformKernelPtr() { return reinterpret_cast<const void*>(&ScanUniformKernel<kPred>); }
-int GenericCtas()
-{
-    static const int ctas = [] {
-        const char* env = getenv("PIRE_B200_GENERIC_CTAS");       // experiments: resident CTAs per SM of the CSR kernel
-        return env && atoi(env) == 3 ? 3 : kGenericBlocksPerSM;
-    }();
-    return ctas;
-}
-
 template <int kMode>
-const void* GenericKernelPtr()
-{
-    return GenericCtas() == 3 ? reinterpret_cast<const void*>(&ScanGenericKernel<kMode, 3>)
-                              : reinterpret_cast<const void*>(&ScanGenericKernel<kMode, kGenericBlocksPerSM>);
-}
+const void* GenericKernelPtr() { return reinterpret_cast<const void*>(&ScanGenericKernel<kMode>); }
 
 int LookRegs()
 {
@@ -1976,32 +1949,16 @@ int LookRegs()
     return regs;
 }
 
-bool LookAlt()
-{
-    static const bool alt = [] {
-        const char* env = getenv("PIRE_B200_LOOK_ALT");
-        return env && env[0] == '1';
-    }();
-    return alt;
-}
-
 const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
-    if ((variant == kVariantLook || variant == kVariantLook64) && uniform) {
-        const int key = (variant == kVariantLook64 ? 4 : 0) + (LookRegs() == 48 ? 2 : 0) + (LookAlt() ? 1 : 0);
-        switch (key) {
-        case 0: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, false>);
-        case 1: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, true>);
-        case 2: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, false>);
-        case 3: return reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, true>);
-        case 4: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40, false>);
-        case 5: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40, true>);
-        case 6: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48, false>);
-        default: return reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48, true>);
-        }
-    }
+    if (variant == kVariantLook && uniform)
+        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48>)
+                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40>);
+    if (variant == kVariantLook64 && uniform)
+        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 48>)
+                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40>);
     if (uniform)
         return variant == kVariantPred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
     if (variant == kVariantLook || variant == kVariantLook64)      // CSR batches: one look-ahead kernel (32-slot filter)
@@ -2052,11 +2009,17 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
         return err;
     if (per_sm < 1)
         return cudaErrorLaunchOutOfResources;
-    if (!uniform) {
-        const int cap = GenericCtas();
-        per_sm = per_sm < cap ? per_sm : cap;
-    }
+    if (!uniform)
+        per_sm = per_sm < kGenericBlocksPerSM ? per_sm : kGenericBlocksPerSM;      // a third CTA measured slower twice (r01, r02 notes)
     plan->grid = sms * per_sm;     // persistent: every SM holds its full share of CTAs
+    // shared-memory carve-out: what the resident CTAs need (plus the 1 KB the system reserves per CTA), the rest of the
+    // 228 KB stays L1 -- small automata leave the CSR kernel's staging copies an L1 to hit in
+    {
+        const size_t need = (size_t) per_sm * (plan->shared + 1024);
+        int pct = (int) ((need * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
+        pct = pct > 100 ? 100 : pct;
+        plan->carveout = pct;
+    }
     return cudaSuccess;
 }
 
@@ -2069,7 +2032,11 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     uint64_t want = (units + warps_per_block - 1) / warps_per_block;
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
     void* args[] = {const_cast<ScanArgs*>(&a)};
-    cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
+    cudaError_t err = cudaSuccess;
+    if (plan.carveout > 0 && plan.carveout < 100 && a.ring_l1)
+        err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributePreferredSharedMemoryCarveout, plan.carveout);
+    if (err == cudaSuccess)
+        err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);
     return err;
