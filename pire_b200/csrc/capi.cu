@@ -177,11 +177,6 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->exit_bitmap0 = t.exit_bitmap0;
     a->look_bitmap = t.look_bitmap;
     a->look_bitmap64 = t.look_bitmap64;
-    {
-        // experiments: PIRE_B200_RING_L1=1 forces the L1-allocating staging copies, =0 forbids them
-        static const int forced = [] { const char* e = getenv("PIRE_B200_RING_L1"); return e ? atoi(e) : -1; }();
-        a->ring_l1 = forced >= 0 ? (uint32_t) forced : 0u;
-    }
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
     a->hot8_small = sc->dev.hot8_small;

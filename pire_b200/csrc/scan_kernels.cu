@@ -115,16 +115,6 @@ __device__ __forceinline__ void CopyAsync16(uint32_t dst_shared, const uint8_t* 
 {
     asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
 }
-// The same copy through L1 (.ca): a lane's next 16 bytes are the other half of the 32-byte sector it has just
-// fetched, so with room in L1 (small automata leave most of the 228 KB to it) the second request hits there
-// instead of going back to L2.
-__device__ __forceinline__ void CopyAsync16(uint32_t dst_shared, const uint8_t* src, bool through_l1)
-{
-    if (through_l1)
-        asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
-    else
-        CopyAsync16(dst_shared, src);
-}
 __device__ __forceinline__ void CopyAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void CopyAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
@@ -873,7 +863,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
 #pragma unroll
         for (int j = 0; j < kStageSlots; ++j) {
             if ((uint32_t) j < chunks)
-                CopyAsync16(stage + j * 512, p + 16 * j, a.ring_l1 != 0);
+                CopyAsync16(stage + j * 512, p + 16 * j);
             CopyAsyncCommit();
         }
         for (uint32_t k = 0; __any_sync(0xffffffffu, k < chunks); k += kStageSlots) {
@@ -882,7 +872,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
                 CopyAsyncWait<kStageSlots - 1>();                 // chunk k + j has landed
                 const uint4 v = LoadShared16(stage + j * 512);
                 if (k + kStageSlots + j < chunks)
-                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j), a.ring_l1 != 0);
+                    CopyAsync16(stage + j * 512, p + 16 * (size_t) (k + kStageSlots + j));
                 CopyAsyncCommit();
                 if (k + j < chunks) {
                     if (kMode == 2)
@@ -2012,14 +2002,6 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
     if (!uniform)
         per_sm = per_sm < kGenericBlocksPerSM ? per_sm : kGenericBlocksPerSM;      // a third CTA measured slower twice (r01, r02 notes)
     plan->grid = sms * per_sm;     // persistent: every SM holds its full share of CTAs
-    // shared-memory carve-out: what the resident CTAs need (plus the 1 KB the system reserves per CTA), the rest of the
-    // 228 KB stays L1 -- small automata leave the CSR kernel's staging copies an L1 to hit in
-    {
-        const size_t need = (size_t) per_sm * (plan->shared + 1024);
-        int pct = (int) ((need * 100 + 228 * 1024 - 1) / (228 * 1024)) + 2;
-        pct = pct > 100 ? 100 : pct;
-        plan->carveout = pct;
-    }
     return cudaSuccess;
 }
 
@@ -2032,11 +2014,7 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     uint64_t want = (units + warps_per_block - 1) / warps_per_block;
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
     void* args[] = {const_cast<ScanArgs*>(&a)};
-    cudaError_t err = cudaSuccess;
-    if (plan.carveout > 0 && plan.carveout < 100 && a.ring_l1)
-        err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributePreferredSharedMemoryCarveout, plan.carveout);
-    if (err == cudaSuccess)
-        err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
+    cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);
     return err;

@@ -36,7 +36,6 @@ struct ScanArgs {
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     uint32_t look_bitmap;        // LOOK variant: 32-slot look-ahead filter (dfa_tables.hpp), slot = byte & 31
     uint64_t look_bitmap64;      // LOOK64 variant: the same filter with 64 slots, slot = byte & 63
-    uint32_t ring_l1;            // CSR scan kernel: staging copies allocate in L1 (automata whose tables leave L1 room)
     uint32_t uniform;            // prefix / count kernels: fixed length, a multiple of 32 bytes, corpus 32-byte aligned
     uint32_t opaque_zero;        // always 0; the LOOK kernels multiply by it to pin an instruction behind the walk
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
@@ -71,7 +70,6 @@ struct LaunchPlan {
     int block = 0;
     int grid = 0;
     size_t shared = 0;
-    int carveout = 0;         // preferred shared-memory carve-out in percent of the SM's 228 KB (0 = leave it)
 };
 
 enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3, kVariantLook = 4, kVariantLook64 = 5 };
