@@ -1011,6 +1011,249 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
     }
 }
 
+// ---------------------------------------------------------------- lines of text, in stream
+//
+// The lines of a newline-delimited text lie back to back, so they can be scanned where they are: the text is cut
+// into segments of a.text_segment bytes on 32-byte boundaries of the address space, lane j of a warp walks segment
+// 32 * unit + j like the uniform kernel walks a string (LDG.256, one block ahead in registers, every lane busy in
+// every step), and owns the lines that START inside its segment -- it runs past the segment's end until the last of
+// them is finished.  What makes this cheap:
+//   * the copy of the hot rows in shared memory maps '\n' to the start state in every row (the sink row keeps the
+//     sink), so the walk restarts by itself behind a line: no branch, no second pass over the rest of a chunk;
+//   * the sixteen states of a chunk are packed into four registers as they appear (one IMAD each, FMA pipe), and the
+//     newlines of the chunk are found in its bytes (exact zero-byte test of word ^ 0x0a0a0a0a, compressed to one bit per
+//     byte by a multiply): a lane picks the state in front of each newline out of the packed ones and reports it
+//     through a copy of the hot states' reports in shared memory -- the steady state reads no offsets and has no
+//     dependent global load;
+//   * a lane outside the hot rows at the end of a chunk (the sink is absorbing) replays the chunk byte by byte, line
+//     ends included; so does a lane over the unaligned start of its first line.
+// The offsets must be those of pire_gpu_split_lines for this text: line i + 1 starts right behind the '\n' of line i.
+// They are read once per lane and unit, by the binary search for the first line that starts in the segment; from then
+// on line numbers just count up.  Bytes outside the text read as '\n': that ends a last line without newline.
+constexpr uint32_t kTextSegment = 2048;
+constexpr int kTextBlocksPerSM = 2;
+constexpr size_t kTextFinBytes = 256 * sizeof(DeviceFin);
+
+struct TextLane {
+    uint32_t line;       // the line being walked
+    int32_t left;        // bytes from the chunk being walked to the end of the segment (negative behind it)
+    bool active;         // false: no line of this segment is left
+};
+
+// which outputs a line writes: bit 0 accept_masks, bit 1 state_idx, bit 2 match_bits (kept in a register: the
+// pointers themselves are 64-bit kernel parameters, and testing them costs three instructions each per line)
+__device__ __forceinline__ uint32_t TextOutputs(const ScanArgs& a)
+{
+    uint32_t outs = (a.accept_masks ? 1u : 0u) | (a.state_idx ? 2u : 0u) | (a.match_bits ? 4u : 0u);
+    asm volatile("mov.u32 %0, %0;" : "+r"(outs));
+    return outs;
+}
+
+__device__ __forceinline__ void TextReport(const ScanArgs& a, uint32_t outs, uint32_t line, DeviceFin f)
+{
+    if ((outs & 4u) && (f.result >> 31))
+        atomicOr(&a.match_bits[line >> 5], 1u << (line & 31));
+    if (outs & 1u)
+        a.accept_masks[line] = f.mask;
+    if (outs & 2u)
+        a.state_idx[line] = f.result & 0x7fffffffu;
+}
+
+// Bytes [from, to) of the block at text position cpos, one at a time from the complete state `full`.
+__device__ __forceinline__ void TextSlow(const ScanArgs& a, const Tables& t, const DeviceFin* fin_hot, uint32_t outs, TextLane& c,
+                                         LaneState& s, uint32_t full, int64_t cpos, uint32_t from, uint32_t to, uint64_t seg_hi,
+                                         uint64_t total)
+{
+    for (uint32_t j = from; j < to; ++j) {
+        const uint64_t at = (uint64_t) (cpos + (int64_t) j);
+        const uint32_t b = at < total ? a.corpus[at] : (uint32_t) '\n';
+        if (b == '\n') {
+            TextReport(a, outs, c.line, full < t.H ? fin_hot[full] : a.fin[full]);
+            ++c.line;
+            full = a.start;
+            if (c.line >= a.n || at + 1 >= seg_hi) {
+                c.active = false;
+                break;
+            }
+            continue;
+        }
+        full = SlowStep(t, full, b);
+    }
+    SetFull(t, s, full);
+}
+
+// Four steps; q collects the state IN FRONT of each byte (byte 3 - i of q for byte i of w).
+template <bool kPred>
+__device__ __forceinline__ void TextWord(const Tables& t, uint32_t& g, uint32_t w, uint32_t& q)
+{
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        asm("mad.lo.u32 %0, %0, 256, %1;" : "+r"(q) : "r"(g));       // q = q << 8 | g, on the FMA pipe
+        FastStep<kPred>(t, g, w, 0x5540u + i);
+    }
+}
+
+// Bit i of the result: byte i of w is '\n'.  Exact (no borrow between bytes): 0x80 in every byte of x that is zero,
+// then the four flags gathered into the top nibble by one multiply (the partial products do not collide).
+__device__ __forceinline__ uint32_t NewlineNibble(uint32_t w)
+{
+    const uint32_t x = w ^ 0x0a0a0a0au;
+    const uint32_t flags = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+    return (flags * 0x00204081u) >> 28;
+}
+
+// One 16-byte chunk at text position cpos.
+template <bool kPred>
+__device__ __forceinline__ void TextChunk(const ScanArgs& a, const Tables& t, const DeviceFin* fin_hot, uint32_t outs, TextLane& c,
+                                          LaneState& s, uint4 v, int64_t cpos, uint64_t seg_hi, uint64_t total)
+{
+    const uint32_t before = s.g;
+    uint32_t g = before, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    TextWord<kPred>(t, g, v.x, q0);
+    TextWord<kPred>(t, g, v.y, q1);
+    TextWord<kPred>(t, g, v.z, q2);
+    TextWord<kPred>(t, g, v.w, q3);
+    const int32_t left = c.left;
+    c.left = left - 16 > -(1 << 30) ? left - 16 : -(1 << 30);
+    if (!c.active)
+        return;
+    if (g == t.H) {
+        TextSlow(a, t, fin_hot, outs, c, s, before == t.H ? s.cold : before, cpos, 0, 16, seg_hi, total);
+        return;
+    }
+    s.g = g;
+    uint32_t ends = NewlineNibble(v.x) | (NewlineNibble(v.y) << 4) | (NewlineNibble(v.z) << 8) | (NewlineNibble(v.w) << 12);
+    const uint32_t n_lines = (uint32_t) a.n;
+    while (ends) {
+        const uint32_t k = (uint32_t) __ffs((int) ends) - 1u;
+        ends &= ends - 1u;
+        // the state in front of byte k sits in byte 3 - k % 4 of word k / 4
+        const uint32_t sel = (k ^ 3u) & 7u;
+        const uint32_t lo = __byte_perm(q0, q1, sel), hi = __byte_perm(q2, q3, sel);
+        const uint32_t st = ((k & 8u) ? hi : lo) & 0xffu;          // a hot state: the lane is not in the sink
+        TextReport(a, outs, c.line, fin_hot[st]);
+        ++c.line;
+        if (c.line >= n_lines || (int32_t) k + 1 >= left) {         // the next line starts behind the segment
+            c.active = false;
+            break;
+        }
+    }
+}
+
+// A 16-byte chunk that may stick out of the text at either end: bytes outside read as '\n'.  Out of line, it is rare.
+__device__ __noinline__ uint4 LoadText16Clipped(const uint8_t* aligned, uintptr_t buf_lo, uintptr_t buf_hi)
+{
+    uint32_t w[4] = {0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au};
+    for (int k = 0; k < 16; ++k) {
+        const uintptr_t at = reinterpret_cast<uintptr_t>(aligned) + k;
+        if (at >= buf_lo && at < buf_hi)
+            w[k >> 2] = (w[k >> 2] & ~(0xffu << (8 * (k & 3)))) | ((uint32_t) aligned[k] << (8 * (k & 3)));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void LoadBlock32(const uint8_t* aligned, uintptr_t buf_lo, uintptr_t buf_hi, uint4& v0, uint4& v1)
+{
+    if (reinterpret_cast<uintptr_t>(aligned) >= buf_lo && reinterpret_cast<uintptr_t>(aligned) + 32 <= buf_hi) {
+        LoadStream32(aligned, v0, v1);
+    } else {
+        v0 = LoadText16Clipped(aligned, buf_lo, buf_hi);
+        v1 = LoadText16Clipped(aligned + 16, buf_lo, buf_hi);
+    }
+}
+
+template <bool kPred>
+__global__ void __launch_bounds__(kBlock, kTextBlocksPerSM) ScanTextKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+    // behind a line the walk starts over: '\n' leads to the start state from every hot row
+    for (uint32_t g = threadIdx.x; g < a.hot; g += blockDim.x)
+        sv.hot[g * kHotStride + '\n'] = (uint8_t) a.start;
+    // what a line that stops in a hot state reports
+    DeviceFin* const fin_hot = reinterpret_cast<DeviceFin*>(sv.stage);
+    for (uint32_t g = threadIdx.x; g < a.hot; g += blockDim.x)
+        fin_hot[g] = a.fin[g];
+    __syncthreads();
+
+    Tables t;
+    t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.exit_bitmap0 | (1u << ('\n' & 31));       // the exit filter must let the separator through
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t outs = TextOutputs(a);
+    const uint64_t total = a.offsets[a.n] - 1;           // position of the last separator (real or the end of the text)
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
+    const uintptr_t buf_hi = buf_lo + total;
+    const uint32_t mis0 = (uint32_t) (buf_lo & 31);
+    const uint64_t seg = a.text_segment;
+    const uint64_t segments = (total + mis0) / seg + 1;
+    const uint64_t units = (segments + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t sidx = unit * 32 + lane;
+        const uint64_t seg_hi = (sidx + 1) * seg - mis0;
+        TextLane c;
+        c.line = 0;
+        c.left = 0;
+        c.active = false;
+        LaneState s;
+        s.g = a.start;
+        s.cold = 0;
+        const uint8_t* p = a.corpus;
+        int64_t pos = 0;
+        if (sidx < segments) {
+            const uint64_t seg_lo = sidx * seg > mis0 ? sidx * seg - mis0 : 0;
+            uint64_t lo = 0, hi = a.n;              // first line that starts at or behind seg_lo
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (a.offsets[mid] < seg_lo)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            if (lo < a.n) {
+                const uint64_t pos0 = a.offsets[lo];
+                if (pos0 < seg_hi) {
+                    c.line = (uint32_t) lo;
+                    c.active = true;
+                    pos = (int64_t) ((pos0 + mis0) & ~31ull) - (int64_t) mis0;      // the 32-byte block the line starts in
+                    const uint32_t skip = (uint32_t) ((int64_t) pos0 - pos);
+                    if (skip) {
+                        // the line starts inside the block: the rest of the block byte by byte
+                        TextSlow(a, t, fin_hot, outs, c, s, a.start, pos, skip, 32, seg_hi, total);
+                        pos += 32;
+                    }
+                    p = a.corpus + pos;
+                    c.left = (int32_t) ((int64_t) seg_hi - pos);
+                }
+            }
+        }
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        if (c.active)
+            LoadBlock32(p, buf_lo, buf_hi, v0, v1);
+        while (__any_sync(0xffffffffu, c.active)) {
+            uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+            if (c.active)
+                LoadBlock32(p + 32, buf_lo, buf_hi, n0, n1);
+            TextChunk<kPred>(a, t, fin_hot, outs, c, s, v0, pos, seg_hi, total);
+            TextChunk<kPred>(a, t, fin_hot, outs, c, s, v1, pos + 16, seg_hi, total);
+            v0 = n0;
+            v1 = n1;
+            p += 32;
+            pos += 32;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- PRIV variant
 //
 // The plain walk is bound by shared-memory wavefronts once lanes sit in different
@@ -2047,14 +2290,23 @@ cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, bool reverse, int dev
 }
 
 
-// Lines of text (CSR, PIRE_GPU_RUN_LINES, no order): lanes pull lines dynamically.  The caller zeroes the bitmap.
+// Lines of text (CSR, PIRE_GPU_RUN_LINES, no order).  The caller zeroes the bitmap.  In stream (ScanTextKernel) when the
+// start state is a hot row -- it practically always is; lanes pulling lines one by one (ScanLinesKernel) otherwise.
 cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t stream)
 {
     if (a.n == 0)
         return cudaSuccess;
-    const void* fn = variant == kVariantPred ? reinterpret_cast<const void*>(&ScanLinesKernel<true>)
-                                             : reinterpret_cast<const void*>(&ScanLinesKernel<false>);
-    const size_t shared = ScanSharedBytes(a.hot, 0);
+    static const int forced = [] {
+        const char* env = getenv("PIRE_B200_LINES_KERNEL");        // experiments: 1 = pulling lanes, 2 = in stream
+        return env ? atoi(env) : 0;
+    }();
+    const bool in_stream = forced == 2 || (forced != 1 && a.start < a.hot);
+    if (in_stream && !(a.start < a.hot))
+        return cudaErrorInvalidValue;
+    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64;
+    const void* fn = in_stream ? (pred ? reinterpret_cast<const void*>(&ScanTextKernel<true>) : reinterpret_cast<const void*>(&ScanTextKernel<false>))
+                               : (pred ? reinterpret_cast<const void*>(&ScanLinesKernel<true>) : reinterpret_cast<const void*>(&ScanLinesKernel<false>));
+    const size_t shared = ScanSharedBytes(a.hot, 0) + (in_stream ? kTextFinBytes : 0);
     int optin = 0, sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err == cudaSuccess)
@@ -2067,16 +2319,26 @@ cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t
         return err;
     if (per_sm < 1)
         return cudaErrorLaunchOutOfResources;
-    const uint64_t groups = (a.n + kLinesPerWarp - 1) / kLinesPerWarp;
-    const uint64_t want = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int grid = (int) (want < (uint64_t) sms * per_sm ? want : (uint64_t) sms * per_sm);
     ScanArgs tuned = a;
-    tuned.lines_turn = kPiecesPerTurn;
-    tuned.lines_min_idle = kLinesMinIdle;
-    if (const char* env = getenv("PIRE_B200_LINES_TURN"))          // experiments
-        tuned.lines_turn = atoi(env) > 0 ? (uint32_t) atoi(env) : tuned.lines_turn;
-    if (const char* env = getenv("PIRE_B200_LINES_MIN_IDLE"))
-        tuned.lines_min_idle = atoi(env) > 0 ? (uint32_t) atoi(env) : tuned.lines_min_idle;
+    int grid = sms * per_sm;
+    if (in_stream) {
+        tuned.text_segment = kTextSegment;
+        if (const char* env = getenv("PIRE_B200_TEXT_SEGMENT"))       // experiments
+            tuned.text_segment = atoi(env) >= 32 ? (uint32_t) atoi(env) / 32u * 32u : tuned.text_segment;
+        // the number of units depends on the text's size, which only the device knows (offsets[n]): a line has at
+        // least its separator, so n lines span at least n bytes -- enough to keep tiny batches from filling the GPU
+        // with idle CTAs; the kernel's own unit count is exact
+    } else {
+        const uint64_t groups = (a.n + kLinesPerWarp - 1) / kLinesPerWarp;
+        const uint64_t want = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        grid = (int) (want < (uint64_t) grid ? want : (uint64_t) grid);
+        tuned.lines_turn = kPiecesPerTurn;
+        tuned.lines_min_idle = kLinesMinIdle;
+        if (const char* env = getenv("PIRE_B200_LINES_TURN"))          // experiments
+            tuned.lines_turn = atoi(env) > 0 ? (uint32_t) atoi(env) : tuned.lines_turn;
+        if (const char* env = getenv("PIRE_B200_LINES_MIN_IDLE"))
+            tuned.lines_min_idle = atoi(env) > 0 ? (uint32_t) atoi(env) : tuned.lines_min_idle;
+    }
     void* args[] = {&tuned};
     err = cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, shared, stream);
     if (err == cudaSuccess)

@@ -61,6 +61,7 @@ struct ScanArgs {
     uint32_t* counts;            // n * regexps words, zeroed by the caller
     uint32_t lines_turn;         // lines kernel: chunks per lane between two hand-outs of lines
     uint32_t lines_min_idle;     // lines kernel: waiting lanes needed for a hand-out
+    uint32_t text_segment;       // in-stream lines kernel: bytes of text per lane and unit, a multiple of 32
     const uint64_t* weights;     // [states * count_words] packed per-state increments, or null
     uint32_t count_words;        // 0 = walk the accept lists, 1..2 = packed increments
     uint32_t count_always;       // final states are frequent: count every chunk, skip the look-ahead pass

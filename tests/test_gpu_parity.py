@@ -558,6 +558,78 @@ def test_lines_front_end(cuda_device, ref):
     assert one.n == 1 and P.Runner(sc).Begin().Run(one).End().Matches().tolist() == [False]
 
 
+def _text_of(rng, n_lines, ending):
+    words = [b"GET /index", b"timeout", b"error 42", b"ok", b"", b"a timeout", b"$(555) 123-4567", b"fatal", b"https://x", b"hello \t world"]
+    lens = [0, 0, 1, 2, 7, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 100, 200]
+    lines = []
+    for k in range(n_lines):
+        r = rng.random()
+        if r < 0.15:
+            body = b""
+        elif r < 0.25:
+            body = bytes(rng.integers(0x20, 0x7F, size=int(rng.choice(lens)), dtype=np.uint8))
+        else:
+            body = bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(0, 60)), dtype=np.uint8))
+        w = words[int(rng.integers(0, len(words)))] if rng.random() < 0.4 else b""
+        where = rng.random()
+        lines.append(w + body if where < 0.4 else body + w if where < 0.8 else body[: len(body) // 2] + w + body[len(body) // 2:])
+    # lines longer than a segment (1 KiB) and longer than a warp's unit of 32 segments, in the middle and at the end
+    lines[n_lines // 3] = bytes(rng.integers(0x20, 0x7F, size=1500, dtype=np.uint8)) + b"error"
+    lines[n_lines // 2] = bytes(rng.integers(0x20, 0x7F, size=40000, dtype=np.uint8)) + b" timeout"
+    lines[-1] = bytes(rng.integers(0x20, 0x7F, size=5000, dtype=np.uint8))
+    for k in range(n_lines // 4, n_lines // 4 + 50):
+        lines[k] = b""                                             # a run of empty lines: several ends in one chunk
+    return b"\n".join(lines) + ending, lines
+
+
+def test_lines_in_stream(cuda_device, ref):
+    """The in-stream lines kernel (one text segment per lane, the walk restarts behind every newline) against the
+    reference line by line: lengths around the 16/32-byte chunk sizes, runs of empty lines, lines longer than a
+    segment and than a warp's 32 segments, every alignment of the text in memory, with and without a last newline,
+    plain and exit-filter walks, hot sets small enough that lanes leave the hot rows inside lines, and a scanner
+    whose every line matches (atomics on every bitmap word)."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    rng = np.random.default_rng(77)
+    cases = [(ref.glue_all(W.GLUE10), W.load_image("glue10")), ]
+    one = ref.compile(rb"timeout$|^GET |error", "")
+    cases.append((one, one.save()))
+    every = ref.compile(rb".*", "")
+    cases.append((every, every.save()))
+    for sc_ref, image in cases:
+        sc = P.Scanner(image, cuda_device)
+        for ending in (b"\n", b""):
+            text, lines = _text_of(rng, 3000, ending)
+            corpus, o = csr(lines)
+            want = sc_ref.run(corpus, o, variant=0)
+            for shift in (0, 1, 7, 16, 31):
+                buf = torch.zeros(len(text) + 64, dtype=torch.uint8, device="cuda:0")
+                view = buf[shift: shift + len(text)]
+                view.copy_(torch.from_numpy(np.frombuffer(text, np.uint8).copy()))
+                batch = P.Batch.from_text(view)
+                assert batch.n == len(lines)
+                for max_hot in (255, 6, 2):
+                    sc.set_max_hot(max_hot)
+                    for variant in (1, 2):
+                        sc.set_variant(variant)
+                        r = P.Runner(sc).Begin().Run(batch).End()
+                        assert (r.Matches().astype(np.uint8) == want[0]).all(), (shift, max_hot, variant, ending)
+                        assert (r.AcceptMasks() == want[1]).all() and (r.States() == want[2]).all(), (shift, max_hot, variant, ending)
+            sc.set_max_hot(255)
+    # texts of a few bytes
+    sc = P.Scanner(cases[1][1], cuda_device)
+    for text in (b"\n", b"\n\n\n", b"error", b"error\n", b"x\nerror", b"\nGET \n", b"a" * 31 + b"\n" + b"timeout", b"a" * 32 + b"\ntimeout\n"):
+        lines = text.split(b"\n")
+        if text.endswith(b"\n"):
+            lines = lines[:-1]
+        corpus, o = csr(lines)
+        want = cases[1][0].run(corpus, o, variant=0)
+        batch = P.Batch.from_text(torch.from_numpy(np.frombuffer(text, np.uint8).copy()).to("cuda:0"))
+        r = P.Runner(sc).Begin().Run(batch).End()
+        assert batch.n == len(lines) and (r.Matches().astype(np.uint8) == want[0]).all() and (r.States() == want[2]).all(), text
+
+
 def test_half_final_counts_golden(cuda_device):
     """pire_gpu_count_batch against the numbers of count_ut.cpp HalfFinal@553 (committed fixtures)."""
     import pire_b200 as P
