@@ -1020,19 +1020,20 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanLinesKernel(const
 // them is finished.  What makes this cheap:
 //   * the copy of the hot rows in shared memory maps '\n' to the start state in every row (the sink row keeps the
 //     sink), so the walk restarts by itself behind a line: no branch, no second pass over the rest of a chunk;
-//   * the sixteen states of a chunk are packed into four registers as they appear (one IMAD each, FMA pipe), and the
-//     newlines of the chunk are found in its bytes (exact zero-byte test of word ^ 0x0a0a0a0a, compressed to one bit per
-//     byte by a multiply): a lane picks the state in front of each newline out of the packed ones and reports it
-//     through a copy of the hot states' reports in shared memory -- the steady state reads no offsets and has no
-//     dependent global load;
+//   * the thirty-two states of a block are packed into eight registers as they appear (one IMAD each, FMA pipe), and
+//     the newlines of the block are found in its bytes (exact zero-byte test of word ^ 0x0a0a0a0a, compressed to one
+//     bit per byte by a multiply): a lane with newlines parks the packed states in shared memory, picks the state in
+//     front of each newline with one LDS.U8 and reports it through a copy of the hot states' reports in shared memory
+//     -- the steady state reads no offsets and has no dependent global load;
 //   * a lane outside the hot rows at the end of a chunk (the sink is absorbing) replays the chunk byte by byte, line
 //     ends included; so does a lane over the unaligned start of its first line.
 // The offsets must be those of pire_gpu_split_lines for this text: line i + 1 starts right behind the '\n' of line i.
 // They are read once per lane and unit, by the binary search for the first line that starts in the segment; from then
 // on line numbers just count up.  Bytes outside the text read as '\n': that ends a last line without newline.
-constexpr uint32_t kTextSegment = 2048;
+constexpr uint32_t kTextSegment = 4096;
 constexpr int kTextBlocksPerSM = 2;
 constexpr size_t kTextFinBytes = 256 * sizeof(DeviceFin);
+constexpr size_t kTextPackBytes = (size_t) kBlock * 32;     // packed states of one 32-byte block per lane
 
 struct TextLane {
     uint32_t line;       // the line being walked
@@ -1102,42 +1103,55 @@ __device__ __forceinline__ uint32_t NewlineNibble(uint32_t w)
     return (flags * 0x00204081u) >> 28;
 }
 
-// One 16-byte chunk at text position cpos.
+// One 32-byte block at text position cpos.  `packs` = this lane's slot in the warp's staging area for packed states:
+// word w (0..7) of the block's states at packs + (w / 4) * 512 + (w % 4) * 4, so that the two 16-byte stores of a warp
+// are contiguous.
 template <bool kPred>
-__device__ __forceinline__ void TextChunk(const ScanArgs& a, const Tables& t, const DeviceFin* fin_hot, uint32_t outs, TextLane& c,
-                                          LaneState& s, uint4 v, int64_t cpos, uint64_t seg_hi, uint64_t total)
+__device__ __forceinline__ void TextBlock(const ScanArgs& a, const Tables& t, const DeviceFin* fin_hot, uint32_t outs, TextLane& c,
+                                          LaneState& s, uint4 v0, uint4 v1, uint32_t packs, int64_t cpos, uint64_t seg_hi,
+                                          uint64_t total)
 {
     const uint32_t before = s.g;
-    uint32_t g = before, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    TextWord<kPred>(t, g, v.x, q0);
-    TextWord<kPred>(t, g, v.y, q1);
-    TextWord<kPred>(t, g, v.z, q2);
-    TextWord<kPred>(t, g, v.w, q3);
+    uint32_t g = before;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    TextWord<kPred>(t, g, v0.x, q0.x);
+    TextWord<kPred>(t, g, v0.y, q0.y);
+    TextWord<kPred>(t, g, v0.z, q0.z);
+    TextWord<kPred>(t, g, v0.w, q0.w);
+    TextWord<kPred>(t, g, v1.x, q1.x);
+    TextWord<kPred>(t, g, v1.y, q1.y);
+    TextWord<kPred>(t, g, v1.z, q1.z);
+    TextWord<kPred>(t, g, v1.w, q1.w);
     const int32_t left = c.left;
-    c.left = left - 16 > -(1 << 30) ? left - 16 : -(1 << 30);
+    c.left = left - 32 > -(1 << 30) ? left - 32 : -(1 << 30);
     if (!c.active)
         return;
     if (g == t.H) {
-        TextSlow(a, t, fin_hot, outs, c, s, before == t.H ? s.cold : before, cpos, 0, 16, seg_hi, total);
+        // the sink is absorbing (its '\n' entry too): the lane was, or fell, outside the hot rows somewhere in the block
+        TextSlow(a, t, fin_hot, outs, c, s, before == t.H ? s.cold : before, cpos, 0, 32, seg_hi, total);
         return;
     }
     s.g = g;
-    uint32_t ends = NewlineNibble(v.x) | (NewlineNibble(v.y) << 4) | (NewlineNibble(v.z) << 8) | (NewlineNibble(v.w) << 12);
+    uint32_t ends = NewlineNibble(v0.x) | (NewlineNibble(v0.y) << 4) | (NewlineNibble(v0.z) << 8) | (NewlineNibble(v0.w) << 12) |
+                    (NewlineNibble(v1.x) << 16) | (NewlineNibble(v1.y) << 20) | (NewlineNibble(v1.z) << 24) | (NewlineNibble(v1.w) << 28);
+    if (ends == 0)
+        return;
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(packs), "r"(q0.x), "r"(q0.y), "r"(q0.z), "r"(q0.w) : "memory");
+    asm volatile("st.shared.v4.u32 [%0+512], {%1,%2,%3,%4};" ::"r"(packs), "r"(q1.x), "r"(q1.y), "r"(q1.z), "r"(q1.w) : "memory");
     const uint32_t n_lines = (uint32_t) a.n;
-    while (ends) {
+    do {
         const uint32_t k = (uint32_t) __ffs((int) ends) - 1u;
         ends &= ends - 1u;
-        // the state in front of byte k sits in byte 3 - k % 4 of word k / 4
-        const uint32_t sel = (k ^ 3u) & 7u;
-        const uint32_t lo = __byte_perm(q0, q1, sel), hi = __byte_perm(q2, q3, sel);
-        const uint32_t st = ((k & 8u) ? hi : lo) & 0xffu;          // a hot state: the lane is not in the sink
+        // the state in front of byte k: byte 3 - k % 4 of word k / 4 -- a hot state, the lane is not in the sink
+        uint32_t st;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(st) : "r"(packs + ((k & 16u) << 5) + ((k & 15u) ^ 3u)) : "memory");
         TextReport(a, outs, c.line, fin_hot[st]);
         ++c.line;
         if (c.line >= n_lines || (int32_t) k + 1 >= left) {         // the next line starts behind the segment
             c.active = false;
             break;
         }
-    }
+    } while (ends);
 }
 
 // A 16-byte chunk that may stick out of the text at either end: bytes outside read as '\n'.  Out of line, it is rare.
@@ -1189,14 +1203,23 @@ __global__ void __launch_bounds__(kBlock, kTextBlocksPerSM) ScanTextKernel(const
 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t outs = TextOutputs(a);
+    const uint32_t packs = SmemAddr(sv.stage) + (uint32_t) kTextFinBytes + (threadIdx.x >> 5) * 1024u + lane * 16u;
     const uint64_t total = a.offsets[a.n] - 1;           // position of the last separator (real or the end of the text)
     const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
     const uintptr_t buf_hi = buf_lo + total;
     const uint32_t mis0 = (uint32_t) (buf_lo & 31);
-    const uint64_t seg = a.text_segment;
+    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
+    // Segment size: about kTextSegment bytes, chosen so that the units (32 segments) come out as a whole number of
+    // rounds over the grid's warps -- with a couple of units per warp, one unit more or less is a third of the run time.
+    uint64_t seg = a.text_segment;
+    if (seg == 0) {
+        const uint64_t lanes = 32 * warps;
+        const uint64_t rounds = (total + 64 + lanes * kTextSegment - 1) / (lanes * kTextSegment);
+        seg = ((total + 64 + lanes * rounds - 1) / (lanes * rounds) + 31) / 32 * 32;
+        seg = seg < 64 ? 64 : seg;
+    }
     const uint64_t segments = (total + mis0) / seg + 1;
     const uint64_t units = (segments + 31) / 32;
-    const uint64_t warps = (uint64_t) gridDim.x * kWarpsPerBlock;
 
     for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); unit < units; unit += warps) {
         const uint64_t sidx = unit * 32 + lane;
@@ -1244,8 +1267,7 @@ __global__ void __launch_bounds__(kBlock, kTextBlocksPerSM) ScanTextKernel(const
             uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
             if (c.active)
                 LoadBlock32(p + 32, buf_lo, buf_hi, n0, n1);
-            TextChunk<kPred>(a, t, fin_hot, outs, c, s, v0, pos, seg_hi, total);
-            TextChunk<kPred>(a, t, fin_hot, outs, c, s, v1, pos + 16, seg_hi, total);
+            TextBlock<kPred>(a, t, fin_hot, outs, c, s, v0, v1, packs, pos, seg_hi, total);
             v0 = n0;
             v1 = n1;
             p += 32;
@@ -2306,7 +2328,7 @@ cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t
     const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64;
     const void* fn = in_stream ? (pred ? reinterpret_cast<const void*>(&ScanTextKernel<true>) : reinterpret_cast<const void*>(&ScanTextKernel<false>))
                                : (pred ? reinterpret_cast<const void*>(&ScanLinesKernel<true>) : reinterpret_cast<const void*>(&ScanLinesKernel<false>));
-    const size_t shared = ScanSharedBytes(a.hot, 0) + (in_stream ? kTextFinBytes : 0);
+    const size_t shared = ScanSharedBytes(a.hot, 0) + (in_stream ? kTextFinBytes + kTextPackBytes : 0);
     int optin = 0, sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err == cudaSuccess)
@@ -2322,12 +2344,11 @@ cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t
     ScanArgs tuned = a;
     int grid = sms * per_sm;
     if (in_stream) {
-        tuned.text_segment = kTextSegment;
+        tuned.text_segment = 0;                                        // chosen on the device from the text's size
         if (const char* env = getenv("PIRE_B200_TEXT_SEGMENT"))       // experiments
-            tuned.text_segment = atoi(env) >= 32 ? (uint32_t) atoi(env) / 32u * 32u : tuned.text_segment;
-        // the number of units depends on the text's size, which only the device knows (offsets[n]): a line has at
-        // least its separator, so n lines span at least n bytes -- enough to keep tiny batches from filling the GPU
-        // with idle CTAs; the kernel's own unit count is exact
+            tuned.text_segment = atoi(env) >= 32 && atoi(env) <= (1 << 20) ? (uint32_t) atoi(env) / 32u * 32u : tuned.text_segment;
+        // the persistent grid is launched whole: the number of units depends on the text's size, which only the device
+        // knows (offsets[n]); warps without a unit leave at once
     } else {
         const uint64_t groups = (a.n + kLinesPerWarp - 1) / kLinesPerWarp;
         const uint64_t want = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
