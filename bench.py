@@ -460,7 +460,11 @@ class Resident:
 
     def kernel_name(self):
         if self.mixed:
-            return "ScanGenericKernel<%s>" % ("plain" if self.chosen == "plain" else "pred")
+            mode = {"plain": "plain", "look": "look", "look64": "look"}.get(self.chosen, "pred")
+            if os.environ.get("PIRE_B200_SPLIT", "1") == "0":
+                return "ScanGenericKernel<%s>" % mode
+            return "ScanSplitKernel<%s> (strings >= 8 KiB, one per warp) + ScanGenericKernel<%s> (the rest)" % (
+                "plain" if mode == "plain" else "pred", mode)
         return {"priv": "ScanUniformPrivKernel", "look": "ScanUniformLookKernel<32 slots>",
                 "look64": "ScanUniformLookKernel<64 slots>"}.get(self.chosen, "ScanUniformKernel<%s>" % self.chosen)
 

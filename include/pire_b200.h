@@ -197,8 +197,11 @@ int pire_gpu_count_batch(const pire_gpu_scanner* sc,
  *   newline is kept, an empty text has no lines (std::getline semantics).
  *   If capacity is too small (or d_line_offsets is NULL) nothing is written, *n_lines
  *   receives a sufficient capacity and PIRE_GPU_EINVAL is returned.  Synchronises `stream`.
- * pire_gpu_run_lines scans those lines (optionally length-binned via d_order, see
- * pire_gpu_length_order; may be NULL); outputs as in pire_gpu_run_batch. */
+ * pire_gpu_run_lines scans those lines; outputs as in pire_gpu_run_batch.  d_line_offsets must be the offsets
+ *   pire_gpu_split_lines produced for d_text: without d_order the lines are scanned where they lie -- every lane
+ *   walks a few KiB of the text and restarts behind each newline it meets -- so line i + 1 has to start right behind the
+ *   newline that ends line i.  With d_order (pire_gpu_length_order; usually slower for lines) they are scanned one
+ *   string per lane like any CSR batch. */
 int pire_gpu_split_lines(const uint8_t* d_text, uint64_t n_bytes, uint64_t* d_line_offsets, uint64_t capacity,
                          uint64_t* n_lines, int device, void* stream);
 int pire_gpu_run_lines(const pire_gpu_scanner* sc, const uint8_t* d_text, const uint64_t* d_line_offsets,

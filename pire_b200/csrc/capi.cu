@@ -509,17 +509,29 @@ static int RunCsr(const pire_gpu_scanner* sc, const uint8_t* d_corpus, const uin
     a.state_idx = d_state_idx;
     unsigned int* counter = nullptr;
     cudaError_t ce = cudaSuccess;
+    static const bool split_long = [] {
+        const char* env = getenv("PIRE_B200_SPLIT");              // experiments: 0 = long strings stay one per lane
+        return !(env && env[0] == '0');
+    }();
+    const bool split = d_order && split_long && !(flags & PIRE_GPU_RUN_LINES);
     if (d_order) {
-        // length-binned: units are claimed longest-first, match bits are OR-ed into a zeroed bitmap
-        CUDA_TRY(ScratchAlloc(reinterpret_cast<void**>(&counter), sizeof(unsigned int), st));
-        ce = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+        // length-binned: units are claimed longest-first, match bits are OR-ed into a zeroed bitmap; three words:
+        // the generic kernel's unit counter, the split kernel's string counter, the number of strings it owns
+        CUDA_TRY(ScratchAlloc(reinterpret_cast<void**>(&counter), 4 * sizeof(unsigned int), st));
+        ce = cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned int), st);
         if (ce == cudaSuccess && d_match_bits)
             ce = cudaMemsetAsync(d_match_bits, 0, (size_t) ((n + 31) / 32) * 4, st);
         a.work_counter = counter;
+        if (split) {
+            a.split_counter = counter + 1;
+            a.split_count = counter + 2;
+        }
     }
     uint32_t variant = ResolveVariant(sc, false);
     if (variant == PIRE_GPU_VARIANT_PRIV)
         variant = PIRE_GPU_VARIANT_PLAIN;
+    if (split && ce == cudaSuccess)
+        ce = LaunchSplit(a, (int) variant, sc->device, st);       // the long strings, one per warp; the rest below
     static const bool lines_kernel = [] {
         const char* env = getenv("PIRE_B200_LINES_KERNEL");       // experiments: 0 = lines go through the generic kernel
         return !(env && env[0] == '0');

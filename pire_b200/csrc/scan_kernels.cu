@@ -802,6 +802,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     // [buf_lo, buf_hi): the caller's corpus buffer; whole aligned chunks may be read inside it only
     const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
     const uintptr_t buf_hi = buf_lo + (a.offsets ? a.offsets[a.n] - a.trim : a.n * a.fixed_len);
+    const uint64_t split_first = a.split_count ? *a.split_count : 0;
 
     for (uint64_t unit = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);; unit += warps) {
         if (a.work_counter) {
@@ -815,7 +816,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
         if (unit >= units)
             break;
         const uint64_t slot = unit * 32 + lane;
-        const bool valid = slot < a.n;
+        const bool valid = slot < a.n && slot >= split_first;          // the first split_first entries are the split kernel's
         const uint64_t i = valid && a.order ? a.order[slot] : slot;
         uint64_t b = 0, e = 0;
         if (valid) {
@@ -910,6 +911,215 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
         else
             Report(a, t, s, unit, i, valid);
     }
+}
+
+// ---------------------------------------------------------------- long strings, split over a warp
+//
+// One string per lane makes the longest string of a batch the critical path: a 64 KiB string is 65 536 dependent
+// table reads, 3.7 ms at the 110 cycles a step takes a warp that shares its SM with 31 others -- as long as the whole
+// mixed-length benchmark batch.  Here a WARP owns one long string: lane j walks piece j of 32 (whole 32-byte blocks,
+// LDG.256 one block ahead), lane 0 from the string's true state, the others from a guess (hot id 0, the most visited
+// state).  Every lane leaves marks -- its hot id after every K blocks, in shared memory.  Then the pieces are stitched:
+// lane j's true start is lane j-1's end; a lane whose walk started from another state re-walks its piece from the true
+// one until it meets a mark (same hot id at the same position: the rest of the walk is the recorded one), replacing the
+// marks it passes.  Two walks over the same bytes fall together within a few bytes for the automata regexps make (a
+// byte that continues no match sends every state to the resting state), so a round of re-walks costs about K blocks;
+// the loop repeats until every lane's start equals its predecessor's end, which is exact whatever the automaton does:
+// lane 0 is exact, and lane j is exact one round after lane j-1 at the latest (31 rounds of a whole piece each in the
+// worst case -- the serial walk).  A true start that is a NoExit state needs no walk at all.
+constexpr uint32_t kSplitMin = 8192;            // bytes; a bucket boundary of LengthOrder
+constexpr uint32_t kSplitMarks = 32;            // marks per lane
+constexpr size_t kSplitMarkBytes = (size_t) kBlock * kSplitMarks;
+
+__device__ __forceinline__ uint64_t EndOffset(const ScanArgs& a, uint64_t i)
+{
+    const uint64_t b = a.offsets[i], e = a.offsets[i + 1] - a.trim;
+    return e < b ? b : e;
+}
+
+template <bool kPred>
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanSplitKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.exit_bitmap0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    // mark m of lane l at marks[m * 32 + l]: the lanes of a warp write one mark with one conflict-free store
+    uint8_t* const marks = sv.stage + (threadIdx.x >> 5) * (32 * kSplitMarks) + lane;
+    volatile uint64_t* const parked = reinterpret_cast<volatile uint64_t*>(sv.stage + kSplitMarkBytes) + (threadIdx.x >> 5) * 4;
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(a.corpus);
+    const uintptr_t buf_hi = buf_lo + (a.offsets[a.n] - a.trim);
+    const uint32_t n_long = *a.split_count;
+
+    for (;;) {
+        unsigned int slot = 0;
+        if (lane == 0)
+            slot = atomicAdd(a.split_counter, 1u);         // longest strings first
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= n_long)
+            break;
+        const uint64_t i = a.order[slot];
+        const uint8_t* p = a.corpus + a.offsets[i];
+        const uint8_t* const end = a.corpus + EndOffset(a, i);
+
+        // head, by every lane alike: to the first 32-byte boundary
+        LaneState s;
+        SetFull(t, s, a.start);
+        {
+            const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(p) & 15);
+            if (p < end && mis != 0) {
+                const uint64_t room = (uint64_t) (end - p);
+                const uint32_t nhead = room < 16 - mis ? (uint32_t) room : 16 - mis;
+                EdgeFast<kPred>(t, s, EdgeBytes(LoadChunk16(p - mis, buf_lo, buf_hi), mis).Words(), nhead);
+                p += nhead;
+            }
+            if ((reinterpret_cast<uintptr_t>(p) & 16) && end - p >= 16) {
+                Chunk16<kPred>(t, s, LoadEdge16(p));
+                p += 16;
+            }
+        }
+        const uint32_t blocks_total = (reinterpret_cast<uintptr_t>(p) & 31) ? 0u : (uint32_t) ((end - p) >> 5);
+        const uint32_t base = blocks_total / 32, rem = blocks_total % 32;
+        const uint32_t my_blocks = base + (lane < rem ? 1u : 0u);
+        const uint32_t my_first = lane * base + (lane < rem ? lane : rem);
+        const uint32_t trips = base + (rem ? 1u : 0u);                    // the longest piece
+        const uint32_t per_mark = (trips + kSplitMarks - 1) / kSplitMarks;   // K: blocks between two marks (0 only if trips == 0)
+        const uint8_t* const piece = p + 32 * (size_t) my_first;
+
+        // the string's bounds wait in shared memory while the pieces are walked: they are the same in every lane and not
+        // needed in the loop, which is short of registers (ptxas spilled the loop counter instead)
+        if (lane == 0) {
+            parked[0] = i;
+            parked[1] = reinterpret_cast<uint64_t>(p + 32 * (size_t) blocks_total);
+            parked[2] = reinterpret_cast<uint64_t>(end);
+        }
+        __syncwarp();
+
+        // the pieces, all at once: lane 0 from the string's state, the others from the guess.  Every lane runs the loop
+        // `trips` times, so that the scheduling fences behind the loads are reached by the whole warp.  The loads ask for
+        // the whole 256-byte line in L2: a piece is contiguous, seven of eight blocks then come from there.
+        uint32_t start_full = lane == 0 ? FullState(t, s) : 0u;
+        SetFull(t, s, start_full);
+        {
+            uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+            if (my_blocks)
+                LoadStream32P(piece, a0, a1);
+            uint32_t countdown = per_mark, m = 0;
+            for (uint32_t k = 0; k < trips; k += 2) {
+                if (k + 1 < my_blocks)
+                    LoadStream32P(piece + 32 * (size_t) (k + 1), b0, b1);
+                __syncwarp();              // scheduling fence: the load is issued here, not next to its first use
+                if (k < my_blocks) {
+                    Chunk16<kPred>(t, s, a0);
+                    Chunk16<kPred>(t, s, a1);
+                    if (--countdown == 0) {
+                        marks[32 * m++] = (uint8_t) s.g;
+                        countdown = per_mark;
+                    }
+                }
+                if (k + 2 < my_blocks)
+                    LoadStream32P(piece + 32 * (size_t) (k + 2), a0, a1);
+                __syncwarp();
+                if (k + 1 < my_blocks) {
+                    Chunk16<kPred>(t, s, b0);
+                    Chunk16<kPred>(t, s, b1);
+                    if (--countdown == 0) {
+                        marks[32 * m++] = (uint8_t) s.g;
+                        countdown = per_mark;
+                    }
+                }
+            }
+        }
+        uint32_t end_full = FullState(t, s);
+
+        // stitch: every lane must have started where its predecessor ended
+        for (;;) {
+            const uint32_t before = __shfl_up_sync(0xffffffffu, end_full, 1);
+            const uint32_t want = lane == 0 ? start_full : before;
+            const bool redo = want != start_full;
+            if (!__any_sync(0xffffffffu, redo))
+                break;
+            if (redo) {
+                start_full = want;
+                const uint32_t n_marks = per_mark ? my_blocks / per_mark : 0u;
+                if (want < t.H && sv.noexit[want] != 0) {
+                    // multi.h:955-958: no byte leaves this state
+                    end_full = want;
+                    for (uint32_t m = 0; m < n_marks; ++m)
+                        marks[32 * m] = (uint8_t) want;
+                } else {
+                    // the piece again from the true state, until the walk meets a mark (same hot id at the same place:
+                    // from there on it is the recorded walk, and so is its end); marks passed on the way are replaced,
+                    // so that they describe this walk afterwards
+                    LaneState r;
+                    SetFull(t, r, want);
+                    uint32_t countdown = per_mark, m = 0;
+                    bool met = false;
+                    for (uint32_t k = 0; k < my_blocks; ++k) {
+                        uint4 v0, v1;
+                        LoadStream32P(piece + 32 * (size_t) k, v0, v1);
+                        Chunk16<kPred>(t, r, v0);
+                        Chunk16<kPred>(t, r, v1);
+                        if (--countdown == 0) {
+                            if (r.g != t.H && r.g == marks[32 * m]) {
+                                met = true;
+                                break;
+                            }
+                            marks[32 * m++] = (uint8_t) r.g;
+                            countdown = per_mark;
+                        }
+                    }
+                    if (!met)
+                        end_full = FullState(t, r);
+                }
+            }
+        }
+
+        // tail, by every lane alike, from the last piece's end
+        SetFull(t, s, __shfl_sync(0xffffffffu, end_full, 31));
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(parked[1]);
+        const uint8_t* const q_end = reinterpret_cast<const uint8_t*>(parked[2]);
+        if (q_end - q >= 16) {
+            Chunk16<kPred>(t, s, LoadEdge16(q));
+            q += 16;
+        }
+        if (q < q_end)
+            EdgeFast<kPred>(t, s, LoadChunk16(q, buf_lo, buf_hi), (uint32_t) (q_end - q));
+        ReportScattered(a, t, s, parked[0], lane == 0);
+        __syncwarp();                      // the next string's bounds replace these
+    }
+}
+
+// n_long = the number of leading entries of `order` whose strings are at least kSplitMin bytes long (LengthOrder puts the
+// longest buckets first, so this is all of them; for any other permutation it is just some prefix, and the split kernel
+// is exact for strings of any length).  Also resets the split kernel's work counter.
+__global__ void SplitCountKernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ order, uint64_t n,
+                                 uint32_t split_min, uint32_t* __restrict__ count, unsigned int* __restrict__ counter)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        const uint64_t i = order[mid];
+        if (offsets[i + 1] - offsets[i] >= split_min)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    *count = (uint32_t) lo;
+    *counter = 0;
 }
 
 // ---------------------------------------------------------------- lines of text
@@ -2280,6 +2490,43 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
     void* args[] = {const_cast<ScanArgs*>(&a)};
     cudaError_t err = cudaLaunchKernel(KernelFor(variant, uniform), dim3(grid), dim3(plan.block), args, plan.shared, stream);
+    if (err == cudaSuccess)
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    return err;
+}
+
+// Length-ordered CSR batch: the leading long strings, one per warp (ScanSplitKernel).  a.split_count / a.split_counter
+// are two device words; the generic kernel launched afterwards with the same a.split_count skips those strings.
+cudaError_t LaunchSplit(const ScanArgs& a, int variant, int device, cudaStream_t stream)
+{
+    if (a.n == 0)
+        return cudaSuccess;
+    static const uint32_t split_min = [] {
+        const char* env = getenv("PIRE_B200_SPLIT_MIN");          // experiments; a power of two keeps it a bucket boundary
+        return env && atoi(env) >= 64 ? (uint32_t) atoi(env) : kSplitMin;
+    }();
+    SplitCountKernel<<<1, 32, 0, stream>>>(a.offsets, a.order, a.n, split_min, const_cast<uint32_t*>(a.split_count), a.split_counter);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return err;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const void* fn = variant == kVariantPlain ? reinterpret_cast<const void*>(&ScanSplitKernel<false>)
+                                              : reinterpret_cast<const void*>(&ScanSplitKernel<true>);
+    const size_t shared = ScanSharedBytes(a.hot, 0) + kSplitMarkBytes + kWarpsPerBlock * 32;
+    int optin = 0, sms = 0, per_sm = 0;
+    err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (err == cudaSuccess)
+        err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (err == cudaSuccess)
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, shared);
+    if (err != cudaSuccess)
+        return err;
+    if (per_sm < 1)
+        return cudaErrorLaunchOutOfResources;
+    void* args[] = {const_cast<ScanArgs*>(&a)};
+    err = cudaLaunchKernel(fn, dim3(sms * per_sm), dim3(kBlock), args, shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);
     return err;

@@ -22,6 +22,8 @@ struct ScanArgs {
     uint32_t trim;               // CSR only: bytes dropped from the end of every string (1 = the newline of a line)
     const uint32_t* order;       // generic kernel: lane i scans string order[i] (length-binned launch), or nullptr
     unsigned int* work_counter;  // with `order`: units are claimed longest-first from this counter
+    const uint32_t* split_count; // with `order`, or null: the first *split_count entries of `order` belong to the split kernel
+    unsigned int* split_counter; // split kernel: strings are claimed from this counter
     uint64_t fixed_len;          // used when offsets == nullptr
     uint64_t n;                  // strings
     const uint8_t* hot8;         // HotTableBytes(hot) bytes (rows kHotStride apart), 16-byte aligned
@@ -82,6 +84,8 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 // CSR batches of short strings (lines of text): lanes pull strings dynamically; a.match_bits must be zeroed
 cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t stream);
+// length-ordered CSR batches: the leading long strings, one per warp; sets *a.split_count, which the generic launch honours
+cudaError_t LaunchSplit(const ScanArgs& a, int variant, int device, cudaStream_t stream);
 cudaError_t LaunchVisitCount(const ScanArgs& a, cudaStream_t stream);
 // prefix (left to right) or suffix (right to left) scan; a.with_begin/begin_class name the mark stepped first,
 // a.through_end/end_class the mark stepped last

@@ -630,6 +630,67 @@ def test_lines_in_stream(cuda_device, ref):
         assert batch.n == len(lines) and (r.Matches().astype(np.uint8) == want[0]).all() and (r.States() == want[2]).all(), text
 
 
+def test_long_strings_split_over_a_warp(cuda_device, ref):
+    """Length-ordered batches hand strings of 8 KiB and more to the split kernel: 32 lanes walk 32 pieces of one string
+    from guessed states and stitch them.  Against the reference: lengths around the threshold and the piece sizes,
+    every start alignment class, planted matches on piece boundaries, automata whose walks fall together (searches),
+    one that needs eleven bytes to do so (a shift register) and one whose walks never do (parity of a run of a's: the
+    stitching degenerates to the serial walk and must still be exact), absorbing accept states (NoExit short cut),
+    small hot sets (pieces that leave the hot rows), plain and filtered walks, short strings in the same batch."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import workloads as W
+    rng = np.random.default_rng(4242)
+    lens = [8191, 8192, 8193, 8192 + 31, 8192 + 32, 9000, 12345, 16384, 20000, 32 * 1024 - 1, 32 * 1024, 40000, 65536, 70001, 131072 + 17]
+    cases = [
+        (ref.glue_all(W.GLUE10), W.load_image("glue10"), bytes(range(0x20, 0x7F)), [p.lstrip(b"^$") for p in W.GLUE10_PLANTS]),
+        (None, (rb"(a|b)*a(a|b)(a|b)(a|b)(a|b)(a|b)(a|b)(a|b)(a|b)(a|b)(a|b)", "n"), b"ab", [b"a"]),
+        (None, (rb"^(aa)*$", "n"), b"a", [b"a"]),
+        (None, (rb"timeout$|^GET |error", ""), b"abcdefg hijk", [b"error", b"timeout", b"GET "]),
+    ]
+    for sc_ref, image, alphabet, plants in cases:
+        if sc_ref is None:
+            sc_ref = ref.compile(*image)
+            image = sc_ref.save()
+        sc = P.Scanner(image, cuda_device)
+        strs = []
+        for k, n in enumerate(lens):
+            row = rng.choice(np.frombuffer(alphabet, np.uint8), size=n)
+            if k % 3 != 2:
+                for j in range(1 + k % 4):
+                    lit = np.frombuffer(plants[(k + j) % len(plants)], np.uint8)
+                    piece = (n // 32) // 32 * 32                        # a piece of the split is about this long
+                    at = min(n - len(lit), max(0, (j + 1) * piece * (3 + k % 5) - len(lit) // 2))
+                    row[at:at + len(lit)] = lit                          # straddles a piece boundary
+            strs.append(bytes(row))
+            strs.append(bytes(rng.choice(np.frombuffer(alphabet, np.uint8), size=int(rng.integers(0, 300)))))
+        strs += [b"", plants[0], bytes(rng.choice(np.frombuffer(alphabet, np.uint8), size=8192 * 3))]
+        # odd gaps between the strings put them on every alignment
+        pad = [bytes(int(rng.integers(0, 32))) for _ in strs]
+        blob = b"".join(p_ + s_ for p_, s_ in zip(pad, strs))
+        offs = np.zeros(2 * len(strs) + 1, np.int64)
+        np.cumsum([len(x) for pair in zip(pad, strs) for x in pair], out=offs[1:])
+        corpus, o = csr([x for pair in zip(pad, strs) for x in pair])
+        want = sc_ref.run(corpus, o, variant=0)
+        dev = torch.from_numpy(np.frombuffer(blob + bytes(64), np.uint8).copy()).to("cuda:0")
+        batch = P.Batch(dev, torch.from_numpy(offs).to("cuda:0"), n=len(offs) - 1)
+        batch.bin_by_length()
+        for max_hot in (255, 6, 2):
+            sc.set_max_hot(max_hot)
+            for variant in (1, 2, 4):
+                sc.set_variant(variant)
+                for begin, end in ((True, True), (False, False)):
+                    r = P.Runner(sc)
+                    if begin:
+                        r = r.Begin()
+                    r = r.Run(batch)
+                    if end:
+                        r = r.End()
+                    w = want if (begin and end) else sc_ref.run(corpus, o, variant=0, begin=begin, end=end)
+                    assert (r.Matches().astype(np.uint8) == w[0]).all(), (image[:8], max_hot, variant, begin, end)
+                    assert (r.AcceptMasks() == w[1]).all() and (r.States() == w[2]).all(), (image[:8], max_hot, variant, begin, end)
+
+
 def test_half_final_counts_golden(cuda_device):
     """pire_gpu_count_batch against the numbers of count_ut.cpp HalfFinal@553 (committed fixtures)."""
     import pire_b200 as P
