@@ -465,9 +465,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 //              Printable text folds 3:1 onto 32 slots but only 3:2 onto 64 (model: 1.72 -> 1.42 wavefronts per step).
 struct LookFilter {
     uint32_t lo, hi;
+    uint32_t zero;      // a kernel argument that is always 0: the addend that keeps the cleaning multiply an IMAD
 };
 
-template <bool k64, int kByte>
+// kClean: the probe's bit is moved to bit 31 with the bits below it cleared by one multiply (IMAD, FMA pipe: pa * 2^31
+// keeps bit 0 only), so that "both bytes pass, or the lane is outside id 0" is ONE LOP3 with a predicate result over
+// (pa, pa_next, g) instead of two: the step keeps six instructions, but two instead of three of them are on the
+// half-rate ALU pipe that ncu shows 66 % busy under the look-ahead kernel.
+template <bool k64, int kByte, bool kClean = false>
 __device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, const LookFilter& f, uint32_t& bb, uint32_t& pa)
 {
     constexpr uint32_t sel = 1u << (8 * kByte);
@@ -478,10 +483,27 @@ __device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, const LookF
     } else {
         pa = __funnelshift_r(f.lo, f.lo, bb);
     }
+    if (kClean)
+        asm("mad.lo.u32 %0, %1, 0x80000000, %2;" : "=r"(pa) : "r"(pa), "r"(f.zero));
 }
 
+template <bool kClean = false>
 __device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, uint32_t pa_next)
 {
+    if (kClean) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, addr;\n"
+            "lop3.b32 t, %1, %2, %0, 0xEA;\n"          // (pa & pa_next) | g
+            "setp.ne.u32 p, t, 0;\n"
+            "mad.lo.u32 addr, %0, %4, %3;\n"
+            "@p ld.shared.u8 %0, [addr];\n"
+            "}\n"
+            : "+r"(g)
+            : "r"(pa), "r"(pa_next), "r"(bb), "n"(kHotStride));
+        return;
+    }
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -499,18 +521,18 @@ __device__ __forceinline__ void LookStep(uint32_t& g, uint32_t bb, uint32_t pa, 
 // Four bytes.  (bb0, pa0) belong to byte 0 of `w` and were computed by the previous call; pan is the probe of the
 // byte that follows the word.  (Looking ahead from the even bytes only -- half a LOP3 less per byte, 1.91 instead of
 // 1.72 wavefronts per step in the model -- measured slower, 2.67 vs 2.63 ms: profiles/r02_experiments_notes.txt.)
-template <bool k64>
+template <bool k64, bool kClean = false>
 __device__ __forceinline__ void LookWord(uint32_t& g, uint32_t w, uint32_t bb0, uint32_t pa0, uint32_t pan, uint32_t base,
                                          const LookFilter& f)
 {
     uint32_t bb1, bb2, bb3, pa1, pa2, pa3;
-    LookProbe<k64, 1>(w, base, f, bb1, pa1);
-    LookProbe<k64, 2>(w, base, f, bb2, pa2);
-    LookProbe<k64, 3>(w, base, f, bb3, pa3);
-    LookStep(g, bb0, pa0, pa1);
-    LookStep(g, bb1, pa1, pa2);
-    LookStep(g, bb2, pa2, pa3);
-    LookStep(g, bb3, pa3, pan);
+    LookProbe<k64, 1, kClean>(w, base, f, bb1, pa1);
+    LookProbe<k64, 2, kClean>(w, base, f, bb2, pa2);
+    LookProbe<k64, 3, kClean>(w, base, f, bb3, pa3);
+    LookStep<kClean>(g, bb0, pa0, pa1);
+    LookStep<kClean>(g, bb1, pa1, pa2);
+    LookStep<kClean>(g, bb2, pa2, pa3);
+    LookStep<kClean>(g, bb3, pa3, pan);
 }
 
 // Shared-window address of the dynamic shared memory array, as a link-time constant (a cvta of a generic pointer
@@ -537,35 +559,35 @@ __device__ __noinline__ uint32_t ReplayBlock32(const ScanArgs* a, uint32_t from,
     return ReplayChunk(sv.hot, sv.cls, a->full, a->hot, letters_wide, mid, v1);
 }
 
-template <bool k64>
+template <bool k64, bool kClean = false>
 __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32_t& prev, const uint4& v0, const uint4& v1,
                                             uint32_t next0, bool more, const LookFilter& f, uint32_t opaque_zero, const ScanArgs* args)
 {
     prev = g == t.H ? prev : g;
     uint32_t bb, pa, bn, pn;
-    LookProbe<k64, 0>(v0.x, t.base, f, bb, pa);
-    LookProbe<k64, 0>(v0.y, t.base, f, bn, pn);
-    LookWord<k64>(g, v0.x, bb, pa, pn, t.base, f);
-    LookProbe<k64, 0>(v0.z, t.base, f, bb, pa);
-    LookWord<k64>(g, v0.y, bn, pn, pa, t.base, f);
-    LookProbe<k64, 0>(v0.w, t.base, f, bn, pn);
-    LookWord<k64>(g, v0.z, bb, pa, pn, t.base, f);
-    LookProbe<k64, 0>(v1.x, t.base, f, bb, pa);
-    LookWord<k64>(g, v0.w, bn, pn, pa, t.base, f);
-    LookProbe<k64, 0>(v1.y, t.base, f, bn, pn);
-    LookWord<k64>(g, v1.x, bb, pa, pn, t.base, f);
-    LookProbe<k64, 0>(v1.z, t.base, f, bb, pa);
-    LookWord<k64>(g, v1.y, bn, pn, pa, t.base, f);
-    LookProbe<k64, 0>(v1.w, t.base, f, bn, pn);
-    LookWord<k64>(g, v1.z, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0, kClean>(v0.x, t.base, f, bb, pa);
+    LookProbe<k64, 0, kClean>(v0.y, t.base, f, bn, pn);
+    LookWord<k64, kClean>(g, v0.x, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0, kClean>(v0.z, t.base, f, bb, pa);
+    LookWord<k64, kClean>(g, v0.y, bn, pn, pa, t.base, f);
+    LookProbe<k64, 0, kClean>(v0.w, t.base, f, bn, pn);
+    LookWord<k64, kClean>(g, v0.z, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0, kClean>(v1.x, t.base, f, bb, pa);
+    LookWord<k64, kClean>(g, v0.w, bn, pn, pa, t.base, f);
+    LookProbe<k64, 0, kClean>(v1.y, t.base, f, bn, pn);
+    LookWord<k64, kClean>(g, v1.x, bb, pa, pn, t.base, f);
+    LookProbe<k64, 0, kClean>(v1.z, t.base, f, bb, pa);
+    LookWord<k64, kClean>(g, v1.y, bn, pn, pa, t.base, f);
+    LookProbe<k64, 0, kClean>(v1.w, t.base, f, bn, pn);
+    LookWord<k64, kClean>(g, v1.z, bb, pa, pn, t.base, f);
     // The word after the block was requested from HBM when this block began: its probe must stay down here (an
     // ordinary intrinsic is hoisted to the top of the block by the compiler, where it waits for the whole DRAM
     // latency -- ncu: 10 % of all stall samples on that one IDP).
     // (a volatile mov is not enough: ptxas schedules across it.  The word is made to depend on the walk itself --
     // plus g times a kernel argument that is always zero -- which costs one IMAD per block.)
     const uint32_t late = next0 + g * opaque_zero;
-    LookProbe<k64, 0>(late, t.base, f, bb, pa);
-    LookWord<k64>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
+    LookProbe<k64, 0, kClean>(late, t.base, f, bb, pa);
+    LookWord<k64, kClean>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
     if (g == t.H) {
         prev = ReplayBlock32(args, prev, v0, v1);
         g = prev < t.H ? prev : t.H;
@@ -579,7 +601,7 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
 constexpr int kLookBlock40 = 512;
 constexpr int kLookBlock48 = 384;
 
-template <bool k64, int kRegs>
+template <bool k64, int kRegs, bool kClean = false>
 __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
@@ -598,6 +620,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
     LookFilter f;
     f.lo = k64 ? (uint32_t) a.look_bitmap64 : a.look_bitmap;
     f.hi = (uint32_t) (a.look_bitmap64 >> 32);
+    f.zero = a.opaque_zero;
 
     const uint32_t units = (uint32_t) ((a.n + 31) / 32);            // pire_gpu_run_batch keeps n <= 2^40: units below 2^32
     const uint32_t warps_per_block = blockDim.x >> 5;
@@ -622,7 +645,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     if (more_b)
                         LoadStream32(p, b0, b1);
                     __syncwarp();          // see below
-                    LookBlock32<k64>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
+                    LookBlock32<k64, kClean>(t, g, prev, a0, a1, b0.x, more_b, f, a.opaque_zero, &a);
                     if (!more_b)
                         break;
                     const bool more_a = left > 2;
@@ -634,7 +657,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
                     // the block's end instead of 32), which exposes most of a DRAM round trip per block (ncu: 14 % of all
                     // stall samples were long-scoreboard waits on the first use of the loaded word).
                     __syncwarp();
-                    LookBlock32<k64>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
+                    LookBlock32<k64, kClean>(t, g, prev, b0, b1, a0.x, more_a, f, a.opaque_zero, &a);
                     left -= 2;
                     // multi.h:955-958,:979-982 (NoExit), looked at every 64 bytes here
                     if (!more_a || __all_sync(0xffffffffu, sv.noexit[g] != 0))
@@ -779,6 +802,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     LookFilter look;
     look.lo = a.look_bitmap;
     look.hi = 0;
+    look.zero = 0;
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv, a.hot8, a.hot);
@@ -2414,10 +2438,23 @@ int LookRegs()
     return regs;
 }
 
+// PIRE_B200_LOOK_CLEAN=0 restores the two-LOP3 step of the look-ahead kernel (see LookProbe) for comparison.
+bool LookClean()
+{
+    static const bool clean = [] {
+        const char* env = getenv("PIRE_B200_LOOK_CLEAN");
+        return !(env && atoi(env) == 0);
+    }();
+    return clean;
+}
+
 const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
+    if (variant == kVariantLook && uniform && LookClean())
+        return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, true>)
+                                : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, true>);
     if (variant == kVariantLook && uniform)
         return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48>)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40>);
@@ -2464,6 +2501,14 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
 {
     const bool priv = variant == kVariantPriv && uniform;
     plan->block = priv ? kPrivBlock : ((variant == kVariantLook || variant == kVariantLook64) && uniform) ? (LookRegs() == 48 ? kLookBlock48 : kLookBlock40) : kBlock;
+    if ((variant == kVariantLook || variant == kVariantLook64) && uniform) {
+        static const int look_block = [] {
+            const char* env = getenv("PIRE_B200_LOOK_BLOCK");          // experiments: e.g. 640 = two CTAs of 20 warps at 48 registers
+            return env && atoi(env) >= 32 && atoi(env) <= 1024 && atoi(env) % 32 == 0 ? atoi(env) : 0;
+        }();
+        if (look_block)
+            plan->block = look_block;
+    }
     plan->shared = priv ? ScanSharedBytes(hot_small, priv_rows) : uniform ? ScanSharedBytes(hot, 0) : GenericSharedBytes(hot);
     int sms = 0, per_sm = 0;
     cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
