@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanUniformKernel(con
 struct LookFilter {
     uint32_t lo, hi;
     uint32_t zero;      // a kernel argument that is always 0: the addend that keeps the cleaning multiply an IMAD
+    uint32_t rev;       // lo with its bits reversed (clean-bit kernels: probes of the odd bytes)
 };
 
 // kClean: the probe's bit is moved to bit 31 with the bits below it cleared by one multiply (IMAD, FMA pipe: pa * 2^31
@@ -477,6 +478,14 @@ __device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, const LookF
 {
     constexpr uint32_t sel = 1u << (8 * kByte);
     bb = __dp4a(w, sel, base);
+    if (kClean && (kByte & 1)) {
+        // odd bytes: the bit-reversed filter shifted LEFT puts the probe's bit in bit 31 with other filter bits below it.
+        // That is good enough: the step ANDs the probes of two neighbouring bytes, one of them is always an even byte,
+        // and an even byte's probe is clean -- so an odd byte costs one SHF, an even byte SHF + IMAD: 5.5 instructions
+        // per step on average.
+        pa = __funnelshift_l(0u, f.rev, bb);
+        return;
+    }
     if (k64) {
         const uint32_t slot = __dp4a(w & 0x3F3F3F3Fu, sel, 0u);
         pa = (uint32_t) ((((uint64_t) f.hi << 32) | f.lo) >> slot);
@@ -587,7 +596,7 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
     // plus g times a kernel argument that is always zero -- which costs one IMAD per block.)
     const uint32_t late = next0 + g * opaque_zero;
     LookProbe<k64, 0, kClean>(late, t.base, f, bb, pa);
-    LookWord<k64, kClean>(g, v1.w, bn, pn, more ? pa : 0xffffffffu, t.base, f);
+    LookWord<k64, kClean>(g, v1.w, bn, pn, more ? pa : (kClean ? 0x80000000u : 0xffffffffu), t.base, f);
     if (g == t.H) {
         prev = ReplayBlock32(args, prev, v0, v1);
         g = prev < t.H ? prev : t.H;
@@ -621,6 +630,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
     f.lo = k64 ? (uint32_t) a.look_bitmap64 : a.look_bitmap;
     f.hi = (uint32_t) (a.look_bitmap64 >> 32);
     f.zero = a.opaque_zero;
+    f.rev = __brev(f.lo);
 
     const uint32_t units = (uint32_t) ((a.n + 31) / 32);            // pire_gpu_run_batch keeps n <= 2^40: units below 2^32
     const uint32_t warps_per_block = blockDim.x >> 5;
@@ -670,6 +680,163 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
         s.g = t.H;              // Report reads the complete state
         s.cold = g == t.H ? prev : g;
         Report(a, t, s, unit, i, i < a.n);
+    }
+}
+
+// ---------------------------------------------------------------- LOOK variant, two strings per lane
+//
+// ncu on the look-ahead kernel (profiles/r02_full_glue10_lookclean.txt): a third of all stall samples sit on the LOP3 that
+// waits for the previous step's LDS, and 40 warps per SM run 2.8 % faster than 36 -- the kernel is short of independent
+// chains, and registers (48 per thread) cap the warps.  Here every lane walks TWO strings (units 2p and 2p+1 of the
+// batch) step by step in turn: the second string's step fills the latency of the first one's table read, and the
+// block bookkeeping is shared.  32 data registers (two LDG.256 ping-pong sets), __maxnreg__ chosen by the launch plan.
+template <bool kClean>
+__device__ __forceinline__ void LookWord2(uint32_t& ga, uint32_t wa, uint32_t bba0, uint32_t paa0, uint32_t pana, uint32_t& gb, uint32_t wb,
+                                          uint32_t bbb0, uint32_t pab0, uint32_t panb, uint32_t base, const LookFilter& f)
+{
+    uint32_t bba1, bba2, bba3, paa1, paa2, paa3, bbb1, bbb2, bbb3, pab1, pab2, pab3;
+    LookProbe<false, 1, kClean>(wa, base, f, bba1, paa1);
+    LookProbe<false, 1, kClean>(wb, base, f, bbb1, pab1);
+    LookStep<kClean>(ga, bba0, paa0, paa1);
+    LookStep<kClean>(gb, bbb0, pab0, pab1);
+    LookProbe<false, 2, kClean>(wa, base, f, bba2, paa2);
+    LookProbe<false, 2, kClean>(wb, base, f, bbb2, pab2);
+    LookStep<kClean>(ga, bba1, paa1, paa2);
+    LookStep<kClean>(gb, bbb1, pab1, pab2);
+    LookProbe<false, 3, kClean>(wa, base, f, bba3, paa3);
+    LookProbe<false, 3, kClean>(wb, base, f, bbb3, pab3);
+    LookStep<kClean>(ga, bba2, paa2, paa3);
+    LookStep<kClean>(gb, bbb2, pab2, pab3);
+    LookStep<kClean>(ga, bba3, paa3, pana);
+    LookStep<kClean>(gb, bbb3, pab3, panb);
+}
+
+template <bool kClean>
+__device__ __forceinline__ void LookBlock32x2(const Tables& t, uint32_t& ga, uint32_t& preva, const uint4& a0, const uint4& a1, uint32_t nexta,
+                                              uint32_t& gb, uint32_t& prevb, const uint4& b0, const uint4& b1, uint32_t nextb, bool more,
+                                              const LookFilter& f, uint32_t opaque_zero, const ScanArgs* args)
+{
+    preva = ga == t.H ? preva : ga;
+    prevb = gb == t.H ? prevb : gb;
+    uint32_t bba, paa, bna, pna, bbb, pab, bnb, pnb;
+    LookProbe<false, 0, kClean>(a0.x, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b0.x, t.base, f, bbb, pab);
+    LookProbe<false, 0, kClean>(a0.y, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b0.y, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a0.x, bba, paa, pna, gb, b0.x, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a0.z, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b0.z, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a0.y, bna, pna, paa, gb, b0.y, bnb, pnb, pab, t.base, f);
+    LookProbe<false, 0, kClean>(a0.w, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b0.w, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a0.z, bba, paa, pna, gb, b0.z, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a1.x, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b1.x, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a0.w, bna, pna, paa, gb, b0.w, bnb, pnb, pab, t.base, f);
+    LookProbe<false, 0, kClean>(a1.y, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b1.y, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a1.x, bba, paa, pna, gb, b1.x, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a1.z, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b1.z, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a1.y, bna, pna, paa, gb, b1.y, bnb, pnb, pab, t.base, f);
+    LookProbe<false, 0, kClean>(a1.w, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b1.w, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a1.z, bba, paa, pna, gb, b1.z, bbb, pab, pnb, t.base, f);
+    // the words after the blocks are still on their way from HBM: their probes stay behind the walk (see LookBlock32)
+    const uint32_t latea = nexta + ga * opaque_zero;
+    const uint32_t lateb = nextb + gb * opaque_zero;
+    LookProbe<false, 0, kClean>(latea, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(lateb, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a1.w, bna, pna, more ? paa : 0x80000000u, gb, b1.w, bnb, pnb, more ? pab : 0x80000000u, t.base, f);
+    if (ga == t.H) {
+        preva = ReplayBlock32(args, preva, a0, a1);
+        ga = preva < t.H ? preva : t.H;
+    }
+    if (gb == t.H) {
+        prevb = ReplayBlock32(args, prevb, b0, b1);
+        gb = prevb < t.H ? prevb : t.H;
+    }
+}
+
+template <int kRegs>
+__global__ void __maxnreg__(kRegs) ScanUniformLook2Kernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+
+    Tables t;
+    t.hot = sv.hot;
+    t.base = SmemWindowBase();
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.look_bitmap;
+    LookFilter f;
+    f.lo = a.look_bitmap;
+    f.hi = 0;
+    f.zero = a.opaque_zero;
+    f.rev = __brev(f.lo);
+
+    const uint32_t units = (uint32_t) ((a.n + 31) / 32);
+    const uint32_t pairs = (units + 1) / 2;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t warps = gridDim.x * warps_per_block;
+    const uint32_t len = (uint32_t) a.fixed_len;
+    const uint32_t blocks = len >> 5;
+
+    for (uint32_t pair = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pair < pairs; pair += warps) {
+        const bool second = 2 * pair + 1 < units;          // the last pair of an odd batch walks its first unit twice
+        uint32_t ga, preva, gb, prevb;
+        {
+            const uint64_t ia = (uint64_t) pair * 64 + (threadIdx.x & 31);
+            const uint64_t ib = ia + (second ? 32 : 0);
+            const uint8_t* pa = a.corpus + (ia < a.n ? ia : a.n - 1) * (uint64_t) len;
+            const uint8_t* pb = a.corpus + (ib < a.n ? ib : a.n - 1) * (uint64_t) len;
+            preva = prevb = a.start;
+            ga = gb = a.start < t.H ? a.start : t.H;
+            if (blocks != 0) {
+                uint4 a0, a1, b0, b1, c0, c1, d0, d1;         // a/c: the first string's ping-pong sets, b/d: the second's
+                LoadStream32(pa, a0, a1);
+                LoadStream32(pb, b0, b1);
+                for (uint32_t left = blocks;;) {
+                    const bool more_c = left > 1;
+                    pa += 32;
+                    pb += 32;
+                    if (more_c) {
+                        LoadStream32(pa, c0, c1);
+                        LoadStream32(pb, d0, d1);
+                    }
+                    __syncwarp();          // scheduling fence: the loads stay up here (see ScanUniformLookKernel)
+                    LookBlock32x2<true>(t, ga, preva, a0, a1, c0.x, gb, prevb, b0, b1, d0.x, more_c, f, a.opaque_zero, &a);
+                    if (!more_c)
+                        break;
+                    const bool more_a = left > 2;
+                    pa += 32;
+                    pb += 32;
+                    if (more_a) {
+                        LoadStream32(pa, a0, a1);
+                        LoadStream32(pb, b0, b1);
+                    }
+                    __syncwarp();
+                    LookBlock32x2<true>(t, ga, preva, c0, c1, a0.x, gb, prevb, d0, d1, b0.x, more_a, f, a.opaque_zero, &a);
+                    left -= 2;
+                    if (!more_a || __all_sync(0xffffffffu, (sv.noexit[ga] & sv.noexit[gb]) != 0))
+                        break;
+                }
+            }
+        }
+        const uint64_t ia = (uint64_t) pair * 64 + (threadIdx.x & 31);
+        LaneState s;
+        s.g = t.H;
+        s.cold = ga == t.H ? preva : ga;
+        Report(a, t, s, 2 * (uint64_t) pair, ia, ia < a.n);
+        if (second) {
+            s.cold = gb == t.H ? prevb : gb;
+            Report(a, t, s, 2 * (uint64_t) pair + 1, ia + 32, ia + 32 < a.n);
+        }
     }
 }
 
@@ -803,6 +970,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) ScanGenericKernel
     look.lo = a.look_bitmap;
     look.hi = 0;
     look.zero = 0;
+    look.rev = 0;
     uint8_t* const smem = pire_b200_smem;
     SharedView sv = CarveShared(smem, a.hot);
     StageTables(a, sv, a.hot8, a.hot);
@@ -2448,10 +2616,34 @@ bool LookClean()
     return clean;
 }
 
+// PIRE_B200_LOOK_ILP=2: two strings per lane (ScanUniformLook2Kernel); PIRE_B200_LOOK_ILP_REGS=64|72|80 picks the
+// register budget and with it the CTA shape (two CTAs of 512 / 448 / 384 threads per SM).
+int LookIlp()
+{
+    static const int ilp = [] {
+        const char* env = getenv("PIRE_B200_LOOK_ILP");
+        return env && atoi(env) == 2 ? 2 : 1;
+    }();
+    return ilp;
+}
+int LookIlpRegs()
+{
+    static const int regs = [] {
+        const char* env = getenv("PIRE_B200_LOOK_ILP_REGS");
+        const int v = env ? atoi(env) : 72;
+        return v == 64 || v == 80 ? v : 72;
+    }();
+    return regs;
+}
+
 const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
+    if (variant == kVariantLook && uniform && LookIlp() == 2)
+        return LookIlpRegs() == 64   ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<64>)
+               : LookIlpRegs() == 80 ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<80>)
+                                     : reinterpret_cast<const void*>(&ScanUniformLook2Kernel<72>);
     if (variant == kVariantLook && uniform && LookClean())
         return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, true>)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, true>);
@@ -2506,6 +2698,8 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
             const char* env = getenv("PIRE_B200_LOOK_BLOCK");          // experiments: e.g. 640 = two CTAs of 20 warps at 48 registers
             return env && atoi(env) >= 32 && atoi(env) <= 1024 && atoi(env) % 32 == 0 ? atoi(env) : 0;
         }();
+        if (variant == kVariantLook && LookIlp() == 2)
+            plan->block = LookIlpRegs() == 64 ? 512 : LookIlpRegs() == 80 ? 384 : 448;
         if (look_block)
             plan->block = look_block;
     }
@@ -2530,6 +2724,8 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     if (a.n == 0)
         return cudaSuccess;
     uint64_t units = (a.n + 31) / 32;
+    if (variant == kVariantLook && uniform && LookIlp() == 2)
+        units = (units + 1) / 2;              // a warp of ScanUniformLook2Kernel takes two units at a time
     const uint64_t warps_per_block = (uint64_t) plan.block / 32;
     uint64_t want = (units + warps_per_block - 1) / warps_per_block;
     int grid = (int) (want < (uint64_t) plan.grid ? want : (uint64_t) plan.grid);
