@@ -465,7 +465,9 @@ class Resident:
                 return "ScanGenericKernel<%s>" % mode
             return "ScanSplitKernel<%s> (strings >= 8 KiB, one per warp) + ScanGenericKernel<%s> (the rest)" % (
                 "plain" if mode == "plain" else "pred", mode)
-        return {"priv": "ScanUniformPrivKernel", "look": "ScanUniformLookKernel<32 slots>",
+        look = "ScanUniformLookKernel<32 slots>" if os.environ.get("PIRE_B200_LOOK_ILP", "2") == "1" \
+            else "ScanUniformLook2Kernel<%s regs> (two strings per lane, 32-slot look-ahead filter)" % os.environ.get("PIRE_B200_LOOK_ILP_REGS", "72")
+        return {"priv": "ScanUniformPrivKernel", "look": look,
                 "look64": "ScanUniformLookKernel<64 slots>"}.get(self.chosen, "ScanUniformKernel<%s>" % self.chosen)
 
 

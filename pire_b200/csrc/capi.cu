@@ -365,6 +365,17 @@ static int PrefixOrSuffix(const pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     a.prefix_len = d_len;
     a.first_final_hot = sc->tab.first_final_hot;
     a.uniform = (!reverse && IsUniform(d_corpus, d_offsets, fixed_len) && !getenv("PIRE_B200_NO_UNIFORM_BODY")) ? 1 : 0;
+    if (a.uniform) {
+        // the uniform prefix kernel walks plain: with the exit filter of hot id 0 its step is five ALU-pipe instructions
+        // (PRMT, SHF, 2 x LOP3, VIMNMX) and measured half the speed (1.64 vs 3.17 TB/s on the glued scanner);
+        // PIRE_B200_PREFIX_PRED=1 selects the filtered walk for experiments
+        static const int forced = [] {
+            const char* env = getenv("PIRE_B200_PREFIX_PRED");
+            return env ? atoi(env) : 0;
+        }();
+        const bool pred = forced != 0;
+        a.uniform = pred ? 2 : 1;
+    }
     CUDA_TRY(LaunchPrefix(a, shortest != 0, reverse, sc->device, static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
 }

@@ -605,10 +605,11 @@ __device__ __forceinline__ void LookBlock32(const Tables& t, uint32_t& g, uint32
 
 // Register budget.  The register file is split between the four warp schedulers (16 K registers each), so a
 // CTA's warps should be a multiple of four: 512 threads x 3 CTAs leaves 40 registers per thread (12 warps x 1280
-// per scheduler), 384 threads x 3 CTAs leaves 48 (9 warps x 1536).  Both instantiations exist; the launch plan picks
-// (PIRE_B200_LOOK_REGS=40|48 for experiments).
+// per scheduler), 384 threads x 3 CTAs or 640 threads x 2 CTAs leave 48 (9 / 10 warps x 1536).  The kernel is short
+// of independent chains, so the ten-warp shape wins (2.423 ms against 2.480 on the glued scan); both instantiations
+// exist (PIRE_B200_LOOK_REGS=40|48, PIRE_B200_LOOK_BLOCK=<threads> for experiments).
 constexpr int kLookBlock40 = 512;
-constexpr int kLookBlock48 = 384;
+constexpr int kLookBlock48 = 640;
 
 template <bool k64, int kRegs, bool kClean = false>
 __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__ ScanArgs a)
@@ -1886,25 +1887,35 @@ __device__ __forceinline__ void PrefixCheck(const ScanArgs& a, uint32_t H, const
         l.stop = true;
 }
 
-template <bool kShortest, bool kReverse>
+template <bool kShortest, bool kReverse, bool kPred = false, bool kIdp = false>
 __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t, const uint8_t* hot_flags, LaneState& s, uint4 v,
                                               PrefixLane& l)
 {
     const uint32_t before = s.g;
-    uint32_t g = before, top = 0;
+    uint32_t g = before, top = 0, low = 0xffffffffu;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         const int at = kReverse ? 3 - w : w;
         const uint32_t word = at == 0 ? v.x : at == 1 ? v.y : at == 2 ? v.z : v.w;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            FastStep<false, false>(t, g, word, 0x5540 + (kReverse ? 3 - b : b));
+            FastStep<kPred, kIdp>(t, g, word, 0x5540 + (kReverse ? 3 - b : b));
             top = max(top, g);
+            if (!kShortest)
+                low = min(low, g);
         }
     }
     if (top < a.first_final_hot) {           // sixteen steps through non-final hot states
         s.g = g;
         l.consumed += 16;
+        return;
+    }
+    if (!kShortest && low >= a.first_final_hot && top != t.H) {
+        // sixteen steps through final hot states (a lane behind an unanchored match sits in such states for the rest of
+        // its string): the longest prefix so far ends with this chunk, no second pass needed
+        s.g = g;
+        l.consumed += 16;
+        l.pos = l.consumed;
         return;
     }
     // ShortestSuffix steps BeginMark from the state it stopped in (run.h:357-359), so that scan needs the
@@ -1921,7 +1932,7 @@ __device__ __forceinline__ void PrefixChunk16(const ScanArgs& a, const Tables& t
             const uint32_t word = at == 0 ? v.x : at == 1 ? v.y : at == 2 ? v.z : v.w;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                FastStep<false, false>(t, h, word, 0x5540 + (kReverse ? 3 - b : b));
+                FastStep<kPred, kIdp>(t, h, word, 0x5540 + (kReverse ? 3 - b : b));
                 const bool final = h >= a.first_final_hot;
                 if (kShortest)
                     mark = final && mark == 0 ? (uint32_t) (4 * w + b + 1) : mark;
@@ -2164,6 +2175,101 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) PrefixKernel(cons
                 const uint32_t last = FullNext(t, full, a.end_class);
                 if ((__ldg(a.flags + last) & 1u) && (!kShortest || l.pos == kNoPrefix))
                     l.pos = len;
+            }
+            a.prefix_len[i] = l.pos;
+        }
+    }
+}
+
+// Forward prefix scans of a fixed-length, 32-byte aligned batch (the BASELINE configs' shape) in a kernel of their own:
+// no edge bytes and no staging ring, so three CTAs (or two of twenty warps) fit an SM instead of the generic kernel's two
+// of sixteen, and the walk can use the exit filter of hot id 0 (kPred): a lane resting there on a byte that cannot leave
+// keeps g = 0, which is all the running maximum needs.  (The look-ahead filter does not carry over: it skips the one-step
+// states behind an exit byte, and a prefix scan must see them if they are final.)
+template <bool kShortest, bool kPred, bool kIdp>
+__global__ void __maxnreg__(48) PrefixUniformKernel(const __grid_constant__ ScanArgs a)
+{
+    uint8_t* const smem = pire_b200_smem;
+    SharedView sv = CarveShared(smem, a.hot);
+    StageTables(a, sv, a.hot8, a.hot);
+    uint8_t* const hot_flags = sv.stage;                            // H + 1 bytes, where the generic kernels keep their ring
+    for (uint32_t i = threadIdx.x; i <= a.hot; i += blockDim.x)
+        hot_flags[i] = i < a.hot ? a.flags[i] : 0;
+    __syncthreads();
+
+    Tables t;
+    t.hot = sv.hot;
+    t.base = SmemAddr(sv.hot);
+    t.cls = sv.cls;
+    t.full = a.full;
+    t.H = a.hot;
+    t.letters = a.letters;
+    t.wide = a.wide;
+    t.m0 = a.exit_bitmap0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint64_t units = (a.n + 31) / 32;
+    const uint64_t warps = (uint64_t) gridDim.x * warps_per_block;
+    const uint32_t ulen = (uint32_t) a.fixed_len;
+
+    for (uint64_t unit = (uint64_t) blockIdx.x * warps_per_block + (threadIdx.x >> 5); unit < units; unit += warps) {
+        const uint64_t i = unit * 32 + lane;
+        const bool valid = i < a.n;
+        // Initialize() and BeginMark (run.h:282-283)
+        uint32_t full = a.initial;
+        if (a.with_begin)
+            full = FullNext(t, full, a.begin_class);
+        PrefixLane l;
+        l.consumed = 0;
+        l.pos = kNoPrefix;
+        l.stop = !valid;
+        if ((full < t.H ? hot_flags[full] : __ldg(a.flags + full)) & 1u) {      // run.h:284 / :301-302
+            l.pos = 0;
+            l.stop = l.stop || kShortest;
+        }
+        LaneState s;
+        SetFull(t, s, full);
+        // every lane of the warp walks the loop (its control flow holds a warp vote), also the lanes past the end of
+        // the batch: they are stopped from the start and read string 0
+        const uint8_t* const src = a.corpus + (valid ? i : 0) * (uint64_t) ulen;
+        if (ulen != 0) {
+            uint4 a0, a1, b0, b1;
+            LoadStream32(src, a0, a1);
+            for (uint32_t off = 0;;) {
+                off += 32;
+                const bool more_b = off < ulen;
+                if (more_b)
+                    LoadStream32(src + off, b0, b1);
+                if (!l.stop)
+                    PrefixChunk16<kShortest, false, kPred, kIdp>(a, t, hot_flags, s, a0, l);
+                if (!l.stop)
+                    PrefixChunk16<kShortest, false, kPred, kIdp>(a, t, hot_flags, s, a1, l);
+                if (!more_b)
+                    break;
+                off += 32;
+                const bool more_a = off < ulen;
+                if (more_a)
+                    LoadStream32(src + off, a0, a1);
+                if (!l.stop)
+                    PrefixChunk16<kShortest, false, kPred, kIdp>(a, t, hot_flags, s, b0, l);
+                if (!l.stop)
+                    PrefixChunk16<kShortest, false, kPred, kIdp>(a, t, hot_flags, s, b1, l);
+                // a dead state only leads to dead states: stop the lane once it is noticed (every 64 bytes)
+                if (!l.stop) {
+                    const uint32_t at = FullState(t, s);
+                    if ((at < t.H ? hot_flags[at] : __ldg(a.flags + at)) & 2u)
+                        l.stop = true;
+                }
+                if (!more_a || __all_sync(0xffffffffu, l.stop))
+                    break;
+            }
+        }
+        if (valid) {
+            if (a.through_end) {                                             // run.h:286-290 / :305-309
+                const uint32_t last = FullNext(t, FullState(t, s), a.end_class);
+                if ((__ldg(a.flags + last) & 1u) && (!kShortest || l.pos == kNoPrefix))
+                    l.pos = ulen;
             }
             a.prefix_len[i] = l.pos;
         }
@@ -2616,13 +2722,15 @@ bool LookClean()
     return clean;
 }
 
-// PIRE_B200_LOOK_ILP=2: two strings per lane (ScanUniformLook2Kernel); PIRE_B200_LOOK_ILP_REGS=64|72|80 picks the
-// register budget and with it the CTA shape (two CTAs of 512 / 448 / 384 threads per SM).
+// Two strings per lane (ScanUniformLook2Kernel) is the default shape of the look-ahead variant; PIRE_B200_LOOK_ILP=1
+// selects one string per lane (ScanUniformLookKernel).  PIRE_B200_LOOK_ILP_REGS=64|72|80 picks the register budget
+// and with it the CTA shape (two CTAs of 512 / 448 / 384 threads per SM); measured 2.739 / 2.374 / 2.384 ms on the
+// glued scan (profiles/r02_experiments_notes.txt).
 int LookIlp()
 {
     static const int ilp = [] {
         const char* env = getenv("PIRE_B200_LOOK_ILP");
-        return env && atoi(env) == 2 ? 2 : 1;
+        return env && atoi(env) == 1 ? 1 : 2;
     }();
     return ilp;
 }
@@ -2789,6 +2897,46 @@ cudaError_t LaunchPrefix(const ScanArgs& a, bool shortest, bool reverse, int dev
         err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (err != cudaSuccess)
         return err;
+    if (a.uniform && !reverse) {
+        // a.uniform: 1 = plain walk, 2 = exit filter
+        static const int block = [] {
+            const char* env = getenv("PIRE_B200_PREFIX_BLOCK");       // experiments; 640 = two CTAs of twenty warps at 48 registers
+            return env && atoi(env) >= 32 && atoi(env) <= 1024 && atoi(env) % 32 == 0 ? atoi(env) : 640;
+        }();
+        const bool pred = a.uniform == 2;
+        static const bool idp = [] {
+            const char* env = getenv("PIRE_B200_PREFIX_IDP");          // experiments: byte extraction on the FMA pipe
+            return env && atoi(env) != 0;
+        }();
+        if (pred)
+            fn = shortest ? reinterpret_cast<const void*>(&PrefixUniformKernel<true, true, false>)
+                          : reinterpret_cast<const void*>(&PrefixUniformKernel<false, true, false>);
+        else if (idp)
+            fn = shortest ? reinterpret_cast<const void*>(&PrefixUniformKernel<true, false, true>)
+                          : reinterpret_cast<const void*>(&PrefixUniformKernel<false, false, true>);
+        else
+            fn = shortest ? reinterpret_cast<const void*>(&PrefixUniformKernel<true, false, false>)
+                          : reinterpret_cast<const void*>(&PrefixUniformKernel<false, false, false>);
+        const size_t shared = ScanSharedBytes(a.hot, 0) + 272;
+        int per_sm = 0;
+        err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (err == cudaSuccess)
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, shared);
+        if (err != cudaSuccess)
+            return err;
+        if (per_sm < 1)
+            return cudaErrorLaunchOutOfResources;
+        const uint64_t per_block = (uint64_t) block;
+        const uint64_t want = (a.n + per_block - 1) / per_block;
+        const int grid = (int) (want < (uint64_t) sms * per_sm ? want : (uint64_t) sms * per_sm);
+        void* args[] = {const_cast<ScanArgs*>(&a)};
+        err = cudaLaunchKernel(fn, dim3(grid), dim3(block), args, shared, stream);
+        if (err == cudaSuccess)
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        return err;
+    }
     const size_t shared = GenericSharedBytes(a.hot) + 272;      // + the hot states' flag bytes
     uint64_t want = (a.n + kBlock - 1) / kBlock;
     int grid = (int) (want < (uint64_t) sms * kGenericBlocksPerSM ? want : (uint64_t) sms * kGenericBlocksPerSM);
