@@ -439,6 +439,9 @@ class Resident:
         if variant == "auto":
             self.variant_ms = self.sc.AutoSelect(self.batch)
             self.chosen = names[self.sc.info().variant]
+            if self.mixed and self.variant_ms:
+                # info() names the choice for uniform batches; a ragged batch runs the fastest of the variants timed on it
+                self.chosen = min(self.variant_ms, key=self.variant_ms.get)
         else:
             self.chosen = variant
             self.sc.set_variant({v: k for k, v in names.items()}[variant])

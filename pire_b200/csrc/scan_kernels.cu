@@ -1209,7 +1209,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanSplitKernel(const
             if (my_blocks)
                 LoadStream32P(piece, a0, a1);
             uint32_t countdown = per_mark, m = 0;
+            const uint32_t ahead = a.split_prefetch;
             for (uint32_t k = 0; k < trips; k += 2) {
+                // optional L2 prefetch, one per 256-byte line, `ahead` blocks in front of the walk.  ncu puts 31 % of this
+                // kernel's stall samples on the first use of a loaded word, but the prefetch measured no gain at 8..64
+                // blocks (3.09-3.12 ms with, 3.09 without): the L2::256B hint of the loads already brings the line into
+                // L2, what is exposed is the L2 -> SM trip under load.  Off by default.
+                if (ahead && (k & 7u) == 0 && k + ahead < my_blocks)
+                    PrefetchL2(piece + 32 * (size_t) (k + ahead));
                 if (k + 1 < my_blocks)
                     LoadStream32P(piece + 32 * (size_t) (k + 1), b0, b1);
                 __syncwarp();              // scheduling fence: the load is issued here, not next to its first use
@@ -2859,6 +2866,10 @@ cudaError_t LaunchSplit(const ScanArgs& a, int variant, int device, cudaStream_t
     if (err != cudaSuccess)
         return err;
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    static const uint32_t split_prefetch = [] {
+        const char* env = getenv("PIRE_B200_SPLIT_PREFETCH");     // blocks of 32 bytes between the walk and its L2 prefetch; 0 = none
+        return env ? (uint32_t) atoi(env) : 0u;
+    }();
     const void* fn = variant == kVariantPlain ? reinterpret_cast<const void*>(&ScanSplitKernel<false>)
                                               : reinterpret_cast<const void*>(&ScanSplitKernel<true>);
     const size_t shared = ScanSharedBytes(a.hot, 0) + kSplitMarkBytes + kWarpsPerBlock * 32;
@@ -2874,7 +2885,9 @@ cudaError_t LaunchSplit(const ScanArgs& a, int variant, int device, cudaStream_t
         return err;
     if (per_sm < 1)
         return cudaErrorLaunchOutOfResources;
-    void* args[] = {const_cast<ScanArgs*>(&a)};
+    ScanArgs with_prefetch = a;                 // kernel arguments are copied at launch
+    with_prefetch.split_prefetch = split_prefetch;
+    void* args[] = {&with_prefetch};
     err = cudaLaunchKernel(fn, dim3(sms * per_sm), dim3(kBlock), args, shared, stream);
     if (err == cudaSuccess)
         g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -24,6 +24,7 @@ struct ScanArgs {
     unsigned int* work_counter;  // with `order`: units are claimed longest-first from this counter
     const uint32_t* split_count; // with `order`, or null: the first *split_count entries of `order` belong to the split kernel
     unsigned int* split_counter; // split kernel: strings are claimed from this counter
+    uint32_t split_prefetch;     // split kernel: 32-byte blocks between a lane's walk and its L2 prefetch (0 = none)
     uint64_t fixed_len;          // used when offsets == nullptr
     uint64_t n;                  // strings
     const uint8_t* hot8;         // HotTableBytes(hot) bytes (rows kHotStride apart), 16-byte aligned

@@ -118,6 +118,18 @@ for name in ("headline", "count_words5"):
                     assert (got == oracle_prefix(orc, c, o, shortest=shortest, through_begin=m1, through_end=m2)).all()
                     got = (P.ShortestSuffix if shortest else P.LongestSuffix)(sc, bb, throughEndMark=m1, throughBeginMark=m2)
                     assert (got == oracle_suffix(orc, c, o, shortest=shortest, through_end=m1, through_begin=m2)).all()
+    # fixed-length, 32-byte aligned batch: the uniform prefix kernel (no ring; chunks walked in final states only)
+    rng_u = np.random.default_rng(7)
+    nu, lu = 1024 + 5, 96
+    hu = rng_u.choice(np.frombuffer(b"helo wrd\tab", np.uint8), size=(nu, lu))
+    hu[::3, :12] = np.frombuffer(b"hello  world", np.uint8)
+    hu = np.ascontiguousarray(hu).reshape(-1)
+    bu = P.Batch(torch.from_numpy(hu).to(dev), fixed_len=lu, n=nu)
+    scu = P.Scanner(image, 0)
+    for shortest in (False, True):
+        for m1 in (False, True):
+            got = (P.ShortestPrefix if shortest else P.LongestPrefix)(scu, bu, throughBeginMark=m1, throughEndMark=True)
+            assert (got == oracle_prefix(orc, hu, fixed_len=lu, n=nu, shortest=shortest, through_begin=m1, through_end=True)).all()
     print("ok prefix/suffix", name, flush=True)
 # counting kernels (HalfFinalScanner): accept lists / packed / packed on every chunk, tiny hot sets, ragged + fixed
 from refpire import oracle_count
