@@ -109,7 +109,11 @@ int  pire_gpu_scanner_set_max_hot(pire_gpu_scanner* sc, uint32_t max_hot_rows);
  *   d_accept_masks  n words; bit r = regexp id r in AcceptedRegexps (r < 32)
  *   d_state_idx     n words; StateIndex() of the last state, reference numbering
  * All pointers are device pointers on the handle's device; the launch is
- * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default). */
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default).
+ * Side effect shared by every entry point that takes a handle, a communicator or a
+ * `device` argument: the device becomes the calling thread's current CUDA device
+ * (cudaSetDevice) and stays so on return; a caller that works with several devices
+ * from one thread re-selects its own afterwards. */
 int pire_gpu_run_batch(const pire_gpu_scanner* sc,
                        const uint8_t* d_corpus, const uint64_t* d_offsets,
                        uint64_t fixed_len, uint64_t n, uint32_t flags,
