@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
     ap.add_argument("--workload", default="glue10", choices=["glue10", "headline", "utf8mixed"])
     ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: 10 GB worth)")
-    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look", "look64"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look", "look64", "look1"])
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -463,14 +463,14 @@ class Resident:
 
     def kernel_name(self):
         if self.mixed:
-            mode = {"plain": "plain", "look": "look", "look64": "look"}.get(self.chosen, "pred")
+            mode = {"plain": "plain", "look": "look", "look64": "look", "look1": "look"}.get(self.chosen, "pred")
             if os.environ.get("PIRE_B200_SPLIT", "1") == "0":
                 return "ScanGenericKernel<%s>" % mode
             return "ScanSplitKernel<%s> (strings >= 8 KiB, one per warp) + ScanGenericKernel<%s> (the rest)" % (
                 "plain" if mode == "plain" else "pred", mode)
         look = "ScanUniformLookKernel<32 slots>" if os.environ.get("PIRE_B200_LOOK_ILP", "2") == "1" \
             else "ScanUniformLook2Kernel<%s regs> (two strings per lane, 32-slot look-ahead filter)" % os.environ.get("PIRE_B200_LOOK_ILP_REGS", "72")
-        return {"priv": "ScanUniformPrivKernel", "look": look,
+        return {"priv": "ScanUniformPrivKernel", "look": look, "look1": "ScanUniformLookKernel<32 slots> (one string per lane)",
                 "look64": "ScanUniformLookKernel<64 slots>"}.get(self.chosen, "ScanUniformKernel<%s>" % self.chosen)
 
 
@@ -582,8 +582,10 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            # VERSION and WARN both print NCCL's version banner on stdout; the contract is ONE JSON line there.  An INFO
+            # (or higher) setting is somebody collecting the communicator log and is left alone.
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
         comm = Comm(local)                           # the C ABI's communicator; torch.distributed only ships its id
 

@@ -60,6 +60,9 @@ enum {
                                       the next can both matter (the device analogue of the ExitMasks skip loop,
                                       multi.h:966-989); fixed-length batches, PRED otherwise */
     PIRE_GPU_VARIANT_LOOK64 = 5,   /* LOOK with a 64-slot filter (one more FMA-pipe instruction per byte, fewer false passes) */
+    PIRE_GPU_VARIANT_LOOK1 = 6,    /* LOOK walks two strings per lane on fixed-length batches (the second string's step fills
+                                      the latency of the first one's table read); LOOK1 is the same filter with one string per
+                                      lane -- the shape for batches too small to give every resident warp two units */
     PIRE_GPU_VARIANT_SLOTS = 8     /* length of per-variant arrays indexed by variant id */
 };
 

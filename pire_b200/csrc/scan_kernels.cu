@@ -1243,6 +1243,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanSplitKernel(const
         }
         uint32_t end_full = FullState(t, s);
 
+        // A lane whose guess was wrong walks the head of its piece again: its first block is asked for now, before the
+        // stitch knows who needs it (one 32-byte L2 hit per lane and string), so that the re-walk does not begin with a
+        // bare load -- ncu had 31 % of this kernel's stall samples on the first use of a loaded word.
+        uint4 head0 = make_uint4(0, 0, 0, 0), head1 = head0;
+        bool head_fresh = my_blocks != 0;
+        if (head_fresh)
+            LoadStream32P(piece, head0, head1);
+
         // stitch: every lane must have started where its predecessor ended
         for (;;) {
             const uint32_t before = __shfl_up_sync(0xffffffffu, end_full, 1);
@@ -1266,9 +1274,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanSplitKernel(const
                     SetFull(t, r, want);
                     uint32_t countdown = per_mark, m = 0;
                     bool met = false;
+                    uint4 v0 = head0, v1 = head1;
+                    if (!head_fresh && my_blocks)
+                        LoadStream32P(piece, v0, v1);
+                    head_fresh = false;
                     for (uint32_t k = 0; k < my_blocks; ++k) {
-                        uint4 v0, v1;
-                        LoadStream32P(piece + 32 * (size_t) k, v0, v1);
+                        uint4 n0 = v0, n1 = v1;
+                        if (k + 1 < my_blocks)
+                            LoadStream32P(piece + 32 * (size_t) (k + 1), n0, n1);      // one block ahead, like the first walk
                         Chunk16<kPred>(t, r, v0);
                         Chunk16<kPred>(t, r, v1);
                         if (--countdown == 0) {
@@ -1279,6 +1292,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocksPerSM) ScanSplitKernel(const
                             marks[32 * m++] = (uint8_t) r.g;
                             countdown = per_mark;
                         }
+                        v0 = n0;
+                        v1 = n1;
                     }
                     if (!met)
                         end_full = FullState(t, r);
@@ -2759,10 +2774,10 @@ const void* KernelFor(int variant, bool uniform)
         return LookIlpRegs() == 64   ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<64>)
                : LookIlpRegs() == 80 ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<80>)
                                      : reinterpret_cast<const void*>(&ScanUniformLook2Kernel<72>);
-    if (variant == kVariantLook && uniform && LookClean())
+    if ((variant == kVariantLook || variant == kVariantLook1) && uniform && LookClean())
         return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48, true>)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40, true>);
-    if (variant == kVariantLook && uniform)
+    if ((variant == kVariantLook || variant == kVariantLook1) && uniform)
         return LookRegs() == 48 ? reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 48>)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<false, 40>);
     if (variant == kVariantLook64 && uniform)
@@ -2770,7 +2785,7 @@ const void* KernelFor(int variant, bool uniform)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40>);
     if (uniform)
         return variant == kVariantPred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
-    if (variant == kVariantLook || variant == kVariantLook64)      // CSR batches: one look-ahead kernel (32-slot filter)
+    if (variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1)      // CSR batches: one look-ahead kernel (32-slot filter)
         return GenericKernelPtr<2>();
     return variant == kVariantPred ? GenericKernelPtr<1>() : GenericKernelPtr<0>();
 }
@@ -2789,7 +2804,7 @@ cudaError_t PrepareScanKernels(int device)
     err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err != cudaSuccess)
         return err;
-    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook, (int) kVariantLook64})
+    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook, (int) kVariantLook64, (int) kVariantLook1})
         for (bool uniform : {false, true}) {
             err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (err != cudaSuccess)
@@ -2807,8 +2822,9 @@ cudaError_t PrepareScanKernels(int device)
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
 {
     const bool priv = variant == kVariantPriv && uniform;
-    plan->block = priv ? kPrivBlock : ((variant == kVariantLook || variant == kVariantLook64) && uniform) ? (LookRegs() == 48 ? kLookBlock48 : kLookBlock40) : kBlock;
-    if ((variant == kVariantLook || variant == kVariantLook64) && uniform) {
+    const bool look = variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1;
+    plan->block = priv ? kPrivBlock : (look && uniform) ? (LookRegs() == 48 ? kLookBlock48 : kLookBlock40) : kBlock;
+    if (look && uniform) {
         static const int look_block = [] {
             const char* env = getenv("PIRE_B200_LOOK_BLOCK");          // experiments: e.g. 640 = two CTAs of 20 warps at 48 registers
             return env && atoi(env) >= 32 && atoi(env) <= 1024 && atoi(env) % 32 == 0 ? atoi(env) : 0;
@@ -2974,7 +2990,7 @@ cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t
     const bool in_stream = forced == 2 || (forced != 1 && a.start < a.hot);
     if (in_stream && !(a.start < a.hot))
         return cudaErrorInvalidValue;
-    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64;
+    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1;
     const void* fn = in_stream ? (pred ? reinterpret_cast<const void*>(&ScanTextKernel<true>) : reinterpret_cast<const void*>(&ScanTextKernel<false>))
                                : (pred ? reinterpret_cast<const void*>(&ScanLinesKernel<true>) : reinterpret_cast<const void*>(&ScanLinesKernel<false>));
     const size_t shared = ScanSharedBytes(a.hot, 0) + (in_stream ? kTextFinBytes + kTextPackBytes : 0);
