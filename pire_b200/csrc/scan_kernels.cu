@@ -10,18 +10,23 @@
 //   * The table of hot rows (dfa_tables.hpp) is staged once per persistent CTA
 //     into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier).
 //   * A lane keeps its state as a hot id g in 0..H (H = "not in the table").
-//     One step is   bb = PRMT(word, base)  (input byte k in the low bits of the table's
-//     256-byte aligned shared address; independent of g, so it runs ahead),
+//     One step is   bb = IDP.4A(word, 1 << 8k, base)  (input byte k plus the table's
+//     256-byte aligned shared address, FMA pipe; PRMT in the prefix kernels; independent
+//     of g, so it runs ahead),
 //     addr = IMAD(g, 292, bb)  (rows are 292 bytes apart: consecutive rows start nine
 //     banks apart, which spreads the conflicts between lanes in different rows),
 //     g = LDS.U8 [addr].  No class lookup, no branch.
 //   * kPred variant: the LDS is predicated off while the lane sits in hot id 0
 //     and the byte cannot leave it (32-slot bitmap probed with a funnel shift),
 //     so fewer lanes hit the banks and the load costs fewer wavefronts.
+//   * LOOK variant (the glued benchmark scan): the filter looks one byte further -- a resting
+//     lane reads the table only if this byte and the next both pass -- in 5.5 instructions per
+//     byte (LookProbe / LookStep), two strings per lane (ScanUniformLook2Kernel).
 //   * Input bytes: each lane streams its own string: 32-byte read-only loads that
-//     bypass L1 allocation, one ahead in a register ping-pong (uniform kernel,
+//     bypass L1 allocation, one ahead in a register ping-pong (uniform kernels,
 //     LDG.256), or a four-deep cp.async ring of 16-byte chunks in shared memory
-//     (CSR kernels).  Lines of text have their own kernel: lanes pull lines one by one.
+//     (CSR kernels).  Long strings of a length-ordered batch are split over a warp
+//     (ScanSplitKernel); lines of text are scanned in stream (ScanTextKernel).
 //   * Prefix / suffix scans and HalfFinalScanner counting reuse the walk; final hot
 //     states carry the highest ids, so a running maximum per chunk says whether any
 //     step needs the per-byte work.
