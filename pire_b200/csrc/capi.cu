@@ -336,6 +336,14 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     uint32_t variant = ResolveVariant(sc, uniform);
     if (variant == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
         variant = PIRE_GPU_VARIANT_PLAIN;       // the private-row kernel exists for uniform batches only
+    if (variant == PIRE_GPU_VARIANT_LOOK && uniform && sc->variant == PIRE_GPU_VARIANT_AUTO) {
+        // two strings per lane pay when every resident warp gets a pair of units; a smaller batch (a 64 MiB chunk of
+        // the host entry point, say) keeps more warps busy with one string per lane
+        const LaunchPlan& two = sc->plan[PIRE_GPU_VARIANT_LOOK][1];
+        const uint64_t pairs = ((n + 31) / 32 + 1) / 2;
+        if (pairs < (uint64_t) two.grid * (uint64_t) (two.block / 32))
+            variant = PIRE_GPU_VARIANT_LOOK1;
+    }
     CUDA_TRY(LaunchScan(a, (int) variant, uniform, sc->plan[variant][uniform ? 1 : 0], static_cast<cudaStream_t>(stream)));
     return PIRE_GPU_OK;
 }
