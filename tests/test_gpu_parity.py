@@ -272,6 +272,29 @@ def test_look_variant_dense_near_misses(length, cuda_device, ref):
                     assert (r.States() == s_ref).all(), (variant, tuned, begin, end)
 
 
+def test_auto_picks_the_shape_of_the_look_ahead_walk_by_batch_size(cuda_device, ref):
+    """AUTO on a large automaton means the look-ahead filter: two strings per lane when the batch gives every resident
+    warp a pair of units, one string per lane below that (capi.cu).  Both sides of the threshold, odd and partial last
+    units, against the reference."""
+    import torch
+    import pire_b200 as P
+    from pire_b200 import _native as N
+    from pire_b200 import workloads as W
+    sc_ref = ref.glue_all(W.GLUE10)
+    sc = P.Scanner(W.load_image("glue10"), cuda_device)
+    assert sc.info().variant == N.VARIANT_LOOK                      # AUTO, no timing run: > 64 states, look-ahead set complete
+    length = 64
+    for n in (33, 1000 + 7, 64 * 6000 + 32 + 5):                    # one pair, a few hundred pairs, more pairs than resident warps
+        spec = W.SynthSpec(n, length, plants=[p[:40] for p in W.GLUE10_PLANTS], plant_every=3)
+        dev = torch.empty(spec.total_bytes(), dtype=torch.uint8, device="cuda:0")
+        spec.fill_device(dev)
+        host = dev.cpu().numpy()
+        f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=length, n=n, variant=1, threads=8)
+        r = P.Runner(sc).Begin().Run(P.Batch(dev, fixed_len=length, n=n)).End()
+        assert (r.Matches().astype(np.uint8) == f_ref).all(), n
+        assert (r.AcceptMasks() == m_ref).all() and (r.States() == s_ref).all(), n
+
+
 def test_noexit_early_stop_is_exact(cuda_device, ref):
     """multi.h:955-958: a state no byte can leave ends the walk early; End() must still be
     stepped.  'foo' un-anchored parks every matching string in an absorbing state."""
