@@ -138,10 +138,14 @@ struct HostSlot {
     size_t h_in_bytes = 0;
     uint8_t* d_in = nullptr;
     size_t d_in_bytes = 0;
+    // capacities are kept per buffer: an allocation that fails leaves ITS capacity at zero, so the next call allocates
+    // again instead of trusting a pointer that is gone
     uint64_t* h_off = nullptr;
+    size_t h_off_cap = 0;         // entries
     uint64_t* d_off = nullptr;
     size_t off_cap = 0;           // entries
     uint32_t* h_out = nullptr;
+    size_t h_out_cap = 0;         // words
     uint32_t* d_out = nullptr;
     size_t out_cap = 0;           // words
     uint32_t* d_order = nullptr;
@@ -205,13 +209,17 @@ cudaError_t GrowDevice(T** p, size_t* cap, size_t want)
 }
 
 template <class T>
-cudaError_t GrowPinned(T** p, size_t have, size_t want)
+cudaError_t GrowPinned(T** p, size_t* cap, size_t want)
 {
-    if (have >= want && *p)
+    if (*cap >= want)
         return cudaSuccess;
     cudaFreeHost(*p);
     *p = nullptr;
-    return cudaHostAlloc(p, want * sizeof(T), cudaHostAllocDefault);
+    *cap = 0;
+    cudaError_t err = cudaHostAlloc(p, want * sizeof(T), cudaHostAllocDefault);
+    if (err == cudaSuccess)
+        *cap = want;
+    return err;
 }
 
 struct Caller {
@@ -299,25 +307,18 @@ int RunStreamed(const pire_gpu_scanner* sc, HostWorkspace* ws, const Caller& c, 
 
         CUDA_TRY(GrowDevice(&s.d_in, &s.d_in_bytes, bytes + 64));
         if (out_words) {
-            if (s.out_cap < out_words) {
-                CUDA_TRY(GrowPinned(&s.h_out, s.out_cap, out_words));
-                CUDA_TRY(GrowDevice(&s.d_out, &s.out_cap, out_words));
-            }
+            CUDA_TRY(GrowPinned(&s.h_out, &s.h_out_cap, out_words));
+            CUDA_TRY(GrowDevice(&s.d_out, &s.out_cap, out_words));
         }
         const uint8_t* dma_src = c.corpus ? c.corpus + byte_lo : nullptr;
         if (!pinned_in && bytes) {
-            if (s.h_in_bytes < bytes) {
-                CUDA_TRY(GrowPinned(&s.h_in, s.h_in_bytes, bytes));
-                s.h_in_bytes = bytes;
-            }
+            CUDA_TRY(GrowPinned(&s.h_in, &s.h_in_bytes, bytes));
             ws->pool->Copy(s.h_in, c.corpus + byte_lo, bytes);
             dma_src = s.h_in;
         }
         if (csr) {
-            if (s.off_cap < count + 1) {
-                CUDA_TRY(GrowPinned(&s.h_off, s.off_cap, (size_t) count + 1));
-                CUDA_TRY(GrowDevice(&s.d_off, &s.off_cap, (size_t) count + 1));
-            }
+            CUDA_TRY(GrowPinned(&s.h_off, &s.h_off_cap, (size_t) count + 1));
+            CUDA_TRY(GrowDevice(&s.d_off, &s.off_cap, (size_t) count + 1));
             uint64_t prev = byte_lo;
             for (uint64_t i = 0; i <= count; ++i) {
                 const uint64_t o = c.offsets[first + i];
