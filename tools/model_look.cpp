@@ -30,6 +30,7 @@ struct Hash {
     std::string name;
     uint32_t slots;
     std::function<uint32_t(uint32_t)> slot;
+    std::function<uint32_t(uint32_t)> slot_odd;       // if set: the slot function of the bytes at odd positions
 };
 
 static int PassCount(const bool* set, const Hash& h)
@@ -207,14 +208,37 @@ int main(int argc, char** argv)
                           }});
     }
 
+    // staircase slots: slot = mulhi(address + b, mul) & 31 -- what ONE multiply-high of (table address + byte) by a
+    // constant gives (IMAD.HI, FMA pipe; the LOOKH variant): runs of neighbouring byte values share a slot, so a filter
+    // whose bytes cluster in the code table (digits, neighbouring letters) keeps its false positives next to its members.
+    // The multiplier is the one the library would choose (ChooseLookMul) for a table at shared address 1024 (MODEL_BASE).
+    {
+        const uint32_t address = std::getenv("MODEL_BASE") ? (uint32_t) std::atoi(std::getenv("MODEL_BASE")) : 1024u;
+        const uint32_t mul = ChooseLookMul(t.look_exact, address);
+        const uint32_t filter = FoldLookFilter(t.look_exact, address, mul);
+        char name[64];
+        std::snprintf(name, sizeof(name), "mulhi32F(mul=%08x)", mul);
+        Hash h{name, 32, [=](uint32_t b) { return (uint32_t) (((uint64_t) (address + b) * mul) >> 32) & 31u; }};
+        std::printf("%s alpha %.4f passes %d of 95, folded filter %08x (%d slots)\n", name, mul / 4294967296.0, PassCount(F, h), filter,
+                    __builtin_popcount(filter));
+        hashes.push_back(h);
+        Hash half{std::string(name) + " even bytes only", 32, h.slot, [](uint32_t b) { return b & 31u; }};
+        hashes.push_back(half);
+        hashes.push_back({"stair32(b>>2)", 32, [](uint32_t b) { return (b >> 2) & 31u; }});
+    }
+
     for (const Hash& h : hashes) {
-        std::vector<uint8_t> f1(h.slots, 0), ff(h.slots, 0);
+        std::vector<uint8_t> f1(h.slots, 0), ff(h.slots, 0), ffo(h.slots, 0);
         for (uint32_t b = 0; b < 256; ++b) {
             if (F1[b])
                 f1[h.slot(b)] = 1;
             if (F[b])
                 ff[h.slot(b)] = 1;
+            if (F[b] && h.slot_odd)
+                ffo[h.slot_odd(b)] = 1;
         }
+        // filter of a byte at position k (look mode): positions alternate between the two slot functions when slot_odd is set
+        auto passes = [&](uint32_t b, uint32_t k) -> bool { return (h.slot_odd && (k & 1)) ? ffo[h.slot_odd(b)] != 0 : ff[h.slot(b)] != 0; };
         uint64_t steps = 0, wf[2] = {0, 0}, act[2] = {0, 0}, nonzero[2] = {0, 0};
         uint64_t mismatch = 0;
         for (uint64_t base = 0; base + 32 <= n; base += 32) {
@@ -240,7 +264,7 @@ int main(int argc, char** argv)
                         else if (alt && (k & 1))
                             need = gg != 0 || ff[h.slot(b)];            // ALT: odd positions use the byte's own filter only
                         else
-                            need = gg != 0 || (ff[h.slot(b)] && (last || !look_ok || ff[h.slot(nb)]));
+                            need = gg != 0 || (passes(b, k) && (last || !look_ok || passes(nb, k + 1)));
                         nonzero[mode] += gg != 0;
                         if (need) {
                             const uint32_t addr = gg * stride + b;
