@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--impl", default="pire_b200", choices=["pire_b200", "reference"])
     ap.add_argument("--workload", default="glue10", choices=["glue10", "headline", "utf8mixed"])
     ap.add_argument("--strings", type=int, default=0, help="strings per GPU (default: 10 GB worth)")
-    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look", "look64", "look1", "lookh"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "plain", "pred", "priv", "look", "look64", "look1"])
     ap.add_argument("--no-tune", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -463,7 +463,7 @@ class Resident:
 
     def kernel_name(self):
         if self.mixed:
-            mode = {"plain": "plain", "look": "look", "look64": "look", "look1": "look", "lookh": "look"}.get(self.chosen, "pred")
+            mode = {"plain": "plain", "look": "look", "look64": "look", "look1": "look"}.get(self.chosen, "pred")
             if os.environ.get("PIRE_B200_SPLIT", "1") == "0":
                 return "ScanGenericKernel<%s>" % mode
             return "ScanSplitKernel<%s> (strings >= 8 KiB, one per warp) + ScanGenericKernel<%s> (the rest)" % (
@@ -471,10 +471,7 @@ class Resident:
         look = "ScanUniformLookKernel<32 slots>" if os.environ.get("PIRE_B200_LOOK_ILP", "2") == "1" \
             else "ScanUniformLook2Kernel<%s regs> (two strings per lane, 32-slot look-ahead filter)" % os.environ.get("PIRE_B200_LOOK_ILP_REGS", "72")
         return {"priv": "ScanUniformPrivKernel", "look": look, "look1": "ScanUniformLookKernel<32 slots> (one string per lane)",
-                "look64": "ScanUniformLookKernel<64 slots>",
-                "lookh": "ScanUniformLook2Kernel<72 regs, hashed slots> (two strings per lane, look-ahead filter with %s hashed)" % (
-                    "every byte's slot" if os.environ.get("PIRE_B200_LOOKH_MODE") == "1" else "the even bytes' slots"),
-                }.get(self.chosen, "ScanUniformKernel<%s>" % self.chosen)
+                "look64": "ScanUniformLookKernel<64 slots>"}.get(self.chosen, "ScanUniformKernel<%s>" % self.chosen)
 
 
 def parity_check(res, world, bits=None, dense=1 << 22, cpu_timing=None):

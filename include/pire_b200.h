@@ -63,9 +63,6 @@ enum {
     PIRE_GPU_VARIANT_LOOK1 = 6,    /* LOOK walks two strings per lane on fixed-length batches (the second string's step fills
                                       the latency of the first one's table read); LOOK1 is the same filter with one string per
                                       lane -- the shape for batches too small to give every resident warp two units */
-    PIRE_GPU_VARIANT_LOOKH = 7,    /* LOOK (two strings per lane) with the filter's 32 slots assigned by a multiplicative hash of
-                                      the byte, chosen per automaton: one more FMA-pipe instruction per byte, far fewer false
-                                      passes when the filter's bytes cluster in the code table; fixed-length batches only */
     PIRE_GPU_VARIANT_SLOTS = 8     /* length of per-variant arrays indexed by variant id */
 };
 

@@ -19,10 +19,10 @@ COMM_ID_BYTES = 128
 RUN_BEGIN = 1
 RUN_END = 2
 RUN_LINES = 4
-VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV, VARIANT_LOOK, VARIANT_LOOK64, VARIANT_LOOK1, VARIANT_LOOKH = 0, 1, 2, 3, 4, 5, 6, 7
+VARIANT_AUTO, VARIANT_PLAIN, VARIANT_PRED, VARIANT_PRIV, VARIANT_LOOK, VARIANT_LOOK64, VARIANT_LOOK1 = 0, 1, 2, 3, 4, 5, 6
 VARIANT_SLOTS = 8
 VARIANT_NAMES = {VARIANT_PLAIN: "plain", VARIANT_PRED: "pred", VARIANT_PRIV: "priv", VARIANT_LOOK: "look", VARIANT_LOOK64: "look64",
-                 VARIANT_LOOK1: "look1", VARIANT_LOOKH: "lookh"}
+                 VARIANT_LOOK1: "look1"}
 
 # every symbol include/pire_b200.h declares
 SYMBOLS = [

@@ -54,7 +54,7 @@ void DeviceTables::Free()
 
 uint32_t ResolveVariant(const pire_gpu_scanner* sc, bool uniform)
 {
-    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_LOOKH) {
+    if (sc->variant >= PIRE_GPU_VARIANT_PLAIN && sc->variant <= PIRE_GPU_VARIANT_LOOK1) {
         if (sc->variant >= PIRE_GPU_VARIANT_LOOK && !sc->tab.look_ok)
             return PIRE_GPU_VARIANT_PRED;       // an exit of the resting state is cold: no look-ahead set
         return sc->variant;
@@ -130,15 +130,8 @@ int Upload(pire_gpu_scanner* sc)
         CUDA_TRY(cudaMalloc(&d.accept_wide, wide.size() * 4));
         CUDA_TRY(cudaMemcpy(d.accept_wide, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice));
     }
-    // LOOKH: the slot function sees byte + table address, so its multiplier is chosen for this device's address
-    sc->tab.look_mul = 0;
-    if (t.look_ok) {
-        uint32_t address = 0;
-        CUDA_TRY(QueryTableAddress(sc->device, &address));
-        sc->tab.look_mul = ChooseLookMul(t.look_exact, address);
-    }
     sc->priv_ok = false;
-    for (int v = kVariantPlain; v <= kVariantLookH; ++v)
+    for (int v = kVariantPlain; v <= kVariantLook1; ++v)
         for (int u = 0; u < 2; ++u) {
             cudaError_t pe = PlanScan(sc->device, t.hot, t.hot_small, t.priv_rows, v, u != 0, &sc->plan[v][u]);
             if (v == kVariantPriv && u == 1) {
@@ -188,9 +181,6 @@ void FillArgs(const pire_gpu_scanner* sc, ScanArgs* a, const uint8_t* corpus, co
     a->exit_bitmap0 = t.exit_bitmap0;
     a->look_bitmap = t.look_bitmap;
     a->look_bitmap64 = t.look_bitmap64;
-    for (int w = 0; w < 8; ++w)
-        a->look_exact[w] = t.look_exact[w];
-    a->look_mul = t.look_mul;
     a->priv_packed = sc->dev.priv_packed;
     a->priv_rows = t.priv_rows;
     a->hot8_small = sc->dev.hot8_small;
@@ -294,7 +284,7 @@ int pire_gpu_scanner_info(const pire_gpu_scanner* sc, pire_gpu_info* out)
 
 int pire_gpu_scanner_set_variant(pire_gpu_scanner* sc, uint32_t variant)
 {
-    if (!sc || variant > PIRE_GPU_VARIANT_LOOKH)
+    if (!sc || variant > PIRE_GPU_VARIANT_LOOK1)
         return Fail(PIRE_GPU_EINVAL, "bad variant");
     sc->variant = variant;
     return PIRE_GPU_OK;
@@ -346,10 +336,10 @@ int pire_gpu_run_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, cons
     uint32_t variant = ResolveVariant(sc, uniform);
     if (variant == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
         variant = PIRE_GPU_VARIANT_PLAIN;       // the private-row kernel exists for uniform batches only
-    if ((variant == PIRE_GPU_VARIANT_LOOK || variant == PIRE_GPU_VARIANT_LOOKH) && uniform && sc->variant == PIRE_GPU_VARIANT_AUTO) {
+    if (variant == PIRE_GPU_VARIANT_LOOK && uniform && sc->variant == PIRE_GPU_VARIANT_AUTO) {
         // two strings per lane pay when every resident warp gets a pair of units; a smaller batch (a 64 MiB chunk of
         // the host entry point, say) keeps more warps busy with one string per lane
-        const LaunchPlan& two = sc->plan[variant][1];
+        const LaunchPlan& two = sc->plan[PIRE_GPU_VARIANT_LOOK][1];
         const uint64_t pairs = ((n + 31) / 32 + 1) / 2;
         if (pairs < (uint64_t) two.grid * (uint64_t) (two.block / 32))
             variant = PIRE_GPU_VARIANT_LOOK1;
@@ -666,12 +656,12 @@ int pire_gpu_scanner_autoselect(pire_gpu_scanner* sc, const uint8_t* d_corpus, c
     const uint32_t saved = sc->variant;
     uint32_t best = 0;
     float best_ms = 0.f;
-    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_LOOKH && ce == cudaSuccess; ++v) {
+    for (uint32_t v = PIRE_GPU_VARIANT_PLAIN; v <= PIRE_GPU_VARIANT_LOOK1 && ce == cudaSuccess; ++v) {
         if (v == PIRE_GPU_VARIANT_PRIV && !(uniform && sc->priv_ok))
             continue;
         if (v >= PIRE_GPU_VARIANT_LOOK && !sc->tab.look_ok)
             continue;
-        if ((v == PIRE_GPU_VARIANT_LOOK64 || v == PIRE_GPU_VARIANT_LOOK1 || v == PIRE_GPU_VARIANT_LOOKH) && !uniform)
+        if ((v == PIRE_GPU_VARIANT_LOOK64 || v == PIRE_GPU_VARIANT_LOOK1) && !uniform)
             continue;               // CSR batches have one look-ahead kernel
         sc->variant = v;
         float ms = 0.f;

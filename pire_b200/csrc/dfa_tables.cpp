@@ -154,18 +154,10 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
                 t.look_bitmap |= 1u << (b & 31);
                 t.look_bitmap64 |= 1ull << (b & 63);
             }
-        for (uint32_t w = 0; w < 8; ++w)
-            t.look_exact[w] = 0;
-        for (uint32_t b = 0; b < 256; ++b)
-            if (in_f[b])
-                t.look_exact[b >> 5] |= 1u << (b & 31);
         if (!t.look_ok) {
             t.look_bitmap = ~0u;
             t.look_bitmap64 = ~0ull;
-            for (uint32_t w = 0; w < 8; ++w)
-                t.look_exact[w] = ~0u;
         }
-        t.look_mul = 0;                      // chosen when the table's shared-memory address is known (capi.cu Upload)
     }
 
     // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,
@@ -254,44 +246,6 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
 
     t.start[0] = t.new_of_old[dfa.initial];                              // Initialize(), multi.h:161
     t.start[1] = t.new_of_old[dfa.Next(dfa.initial, kBeginMark)];        // Begin(), run.h:375
-}
-
-uint32_t FoldLookFilter(const uint32_t exact[8], uint32_t table_address, uint32_t mul)
-{
-    uint32_t filter = 0;
-    for (uint32_t b = 0; b < 256; ++b)
-        if (exact[b >> 5] >> (b & 31) & 1u)
-            filter |= 1u << ((uint32_t) (((uint64_t) (table_address + b) * mul) >> 32) & 31u);
-    return filter;
-}
-
-uint32_t ChooseLookMul(const uint32_t exact[8], uint32_t table_address)
-{
-    // slot(b) = floor(alpha * (a + b)) & 31 with alpha = mul / 2^32: a staircase whose steps are 1 / alpha byte values
-    // wide.  alpha runs over i / 1024; adding j * 2^32 / (32 a) to the multiplier moves the staircase by j / 32 of a
-    // step (and changes alpha by less than 0.001).
-    uint32_t best_mul = 0;
-    uint32_t best_cost = ~0u;
-    const uint64_t phase_step = table_address ? (1ull << 32) / (32ull * table_address) : 0;
-    for (uint32_t i = 92; i <= 1024; ++i) {
-        const uint64_t alpha = ((uint64_t) i << 32) / 1024;
-        for (uint32_t j = 0; j < (phase_step ? 32u : 1u); ++j) {
-            const uint64_t m64 = alpha + j * phase_step;
-            if (m64 == 0 || m64 > 0xffffffffull)
-                continue;
-            const uint32_t mul = (uint32_t) m64;
-            const uint32_t filter = FoldLookFilter(exact, table_address, mul);
-            uint32_t cost = 0;
-            for (uint32_t b = 0; b < 256 && cost < best_cost; ++b)
-                if (filter >> ((uint32_t) (((uint64_t) (table_address + b) * mul) >> 32) & 31u) & 1u)
-                    cost += (b >= 0x20 && b < 0x7f) ? 8 : 1;
-            if (cost < best_cost) {
-                best_cost = cost;
-                best_mul = mul;
-            }
-        }
-    }
-    return best_mul;
 }
 
 } // namespace pire_b200

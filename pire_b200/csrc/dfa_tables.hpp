@@ -70,13 +70,6 @@ struct ScanTables {
     uint32_t look_bitmap = ~0u;
     uint64_t look_bitmap64 = ~0ull;          // the same set with 64 slots (slot = b & 63): LOOK64 variant
     bool look_ok = false;
-    // LOOKH variant: the same set, exact (bit b & 31 of look_exact[b >> 5]).  The kernel folds it onto 32 slots with a
-    // slot function of its own, slot(b) = mulhi(a + b, look_mul) & 31 (a = the table's shared-memory address, which the
-    // walk adds to every byte anyway): runs of neighbouring byte values share a slot, so a set that clusters in the
-    // code table -- digits, a few letters -- keeps its false positives next to its members instead of folding
-    // "a", "A" and "!" together.  look_mul is chosen per automaton (ChooseLookMul) once the address is known.
-    uint32_t look_exact[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
-    uint32_t look_mul = 0;
     // Counting (HalfFinalScanner, half_final.h:154-163): hot ids >= first_final_hot are final states
     // (== hot when none is); accept lists in the new numbering as CSR, ids repeated as the image has them.
     uint32_t first_final_hot = 0;
@@ -111,14 +104,6 @@ std::vector<uint32_t> StaticHotOrder(const Dfa& dfa);
 // Hot order from observed visit counts (pire_gpu_scanner_tune): old ids by
 // descending count, ties by id; unvisited states are appended in static order.
 std::vector<uint32_t> HotOrderFromCounts(const Dfa& dfa, const std::vector<uint64_t>& visits);
-
-// The 32-slot filter of the LOOKH variant: bit mulhi(table_address + b, mul) & 31 for every byte b of the exact set.
-// The kernel computes the same fold on the device; this is its host mirror (the multiplier search, the host model
-// tools/model_look.cpp).
-uint32_t FoldLookFilter(const uint32_t exact[8], uint32_t table_address, uint32_t mul);
-// Multiplier that lets the fewest bytes pass the folded filter (printable ASCII weighted 8:1 over the other byte
-// values), searched over slot widths of 1 to 11 byte values and 32 phases.
-uint32_t ChooseLookMul(const uint32_t exact[8], uint32_t table_address);
 
 // hot_order lists old state ids, most important first; the first
 // min(kMaxHot, states, max_hot) become hot.

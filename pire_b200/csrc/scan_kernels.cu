@@ -472,57 +472,30 @@ struct LookFilter {
     uint32_t lo, hi;
     uint32_t zero;      // a kernel argument that is always 0: the addend that keeps the cleaning multiply an IMAD
     uint32_t rev;       // lo with its bits reversed (clean-bit kernels: probes of the odd bytes)
-    uint32_t mul;       // kHash: slot = mulhi(byte + table address, mul) & 31 instead of byte & 31
 };
-
-// The LOOKH variant's filter: the exact look-ahead set (256 bits in the kernel arguments) folded onto 32 slots with
-// slot(b) = mulhi(address + b, mul) & 31, `address` being the shared-window address of the hot rows of THIS launch -- the
-// host mirror is FoldLookFilter (dfa_tables.cpp).  Every warp folds for itself: a lane takes eight byte values, one
-// warp-wide OR joins them.
-__device__ __forceinline__ uint32_t FoldLookFilterDevice(const ScanArgs& a, uint32_t address)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t members = (a.look_exact[lane >> 2] >> (8 * (lane & 3))) & 0xffu;      // byte values 8 * lane .. 8 * lane + 7
-    uint32_t folded = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k)
-        if (members >> k & 1u)
-            folded |= 1u << (__umulhi(address + 8 * lane + k, a.look_mul) & 31u);
-    return __reduce_or_sync(0xffffffffu, folded);
-}
 
 // kClean: the probe's bit is moved to bit 31 with the bits below it cleared by one multiply (IMAD, FMA pipe: pa * 2^31
 // keeps bit 0 only), so that "both bytes pass, or the lane is outside id 0" is ONE LOP3 with a predicate result over
 // (pa, pa_next, g) instead of two: the step keeps six instructions, but two instead of three of them are on the
 // half-rate ALU pipe that ncu shows 66 % busy under the look-ahead kernel.
-// kHash (LOOKH variant): the probe's slot is mulhi(bb, mul) & 31 -- one IMAD.HI on the FMA pipe -- instead of the low
-// five bits of the byte.  Runs of neighbouring byte values share a slot (the width of a run is 2^32 / mul), which for a
-// filter set that clusters in the code table passes far fewer bytes than folding the table in three at a distance of
-// 32 (glued benchmark scanner: 32 of the 95 printable bytes pass instead of 51; host model 1.39 instead of 1.72
-// wavefronts per step).  The filter itself is folded on the device with the same function (FoldLookFilterDevice).
-// Hashing only the even bytes (kHash = 2) costs half an instruction per byte instead of one: a step ANDs the probes of an
-// even and an odd byte, so one sharp probe per pair already removes most false passes (model: 1.54 wavefronts).
-template <bool k64, int kByte, bool kClean = false, int kHash = 0>
+template <bool k64, int kByte, bool kClean = false>
 __device__ __forceinline__ void LookProbe(uint32_t w, uint32_t base, const LookFilter& f, uint32_t& bb, uint32_t& pa)
 {
     constexpr uint32_t sel = 1u << (8 * kByte);
     bb = __dp4a(w, sel, base);
-    // kHash 1: every byte is hashed; 2: the even bytes only (the odd bytes keep slot = byte & 31 and the plain filter in f.rev)
-    const bool hashed = kHash == 1 || (kHash == 2 && !(kByte & 1));
-    const uint32_t slot = hashed ? __umulhi(bb, f.mul) : bb;        // the funnel shifts below use its low five bits
     if (kClean && (kByte & 1)) {
         // odd bytes: the bit-reversed filter shifted LEFT puts the probe's bit in bit 31 with other filter bits below it.
         // That is good enough: the step ANDs the probes of two neighbouring bytes, one of them is always an even byte,
         // and an even byte's probe is clean -- so an odd byte costs one SHF, an even byte SHF + IMAD: 5.5 instructions
         // per step on average.
-        pa = __funnelshift_l(0u, f.rev, slot);
+        pa = __funnelshift_l(0u, f.rev, bb);
         return;
     }
     if (k64) {
-        const uint32_t slot64 = __dp4a(w & 0x3F3F3F3Fu, sel, 0u);
-        pa = (uint32_t) ((((uint64_t) f.hi << 32) | f.lo) >> slot64);
+        const uint32_t slot = __dp4a(w & 0x3F3F3F3Fu, sel, 0u);
+        pa = (uint32_t) ((((uint64_t) f.hi << 32) | f.lo) >> slot);
     } else {
-        pa = __funnelshift_r(f.lo, f.lo, slot);
+        pa = __funnelshift_r(f.lo, f.lo, bb);
     }
     if (kClean)
         asm("mad.lo.u32 %0, %1, 0x80000000, %2;" : "=r"(pa) : "r"(pa), "r"(f.zero));
@@ -723,28 +696,28 @@ __global__ void __maxnreg__(kRegs) ScanUniformLookKernel(const __grid_constant__
 // chains, and registers (48 per thread) cap the warps.  Here every lane walks TWO strings (units 2p and 2p+1 of the
 // batch) step by step in turn: the second string's step fills the latency of the first one's table read, and the
 // block bookkeeping is shared.  32 data registers (two LDG.256 ping-pong sets), __maxnreg__ chosen by the launch plan.
-template <bool kClean, int kHash = 0>
+template <bool kClean>
 __device__ __forceinline__ void LookWord2(uint32_t& ga, uint32_t wa, uint32_t bba0, uint32_t paa0, uint32_t pana, uint32_t& gb, uint32_t wb,
                                           uint32_t bbb0, uint32_t pab0, uint32_t panb, uint32_t base, const LookFilter& f)
 {
     uint32_t bba1, bba2, bba3, paa1, paa2, paa3, bbb1, bbb2, bbb3, pab1, pab2, pab3;
-    LookProbe<false, 1, kClean, kHash>(wa, base, f, bba1, paa1);
-    LookProbe<false, 1, kClean, kHash>(wb, base, f, bbb1, pab1);
+    LookProbe<false, 1, kClean>(wa, base, f, bba1, paa1);
+    LookProbe<false, 1, kClean>(wb, base, f, bbb1, pab1);
     LookStep<kClean>(ga, bba0, paa0, paa1);
     LookStep<kClean>(gb, bbb0, pab0, pab1);
-    LookProbe<false, 2, kClean, kHash>(wa, base, f, bba2, paa2);
-    LookProbe<false, 2, kClean, kHash>(wb, base, f, bbb2, pab2);
+    LookProbe<false, 2, kClean>(wa, base, f, bba2, paa2);
+    LookProbe<false, 2, kClean>(wb, base, f, bbb2, pab2);
     LookStep<kClean>(ga, bba1, paa1, paa2);
     LookStep<kClean>(gb, bbb1, pab1, pab2);
-    LookProbe<false, 3, kClean, kHash>(wa, base, f, bba3, paa3);
-    LookProbe<false, 3, kClean, kHash>(wb, base, f, bbb3, pab3);
+    LookProbe<false, 3, kClean>(wa, base, f, bba3, paa3);
+    LookProbe<false, 3, kClean>(wb, base, f, bbb3, pab3);
     LookStep<kClean>(ga, bba2, paa2, paa3);
     LookStep<kClean>(gb, bbb2, pab2, pab3);
     LookStep<kClean>(ga, bba3, paa3, pana);
     LookStep<kClean>(gb, bbb3, pab3, panb);
 }
 
-template <bool kClean, int kHash = 0>
+template <bool kClean>
 __device__ __forceinline__ void LookBlock32x2(const Tables& t, uint32_t& ga, uint32_t& preva, const uint4& a0, const uint4& a1, uint32_t nexta,
                                               uint32_t& gb, uint32_t& prevb, const uint4& b0, const uint4& b1, uint32_t nextb, bool more,
                                               const LookFilter& f, uint32_t opaque_zero, const ScanArgs* args)
@@ -752,35 +725,35 @@ __device__ __forceinline__ void LookBlock32x2(const Tables& t, uint32_t& ga, uin
     preva = ga == t.H ? preva : ga;
     prevb = gb == t.H ? prevb : gb;
     uint32_t bba, paa, bna, pna, bbb, pab, bnb, pnb;
-    LookProbe<false, 0, kClean, kHash>(a0.x, t.base, f, bba, paa);
-    LookProbe<false, 0, kClean, kHash>(b0.x, t.base, f, bbb, pab);
-    LookProbe<false, 0, kClean, kHash>(a0.y, t.base, f, bna, pna);
-    LookProbe<false, 0, kClean, kHash>(b0.y, t.base, f, bnb, pnb);
-    LookWord2<kClean, kHash>(ga, a0.x, bba, paa, pna, gb, b0.x, bbb, pab, pnb, t.base, f);
-    LookProbe<false, 0, kClean, kHash>(a0.z, t.base, f, bba, paa);
-    LookProbe<false, 0, kClean, kHash>(b0.z, t.base, f, bbb, pab);
-    LookWord2<kClean, kHash>(ga, a0.y, bna, pna, paa, gb, b0.y, bnb, pnb, pab, t.base, f);
-    LookProbe<false, 0, kClean, kHash>(a0.w, t.base, f, bna, pna);
-    LookProbe<false, 0, kClean, kHash>(b0.w, t.base, f, bnb, pnb);
-    LookWord2<kClean, kHash>(ga, a0.z, bba, paa, pna, gb, b0.z, bbb, pab, pnb, t.base, f);
-    LookProbe<false, 0, kClean, kHash>(a1.x, t.base, f, bba, paa);
-    LookProbe<false, 0, kClean, kHash>(b1.x, t.base, f, bbb, pab);
-    LookWord2<kClean, kHash>(ga, a0.w, bna, pna, paa, gb, b0.w, bnb, pnb, pab, t.base, f);
-    LookProbe<false, 0, kClean, kHash>(a1.y, t.base, f, bna, pna);
-    LookProbe<false, 0, kClean, kHash>(b1.y, t.base, f, bnb, pnb);
-    LookWord2<kClean, kHash>(ga, a1.x, bba, paa, pna, gb, b1.x, bbb, pab, pnb, t.base, f);
-    LookProbe<false, 0, kClean, kHash>(a1.z, t.base, f, bba, paa);
-    LookProbe<false, 0, kClean, kHash>(b1.z, t.base, f, bbb, pab);
-    LookWord2<kClean, kHash>(ga, a1.y, bna, pna, paa, gb, b1.y, bnb, pnb, pab, t.base, f);
-    LookProbe<false, 0, kClean, kHash>(a1.w, t.base, f, bna, pna);
-    LookProbe<false, 0, kClean, kHash>(b1.w, t.base, f, bnb, pnb);
-    LookWord2<kClean, kHash>(ga, a1.z, bba, paa, pna, gb, b1.z, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a0.x, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b0.x, t.base, f, bbb, pab);
+    LookProbe<false, 0, kClean>(a0.y, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b0.y, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a0.x, bba, paa, pna, gb, b0.x, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a0.z, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b0.z, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a0.y, bna, pna, paa, gb, b0.y, bnb, pnb, pab, t.base, f);
+    LookProbe<false, 0, kClean>(a0.w, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b0.w, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a0.z, bba, paa, pna, gb, b0.z, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a1.x, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b1.x, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a0.w, bna, pna, paa, gb, b0.w, bnb, pnb, pab, t.base, f);
+    LookProbe<false, 0, kClean>(a1.y, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b1.y, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a1.x, bba, paa, pna, gb, b1.x, bbb, pab, pnb, t.base, f);
+    LookProbe<false, 0, kClean>(a1.z, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(b1.z, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a1.y, bna, pna, paa, gb, b1.y, bnb, pnb, pab, t.base, f);
+    LookProbe<false, 0, kClean>(a1.w, t.base, f, bna, pna);
+    LookProbe<false, 0, kClean>(b1.w, t.base, f, bnb, pnb);
+    LookWord2<kClean>(ga, a1.z, bba, paa, pna, gb, b1.z, bbb, pab, pnb, t.base, f);
     // the words after the blocks are still on their way from HBM: their probes stay behind the walk (see LookBlock32)
     const uint32_t latea = nexta + ga * opaque_zero;
     const uint32_t lateb = nextb + gb * opaque_zero;
-    LookProbe<false, 0, kClean, kHash>(latea, t.base, f, bba, paa);
-    LookProbe<false, 0, kClean, kHash>(lateb, t.base, f, bbb, pab);
-    LookWord2<kClean, kHash>(ga, a1.w, bna, pna, more ? paa : 0x80000000u, gb, b1.w, bnb, pnb, more ? pab : 0x80000000u, t.base, f);
+    LookProbe<false, 0, kClean>(latea, t.base, f, bba, paa);
+    LookProbe<false, 0, kClean>(lateb, t.base, f, bbb, pab);
+    LookWord2<kClean>(ga, a1.w, bna, pna, more ? paa : 0x80000000u, gb, b1.w, bnb, pnb, more ? pab : 0x80000000u, t.base, f);
     if (ga == t.H) {
         preva = ReplayBlock32(args, preva, a0, a1);
         ga = preva < t.H ? preva : t.H;
@@ -791,7 +764,7 @@ __device__ __forceinline__ void LookBlock32x2(const Tables& t, uint32_t& ga, uin
     }
 }
 
-template <int kRegs, int kHash = 0>
+template <int kRegs>
 __global__ void __maxnreg__(kRegs) ScanUniformLook2Kernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
@@ -808,11 +781,10 @@ __global__ void __maxnreg__(kRegs) ScanUniformLook2Kernel(const __grid_constant_
     t.wide = a.wide;
     t.m0 = a.look_bitmap;
     LookFilter f;
-    f.lo = kHash ? FoldLookFilterDevice(a, t.base) : a.look_bitmap;
+    f.lo = a.look_bitmap;
     f.hi = 0;
     f.zero = a.opaque_zero;
-    f.rev = __brev(kHash == 2 ? a.look_bitmap : f.lo);      // kHash 2: the odd bytes are probed with slot = byte & 31
-    f.mul = a.look_mul;
+    f.rev = __brev(f.lo);
 
     const uint32_t units = (uint32_t) ((a.n + 31) / 32);
     const uint32_t pairs = (units + 1) / 2;
@@ -844,7 +816,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLook2Kernel(const __grid_constant_
                         LoadStream32(pb, d0, d1);
                     }
                     __syncwarp();          // scheduling fence: the loads stay up here (see ScanUniformLookKernel)
-                    LookBlock32x2<true, kHash>(t, ga, preva, a0, a1, c0.x, gb, prevb, b0, b1, d0.x, more_c, f, a.opaque_zero, &a);
+                    LookBlock32x2<true>(t, ga, preva, a0, a1, c0.x, gb, prevb, b0, b1, d0.x, more_c, f, a.opaque_zero, &a);
                     if (!more_c)
                         break;
                     const bool more_a = left > 2;
@@ -855,7 +827,7 @@ __global__ void __maxnreg__(kRegs) ScanUniformLook2Kernel(const __grid_constant_
                         LoadStream32(pb, b0, b1);
                     }
                     __syncwarp();
-                    LookBlock32x2<true, kHash>(t, ga, preva, c0, c1, a0.x, gb, prevb, d0, d1, b0.x, more_a, f, a.opaque_zero, &a);
+                    LookBlock32x2<true>(t, ga, preva, c0, c1, a0.x, gb, prevb, d0, d1, b0.x, more_a, f, a.opaque_zero, &a);
                     left -= 2;
                     if (!more_a || __all_sync(0xffffffffu, (sv.noexit[ga] & sv.noexit[gb]) != 0))
                         break;
@@ -2799,23 +2771,10 @@ int LookIlpRegs()
     return regs;
 }
 
-// LOOKH hashes the even bytes only (half an instruction per byte); PIRE_B200_LOOKH_MODE=1 hashes every byte.
-int LookHashMode()
-{
-    static const int mode = [] {
-        const char* env = getenv("PIRE_B200_LOOKH_MODE");
-        return env && atoi(env) == 1 ? 1 : 2;
-    }();
-    return mode;
-}
-
 const void* KernelFor(int variant, bool uniform)
 {
     if (variant == kVariantPriv && uniform)
         return reinterpret_cast<const void*>(&ScanUniformPrivKernel);
-    if (variant == kVariantLookH && uniform)
-        return LookHashMode() == 1 ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<72, 1>)
-                                   : reinterpret_cast<const void*>(&ScanUniformLook2Kernel<72, 2>);
     if (variant == kVariantLook && uniform && LookIlp() == 2)
         return LookIlpRegs() == 64   ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<64>)
                : LookIlpRegs() == 80 ? reinterpret_cast<const void*>(&ScanUniformLook2Kernel<80>)
@@ -2831,46 +2790,12 @@ const void* KernelFor(int variant, bool uniform)
                                 : reinterpret_cast<const void*>(&ScanUniformLookKernel<true, 40>);
     if (uniform)
         return variant == kVariantPred ? UniformKernelPtr<true>() : UniformKernelPtr<false>();
-    if (variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1 || variant == kVariantLookH)
-        return GenericKernelPtr<2>();          // CSR batches: one look-ahead kernel (32-slot filter)
+    if (variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1)      // CSR batches: one look-ahead kernel (32-slot filter)
+        return GenericKernelPtr<2>();
     return variant == kVariantPred ? GenericKernelPtr<1>() : GenericKernelPtr<0>();
 }
 
 } // namespace
-
-namespace {
-__global__ void TableAddressKernel(uint32_t* out) { *out = SmemWindowBase(); }
-} // namespace
-
-// The hot rows are the first thing in the dynamic shared-memory array of every uniform kernel (CarveShared without a
-// private region); the array's shared-window address is a property of the module, asked of the device once.
-cudaError_t QueryTableAddress(int device, uint32_t* address)
-{
-    static std::mutex mu;
-    static uint32_t cached[64];
-    static bool have[64];
-    std::lock_guard<std::mutex> lock(mu);
-    if (device >= 0 && device < 64 && have[device]) {
-        *address = cached[device];
-        return cudaSuccess;
-    }
-    cudaError_t err = cudaSetDevice(device);
-    uint32_t* d = nullptr;
-    if (err == cudaSuccess)
-        err = cudaMalloc(&d, 4);
-    if (err != cudaSuccess)
-        return err;
-    TableAddressKernel<<<1, 1, 16>>>(d);
-    err = cudaGetLastError();
-    if (err == cudaSuccess)
-        err = cudaMemcpy(address, d, 4, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (err == cudaSuccess && device >= 0 && device < 64) {
-        cached[device] = *address;
-        have[device] = true;
-    }
-    return err;
-}
 
 size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows) { return PrivBytes(priv_rows) + HotBytes(hot) + 512 + 256 + 16; }
 size_t GenericSharedBytes(uint32_t hot) { return ScanSharedBytes(hot, 0) + kStageBytes; }
@@ -2884,8 +2809,7 @@ cudaError_t PrepareScanKernels(int device)
     err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err != cudaSuccess)
         return err;
-    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook, (int) kVariantLook64, (int) kVariantLook1,
-                        (int) kVariantLookH})
+    for (int variant : {(int) kVariantPlain, (int) kVariantPred, (int) kVariantPriv, (int) kVariantLook, (int) kVariantLook64, (int) kVariantLook1})
         for (bool uniform : {false, true}) {
             err = cudaFuncSetAttribute(KernelFor(variant, uniform), cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
             if (err != cudaSuccess)
@@ -2903,7 +2827,7 @@ cudaError_t PrepareScanKernels(int device)
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan)
 {
     const bool priv = variant == kVariantPriv && uniform;
-    const bool look = variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1 || variant == kVariantLookH;
+    const bool look = variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1;
     plan->block = priv ? kPrivBlock : (look && uniform) ? (LookRegs() == 48 ? kLookBlock48 : kLookBlock40) : kBlock;
     if (look && uniform) {
         static const int look_block = [] {
@@ -2912,8 +2836,6 @@ cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv
         }();
         if (variant == kVariantLook && LookIlp() == 2)
             plan->block = LookIlpRegs() == 64 ? 512 : LookIlpRegs() == 80 ? 384 : 448;
-        if (variant == kVariantLookH)
-            plan->block = 448;                 // two strings per lane at 72 registers, as the default look-ahead shape
         if (look_block)
             plan->block = look_block;
     }
@@ -2938,7 +2860,7 @@ cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const Launc
     if (a.n == 0)
         return cudaSuccess;
     uint64_t units = (a.n + 31) / 32;
-    if (uniform && (variant == kVariantLookH || (variant == kVariantLook && LookIlp() == 2)))
+    if (variant == kVariantLook && uniform && LookIlp() == 2)
         units = (units + 1) / 2;              // a warp of ScanUniformLook2Kernel takes two units at a time
     const uint64_t warps_per_block = (uint64_t) plan.block / 32;
     uint64_t want = (units + warps_per_block - 1) / warps_per_block;
@@ -3073,8 +2995,7 @@ cudaError_t LaunchLines(const ScanArgs& a, int variant, int device, cudaStream_t
     const bool in_stream = forced == 2 || (forced != 1 && a.start < a.hot);
     if (in_stream && !(a.start < a.hot))
         return cudaErrorInvalidValue;
-    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1 ||
-                      variant == kVariantLookH;
+    const bool pred = variant == kVariantPred || variant == kVariantLook || variant == kVariantLook64 || variant == kVariantLook1;
     const void* fn = in_stream ? (pred ? reinterpret_cast<const void*>(&ScanTextKernel<true>) : reinterpret_cast<const void*>(&ScanTextKernel<false>))
                                : (pred ? reinterpret_cast<const void*>(&ScanLinesKernel<true>) : reinterpret_cast<const void*>(&ScanLinesKernel<false>));
     const size_t shared = ScanSharedBytes(a.hot, 0) + (in_stream ? kTextFinBytes + kTextPackBytes : 0);

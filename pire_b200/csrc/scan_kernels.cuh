@@ -39,8 +39,6 @@ struct ScanArgs {
     uint32_t exit_bitmap0;       // 32-slot exit bitmap of hot id 0, slot = byte & 31
     uint32_t look_bitmap;        // LOOK variant: 32-slot look-ahead filter (dfa_tables.hpp), slot = byte & 31
     uint64_t look_bitmap64;      // LOOK64 variant: the same filter with 64 slots, slot = byte & 63
-    uint32_t look_exact[8];      // LOOKH variant: the same set, exact (bit b & 31 of word b >> 5); folded in the kernel
-    uint32_t look_mul;           // LOOKH variant: slot = mulhi(byte + table address, look_mul) & 31
     uint32_t uniform;            // prefix / count kernels: fixed length, a multiple of 32 bytes, corpus 32-byte aligned
     uint32_t opaque_zero;        // always 0; the LOOK kernels multiply by it to pin an instruction behind the walk
     const uint32_t* priv_packed; // (priv_rows/4)*128 words, PRIV variant
@@ -78,14 +76,11 @@ struct LaunchPlan {
     size_t shared = 0;
 };
 
-enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3, kVariantLook = 4, kVariantLook64 = 5, kVariantLook1 = 6, kVariantLookH = 7 };
+enum ScanVariant { kVariantPlain = 1, kVariantPred = 2, kVariantPriv = 3, kVariantLook = 4, kVariantLook64 = 5, kVariantLook1 = 6 };
 constexpr int kVariantSlots = 8;      // size of per-variant arrays (variant ids are 1-based)
 
 size_t ScanSharedBytes(uint32_t hot, uint32_t priv_rows);
 cudaError_t PrepareScanKernels(int device);                       // raises the dynamic smem limit
-// shared-window address of the hot rows in the uniform kernels (the dynamic shared-memory array's base): what the
-// LOOKH variant's slot function adds to every byte
-cudaError_t QueryTableAddress(int device, uint32_t* address);
 cudaError_t PlanScan(int device, uint32_t hot, uint32_t hot_small, uint32_t priv_rows, int variant, bool uniform, LaunchPlan* plan);
 cudaError_t LaunchScan(const ScanArgs& a, int variant, bool uniform, const LaunchPlan& plan, cudaStream_t stream);
 // CSR batches of short strings (lines of text): lanes pull strings dynamically; a.match_bits must be zeroed

@@ -34,7 +34,7 @@ def checker_run(image, strings, begin, end, ref_sc=None):
     return Oracle(image).run(corpus, offs, begin=begin, end=end)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 4, 6, 7], ids=["plain", "pred", "look", "look1", "lookh"])
+@pytest.mark.parametrize("variant", [1, 2, 4, 6], ids=["plain", "pred", "look", "look1"])
 @pytest.mark.parametrize("case", GOLDEN, ids=lambda c: c.name)
 def test_golden_vectors(case, variant, cuda_device):
     import pire_b200 as P
@@ -114,7 +114,7 @@ def random_text(rng, n, length, alphabet=None):
     return rng.choice(np.frombuffer(alphabet, np.uint8), size=(n, length))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7], ids=["plain", "pred", "priv", "look", "look64", "look1", "lookh"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6], ids=["plain", "pred", "priv", "look", "look64", "look1"])
 def test_uniform_kernel_headline(variant, cuda_device, ref):
     """Fixed 1 KiB strings (the BASELINE configs' shape) through the uniform kernel,
     full comparison with the reference on 64 Ki strings, incl. StateIndex."""
@@ -199,7 +199,7 @@ def test_generic_kernel_mixed_lengths_utf8(cuda_device, ref):
     assert int(want[0].sum()) >= len(strings) // 5
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7], ids=["plain", "pred", "priv", "look", "look64", "look1", "lookh"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6], ids=["plain", "pred", "priv", "look", "look64", "look1"])
 def test_uniform_kernel_binary_bytes(variant, cuda_device, ref):
     """Fixed-length strings over the whole byte range (UTF-8 pattern): the private-row
     kernel covers bytes < 128 only and must re-walk every word holding a byte >= 128."""
@@ -228,8 +228,7 @@ def test_uniform_kernel_binary_bytes(variant, cuda_device, ref):
 
 @pytest.mark.parametrize("length", [32, 64, 96, 480, 1024])
 def test_look_variant_dense_near_misses(length, cuda_device, ref):
-    """LOOK variants (one byte of look-ahead over the exit filter; LOOKH = the same with hashed filter slots, its
-    multiplier re-chosen by Tune): text made almost only of the bytes that start
+    """LOOK variant (one byte of look-ahead over the exit filter): text made almost only of the bytes that start
     or continue the ten patterns, so that nearly every position is an exit byte followed by a continuing or a
     non-continuing byte, strings that end on exit bytes and on half matches, every mark combination, static and
     tuned hot rows.  Everything must equal the reference (and the plain kernel)."""
@@ -262,7 +261,7 @@ def test_look_variant_dense_near_misses(length, cuda_device, ref):
         for begin in (True, False):
             for end in (True, False):
                 f_ref, m_ref, s_ref = sc_ref.run(host, fixed_len=length, n=n, begin=begin, end=end, variant=1, threads=8)
-                for variant in (1, 4, 5, 6, 7):
+                for variant in (1, 4, 5, 6):
                     sc.set_variant(variant)
                     r = P.Runner(sc)
                     r = r.Begin() if begin else r

@@ -1,9 +1,10 @@
 """The look-ahead exit filters on the CPU: the host model (tools/model_look.cpp) walks the glued benchmark scanner over
-synthetic text with every slot function the kernels use -- byte & 31 (LOOK), byte & 63 (LOOK64), and the multiplicative
-hash whose multiplier the library chooses per automaton (LOOKH: dfa_tables.cpp ChooseLookMul / FoldLookFilter, also with
-only the even positions hashed, as the kernel does by default) -- and compares the end state of every string with the
-plain walk.  A filter that drops a byte it must not drop shows up as a mismatch here, before any GPU sees it.  The model
-also counts shared-memory wavefronts per step; the hashed filter has to beat the folded one it was built to replace."""
+synthetic text with every slot function the kernels use -- byte & 31 (LOOK), byte & 63 (LOOK64) -- and with the ones that
+were tried and dropped (a multiplicative hash whose multiplier is searched per automaton, the LOOKH experiment, also
+with only the even positions hashed), and compares the end state of every string with the plain walk.  A filter that
+drops a byte it must not drop shows up as a mismatch here, before any GPU sees it.  The model also counts shared-memory
+wavefronts per step: the numbers DESIGN.md 8.4 / 8.8 argue from (the hashed filter is sharper -- and its kernel was
+slower all the same, profiles/r02_experiments_notes.txt)."""
 import lzma
 import os
 import re

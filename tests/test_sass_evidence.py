@@ -67,24 +67,12 @@ def test_look_ahead_step_is_five_and_a_half_instructions(kernels):
     """Per byte: IDP (byte + table base), SHF (probe), half an IMAD (clean bit of the even bytes), LOP3 -> predicate,
     IMAD (row address), predicated LDS.U8: the walk's SHF count equals its predicated loads, half of them left shifts of
     the bit-reversed filter, and there is about one LOP3 per step, not two."""
-    for name, text in kernels[1].items():
-        if "ScanUniformLook2Kernel" not in name:
-            continue
-        hashed = int(re.search(r"ScanUniformLook2KernelILi\d+ELi(\d)E", name).group(1))      # 0 plain slots, 1 every byte, 2 even bytes
+    for text in pick(kernels, "ScanUniformLook2Kernel"):
         steps = count(text, r"@!?P\d\s+LDS\.U8")
         assert steps == 128                                              # 2 strings x 32 bytes x 2 ping-pong blocks
         assert count(text, r"\bIDP\.4A") >= steps
         assert steps // 2 <= count(text, r"\bSHF\.L\.W") <= steps // 2 + 8
         assert steps // 2 <= count(text, r"\bSHF\.R\.W") <= steps // 2 + 16
-        # the hashed kernels fold their filter in the prologue: eight byte values per lane, a shift and an OR each
-        assert count(text, r"\bLOP3") < steps + 40 + (24 if hashed else 0)
-        # LOOKH: one IMAD.HI per hashed byte (every byte, or the even ones), plus the eight of the fold and the probes of
-        # the words that follow a block
-        hi = count(text, r"\bIMAD\.HI")
-        if hashed == 0:
-            assert hi < 8
-        else:
-            per_block = steps if hashed == 1 else steps // 2
-            assert per_block + 8 <= hi <= per_block + 24, (name, hi)
+        assert count(text, r"\bLOP3") < steps + 40
     for text in pick(kernels, "ScanUniformLookKernelILb0ELi48ELb0"):        # the six-instruction step kept for comparison
         assert count(text, r"\bLOP3") > 2 * 64

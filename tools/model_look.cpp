@@ -26,6 +26,46 @@
 
 using namespace pire_b200;
 
+// The LOOKH experiment (round 2, session 44): the filter's 32 slots assigned by slot(b) = mulhi(address + b, mul) & 31,
+// `address` = the table's shared-memory address, which the walk adds to every byte anyway.  FoldLookFilter folds an exact
+// set (bit b & 31 of exact[b >> 5]) onto those slots; ChooseLookMul searches the multiplier that lets the fewest bytes
+// pass (printable ASCII weighted 8:1), over slot widths of 1 to 11 byte values and 32 phases.  The kernel built on it was
+// bit-exact and slower (IMAD.HI issues at a quarter of the rate): profiles/r02_experiments_notes.txt.
+static uint32_t FoldLookFilter(const uint32_t exact[8], uint32_t table_address, uint32_t mul)
+{
+    uint32_t filter = 0;
+    for (uint32_t b = 0; b < 256; ++b)
+        if (exact[b >> 5] >> (b & 31) & 1u)
+            filter |= 1u << ((uint32_t) (((uint64_t) (table_address + b) * mul) >> 32) & 31u);
+    return filter;
+}
+
+static uint32_t ChooseLookMul(const uint32_t exact[8], uint32_t table_address)
+{
+    uint32_t best_mul = 0;
+    uint32_t best_cost = ~0u;
+    const uint64_t phase_step = table_address ? (1ull << 32) / (32ull * table_address) : 0;
+    for (uint32_t i = 92; i <= 1024; ++i) {
+        const uint64_t alpha = ((uint64_t) i << 32) / 1024;
+        for (uint32_t j = 0; j < (phase_step ? 32u : 1u); ++j) {
+            const uint64_t m64 = alpha + j * phase_step;
+            if (m64 == 0 || m64 > 0xffffffffull)
+                continue;
+            const uint32_t mul = (uint32_t) m64;
+            const uint32_t filter = FoldLookFilter(exact, table_address, mul);
+            uint32_t cost = 0;
+            for (uint32_t b = 0; b < 256 && cost < best_cost; ++b)
+                if (filter >> ((uint32_t) (((uint64_t) (table_address + b) * mul) >> 32) & 31u) & 1u)
+                    cost += (b >= 0x20 && b < 0x7f) ? 8 : 1;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best_mul = mul;
+            }
+        }
+    }
+    return best_mul;
+}
+
 struct Hash {
     std::string name;
     uint32_t slots;
@@ -209,13 +249,17 @@ int main(int argc, char** argv)
     }
 
     // staircase slots: slot = mulhi(address + b, mul) & 31 -- what ONE multiply-high of (table address + byte) by a
-    // constant gives (IMAD.HI, FMA pipe; the LOOKH variant): runs of neighbouring byte values share a slot, so a filter
+    // constant gives (IMAD.HI, FMA pipe; the LOOKH experiment): runs of neighbouring byte values share a slot, so a filter
     // whose bytes cluster in the code table (digits, neighbouring letters) keeps its false positives next to its members.
-    // The multiplier is the one the library would choose (ChooseLookMul) for a table at shared address 1024 (MODEL_BASE).
+    // The multiplier is searched (ChooseLookMul above) for a table at shared address 1024 (MODEL_BASE).
     {
         const uint32_t address = std::getenv("MODEL_BASE") ? (uint32_t) std::atoi(std::getenv("MODEL_BASE")) : 1024u;
-        const uint32_t mul = ChooseLookMul(t.look_exact, address);
-        const uint32_t filter = FoldLookFilter(t.look_exact, address, mul);
+        uint32_t exact[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t b = 0; b < 256; ++b)
+            if (F[b])
+                exact[b >> 5] |= 1u << (b & 31);
+        const uint32_t mul = ChooseLookMul(exact, address);
+        const uint32_t filter = FoldLookFilter(exact, address, mul);
         char name[64];
         std::snprintf(name, sizeof(name), "mulhi32F(mul=%08x)", mul);
         Hash h{name, 32, [=](uint32_t b) { return (uint32_t) (((uint64_t) (address + b) * mul) >> 32) & 31u; }};

@@ -19,7 +19,7 @@ dev = "cuda:0"
 
 def check(sc, orc, batch, corpus_host, offsets_host, fixed_len, n, tag):
     f, m, s = orc.run(corpus_host, offsets_host, fixed_len=fixed_len, n=n, shortcuts=True)
-    for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED, N.VARIANT_PRIV, N.VARIANT_LOOK, N.VARIANT_LOOK64, N.VARIANT_LOOK1, N.VARIANT_LOOKH):
+    for variant in (N.VARIANT_PLAIN, N.VARIANT_PRED, N.VARIANT_PRIV, N.VARIANT_LOOK, N.VARIANT_LOOK64, N.VARIANT_LOOK1):
         sc.set_variant(variant)
         r = P.Runner(sc).Begin().Run(batch).End()
         assert (r.Matches().astype(np.uint8) == f).all() and (r.AcceptMasks() == m).all() and (r.States() == s).all(), (tag, variant)
