@@ -437,13 +437,6 @@ int pire_gpu_count_batch(const pire_gpu_scanner* sc, const uint8_t* d_corpus, co
     a.count_words = sc->count_mode == 1 ? 0 : sc->tab.count_words;
     a.count_always = (sc->count_mode == 3 || (sc->count_mode == 0 && sc->final_share > 0.025)) ? 1 : 0;
     a.uniform = (IsUniform(d_corpus, d_offsets, fixed_len) && !getenv("PIRE_B200_NO_UNIFORM_BODY")) ? 1 : 0;
-    if (a.uniform && !a.count_always && sc->tab.look_skips_nonfinal && sc->tab.states > 64) {
-        // large automata on uniform batches: the first pass walks with the look-ahead filter of the scan kernels (fewer
-        // lanes read the table: fewer shared-memory wavefronts); PIRE_B200_COUNT_LOOK=0 keeps the plain first pass
-        const char* env = getenv("PIRE_B200_COUNT_LOOK");
-        if (!(env && atoi(env) == 0))
-            a.uniform = 2;
-    }
     CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t) n * a.regexps * 4, st));
     CUDA_TRY(LaunchCount(a, sc->device, st));
     return PIRE_GPU_OK;

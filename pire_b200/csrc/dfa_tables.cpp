@@ -158,10 +158,6 @@ void BuildScanTables(const Dfa& dfa, const std::vector<uint32_t>& hot_order, uin
             t.look_bitmap = ~0u;
             t.look_bitmap64 = ~0ull;
         }
-        t.look_skips_nonfinal = t.look_ok && t.first_final_hot > 0;
-        for (uint32_t b = 0; b < 256 && t.look_skips_nonfinal; ++b)
-            if (t.hot8[b] != 0 && t.hot8[b] >= t.first_final_hot)
-                t.look_skips_nonfinal = false;
     }
 
     // Lane-private rows: as many of the hottest states as fit, rounded to whole quads,

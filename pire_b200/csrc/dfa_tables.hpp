@@ -70,9 +70,6 @@ struct ScanTables {
     uint32_t look_bitmap = ~0u;
     uint64_t look_bitmap64 = ~0ull;          // the same set with 64 slots (slot = b & 63): LOOK64 variant
     bool look_ok = false;
-    // The look-ahead walk never visits the one-step states it skips: a kernel that acts on the states it enters
-    // (HalfFinalScanner counting) may use it only if hot id 0 and every state entered from it in one step are non-final.
-    bool look_skips_nonfinal = false;
     // Counting (HalfFinalScanner, half_final.h:154-163): hot ids >= first_final_hot are final states
     // (== hot when none is); accept lists in the new numbering as CSR, ids repeated as the image has them.
     uint32_t first_final_hot = 0;

@@ -2418,13 +2418,31 @@ struct Counter<0> {
     }
 };
 
-// What follows a chunk whose first pass said "a final state was entered, or the hot rows were left" (or, kAlways,
-// every chunk): the chunk again with the packed increments of every state entered; byte by byte through the complete
-// table if it leaves the hot rows.  `before` is the state the chunk began in (H = cold: s.cold).
-template <int kWords>
-__device__ __forceinline__ void CountChunkRest(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, Counter<kWords>& c, uint32_t before)
+template <int kWords, bool kAlways>
+__device__ __forceinline__ void CountChunk16(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, Counter<kWords>& c)
 {
+    const uint32_t before = s.g;
+    if (!kAlways || kWords == 0) {
+        uint32_t g = before, top = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+            FastStep<false>(t, g, word, 0x5540);
+            top = max(top, g);
+            FastStep<false>(t, g, word, 0x5541);
+            top = max(top, g);
+            FastStep<false>(t, g, word, 0x5542);
+            top = max(top, g);
+            FastStep<false>(t, g, word, 0x5543);
+            top = max(top, g);
+        }
+        if (top < a.first_final_hot) {       // sixteen steps through non-final hot states: nothing to count
+            s.g = g;
+            return;
+        }
+    }
     if (kWords > 0 && before != t.H) {
+        // the chunk again (or, kAlways, for the first time) with the packed increments of every state entered
         uint32_t g = before;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -2453,80 +2471,7 @@ __device__ __forceinline__ void CountChunkRest(const ScanArgs& a, const Tables& 
     c.EndGroup(a.regexps);
     SetFull(t, s, full);
 }
-
 template <int kWords, bool kAlways>
-__device__ __forceinline__ void CountChunk16(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, Counter<kWords>& c)
-{
-    const uint32_t before = s.g;
-    if (!kAlways || kWords == 0) {
-        uint32_t g = before, top = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t word = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
-            FastStep<false>(t, g, word, 0x5540);
-            top = max(top, g);
-            FastStep<false>(t, g, word, 0x5541);
-            top = max(top, g);
-            FastStep<false>(t, g, word, 0x5542);
-            top = max(top, g);
-            FastStep<false>(t, g, word, 0x5543);
-            top = max(top, g);
-        }
-        if (top < a.first_final_hot) {       // sixteen steps through non-final hot states: nothing to count
-            s.g = g;
-            return;
-        }
-    }
-    CountChunkRest<kWords>(a, t, s, v, c, before);
-}
-
-// The first pass with the look-ahead filter of the scan kernels (LookProbe / LookStep): a lane resting in hot id 0 reads
-// the table only when this byte and the next one pass the filter.  Valid for counting when hot id 0 and every state
-// entered from it in one step are non-final (capi.cu checks): a skipped one-step state then has nothing to count, and
-// the lane is back in id 0 behind the next byte on either path, so a chunk that is walked again -- or replayed byte by
-// byte -- from the "virtual" id 0 counts exactly what the real walk counts.
-// (bb, pa): the probe of the chunk's first byte on entry, of the first byte of `next` on return; `more` = a byte follows
-// the chunk (the last byte of a string is filtered alone).
-template <int kWords>
-__device__ __forceinline__ void CountLookWord(uint32_t& g, uint32_t& top, uint32_t w, uint32_t bb0, uint32_t pa0, uint32_t pan, uint32_t base,
-                                              const LookFilter& f)
-{
-    uint32_t bb1, bb2, bb3, pa1, pa2, pa3;
-    LookProbe<false, 1, true>(w, base, f, bb1, pa1);
-    LookProbe<false, 2, true>(w, base, f, bb2, pa2);
-    LookProbe<false, 3, true>(w, base, f, bb3, pa3);
-    LookStep<true>(g, bb0, pa0, pa1);
-    top = max(top, g);
-    LookStep<true>(g, bb1, pa1, pa2);
-    top = max(top, g);
-    LookStep<true>(g, bb2, pa2, pa3);
-    top = max(top, g);
-    LookStep<true>(g, bb3, pa3, pan);
-    top = max(top, g);
-}
-
-template <int kWords>
-__device__ __forceinline__ void CountChunk16Look(const ScanArgs& a, const Tables& t, LaneState& s, uint4 v, uint32_t next, bool more,
-                                                 const LookFilter& f, uint32_t& bb, uint32_t& pa, Counter<kWords>& c)
-{
-    const uint32_t before = s.g;
-    uint32_t g = before, top = 0, bn, pn;
-    LookProbe<false, 0, true>(v.y, t.base, f, bn, pn);
-    CountLookWord<kWords>(g, top, v.x, bb, pa, pn, t.base, f);
-    LookProbe<false, 0, true>(v.z, t.base, f, bb, pa);
-    CountLookWord<kWords>(g, top, v.y, bn, pn, pa, t.base, f);
-    LookProbe<false, 0, true>(v.w, t.base, f, bn, pn);
-    CountLookWord<kWords>(g, top, v.z, bb, pa, pn, t.base, f);
-    LookProbe<false, 0, true>(next, t.base, f, bb, pa);
-    CountLookWord<kWords>(g, top, v.w, bn, pn, more ? pa : 0x80000000u, t.base, f);
-    if (top < a.first_final_hot) {
-        s.g = g;
-        return;
-    }
-    CountChunkRest<kWords>(a, t, s, v, c, before);
-}
-
-template <int kWords, bool kAlways, bool kLook = false>
 __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const __grid_constant__ ScanArgs a)
 {
     uint8_t* const smem = pire_b200_smem;
@@ -2612,38 +2557,7 @@ __global__ void __launch_bounds__(kBlock, kGenericBlocksPerSM) CountKernel(const
         if (a.uniform) {
             // fixed-length, 32-byte aligned batch: LDG.256 ping-pong through registers, no staging ring (see PrefixKernel)
             const uint32_t len = (uint32_t) (end - p);
-            if (kLook && len != 0) {
-                // the same ping-pong with the look-ahead first pass; the word that follows a block is still on its way from
-                // HBM when the block's walk begins: its probe is tied to the walk (+ s.g * 0) so that it stays behind it
-                LookFilter f;
-                f.lo = a.look_bitmap;
-                f.hi = 0;
-                f.zero = a.opaque_zero;
-                f.rev = __brev(f.lo);
-                uint4 a0, a1, b0, b1;
-                uint32_t bb, pa;
-                LoadStream32(p, a0, a1);
-                b0.x = 0;
-                LookProbe<false, 0, true>(a0.x, t.base, f, bb, pa);
-                for (uint32_t off = 0;;) {
-                    off += 32;
-                    const bool more_b = off < len;
-                    if (more_b)
-                        LoadStream32(p + off, b0, b1);
-                    CountChunk16Look<kWords>(a, t, s, a0, a1.x, true, f, bb, pa, c);
-                    CountChunk16Look<kWords>(a, t, s, a1, b0.x + s.g * a.opaque_zero, more_b, f, bb, pa, c);
-                    if (!more_b)
-                        break;
-                    off += 32;
-                    const bool more_a = off < len;
-                    if (more_a)
-                        LoadStream32(p + off, a0, a1);
-                    CountChunk16Look<kWords>(a, t, s, b0, b1.x, true, f, bb, pa, c);
-                    CountChunk16Look<kWords>(a, t, s, b1, a0.x + s.g * a.opaque_zero, more_a, f, bb, pa, c);
-                    if (!more_a)
-                        break;
-                }
-            } else if (len != 0) {
+            if (len != 0) {
                 uint4 a0, a1, b0, b1;
                 LoadStream32(p, a0, a1);
                 for (uint32_t off = 0;;) {
@@ -3135,10 +3049,6 @@ cudaError_t LaunchCount(const ScanArgs& a, int device, cudaStream_t stream)
     case 5: fn = reinterpret_cast<const void*>(&CountKernel<2, true>); break;
     default: fn = reinterpret_cast<const void*>(&CountKernel<0, false>); break;
     }
-    if (a.uniform == 2 && !a.count_always)          // look-ahead first pass (uniform batches; capi.cu checked the automaton)
-        fn = a.count_words == 1   ? reinterpret_cast<const void*>(&CountKernel<1, false, true>)
-             : a.count_words == 2 ? reinterpret_cast<const void*>(&CountKernel<2, false, true>)
-                                  : reinterpret_cast<const void*>(&CountKernel<0, false, true>);
     int optin = 0, sms = 0;
     cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (err == cudaSuccess)

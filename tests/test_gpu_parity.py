@@ -797,55 +797,6 @@ def test_half_final_counts_vs_reference(cuda_device, ref):
         assert (res.counts == want).all() and (res.final == wfin.astype(bool)).all()
 
 
-@pytest.mark.parametrize("length", [32, 96, 1024])
-def test_counting_with_the_look_ahead_first_pass(length, cuda_device, ref, monkeypatch):
-    """HalfFinalScanner counting of a large automaton on a fixed-length batch walks its first pass with the look-ahead
-    filter of the scan kernels (capi.cu: hot id 0 and the states entered from it in one step are non-final).  The ten
-    glued counters over text made of the bytes that start or continue the patterns -- exit bytes followed by continuing and
-    by non-continuing bytes at every position, chunk and block boundaries included, strings that end on half matches --
-    with and without marks, accept lists and packed increments, static and tuned hot rows: the counters and the final
-    flags equal the reference's, and the plain first pass gives the same."""
-    import torch
-    import pire_b200 as P
-    from pire_b200 import workloads as W
-    image = W.load_image("hf_glue10")
-    hf = ref.load_half_final(image)
-    sc = P.Scanner(image, cuda_device)
-    assert sc.Size() > 64
-    rng = np.random.default_rng(500 + length)
-    n = 2048 + 9
-    dense = b"(0123456789ABCXYZaefhilmorstuw)-: /GET"
-    sparse = bytes(range(0x20, 0x7F))
-    host = np.empty((n, length), np.uint8)
-    for i in range(n):
-        alphabet = dense if rng.random() < 0.6 else dense + sparse
-        row = rng.choice(np.frombuffer(alphabet, np.uint8), size=length)
-        if i % 5 == 0:
-            lit = W.GLUE10_PLANTS[(i // 5) % 10].lstrip(b"^$")
-            for _ in range(1 + i % 3):                                    # several matches per string: counters above one
-                cut = int(rng.integers(1, len(lit) + 1))
-                at = int(rng.integers(0, max(1, length - cut)))
-                row[at:at + cut] = np.frombuffer(lit[:cut], np.uint8)[:length - at]
-        host[i] = row
-    host = np.ascontiguousarray(host).reshape(-1)
-    batch = P.Batch(torch.from_numpy(host).to("cuda:0"), fixed_len=length, n=n)
-    seen_counts = 0
-    for tuned in (False, True):
-        if tuned:
-            sc.Tune(batch, 2048)
-        for begin, end in ((True, True), (False, False), (True, False), (False, True)):
-            want, wfin = hf.count(host, fixed_len=length, n=n, begin=begin, end=end)
-            seen_counts = max(seen_counts, int(want.max()))
-            for mode in (1, 2):
-                sc.set_count_mode(mode)
-                for look in ("1", "0"):
-                    monkeypatch.setenv("PIRE_B200_COUNT_LOOK", look)
-                    res = P.HalfFinalCount(sc, batch, begin=begin, end=end)
-                    assert (res.counts == want).all(), (tuned, begin, end, mode, look, np.argwhere(res.counts != want)[:4])
-                    assert (res.final == wfin.astype(bool)).all(), (tuned, begin, end, mode, look)
-    assert seen_counts >= 2
-
-
 def test_half_final_scanner_matches_like_scanner(cuda_device, ref):
     """A HalfFinalScanner image through the ordinary run entry point: pire_ut.cpp runs its Matches() vectors on
     HalfFinalScanner too (TestGlue@701-704, Serialization@576-579); Final() must agree with the reference's."""
