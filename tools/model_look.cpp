@@ -268,7 +268,15 @@ int main(int argc, char** argv)
         hashes.push_back(h);
         Hash half{std::string(name) + " even bytes only", 32, h.slot, [](uint32_t b) { return b & 31u; }};
         hashes.push_back(half);
-        hashes.push_back({"stair32(b>>2)", 32, [](uint32_t b) { return (b >> 2) & 31u; }});
+        // what ONE shift on the ALU pipe gives: slot = (byte + c) >> s, on every position or on the even ones only
+        for (uint32_t sh : {1u, 2u})
+            for (uint32_t c = 0; c < (1u << sh); ++c) {
+                char nm[64];
+                std::snprintf(nm, sizeof(nm), "shift32((b+%u)>>%u)", c, sh);
+                auto fn = [=](uint32_t b) { return ((b + c) >> sh) & 31u; };
+                hashes.push_back({nm, 32, fn});
+                hashes.push_back({std::string(nm) + " even bytes only", 32, fn, [](uint32_t b) { return b & 31u; }});
+            }
     }
 
     for (const Hash& h : hashes) {
