@@ -76,10 +76,11 @@ def measured_peak():
 class ClockSampler:
     """SM clock + throttle reasons during the timed region.
 
-    Two sources run side by side from before the warm-up: NVML polled every 4 ms from a thread (the same
-    counters nvidia-smi prints, exact timestamps), and the recipe's `nvidia-smi --query-gpu=... -lms 20`
-    line as a subprocess (its lines reach us through a pipe, so their arrival times are only approximate
-    and a short timed region can end before the first one arrives).  NVML samples are preferred."""
+    NVML polled every 4 ms from a thread, started before the warm-up (the same counters nvidia-smi prints, exact
+    timestamps).  Without NVML the recipe's `nvidia-smi --query-gpu=... -lms 20` line runs as a subprocess (its
+    lines reach us through a pipe, so their arrival times are only approximate and a short timed region can end
+    before the first one arrives).  Measured (tools/sessions/gpu_r2_s49.sh): neither source, nor both, moves the
+    step time (2.367-2.369 ms with NVML + nvidia-smi, NVML at 4 or 10 ms, and without any sampling)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -88,6 +89,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         self.nvml_rows, self.nvml, self.nvml_max, self._halt = [], None, None, False
+        self.poll_s = max(1, int(os.environ.get("PIRE_B200_CLOCKS_POLL_MS", "4"))) / 1e3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -98,6 +100,10 @@ class ClockSampler:
             self.nvml_thread.start()
         except Exception:
             self.nvml = None
+        # nvidia-smi is the fallback: with NVML at hand its subprocess (a full query every 20 ms) would only add to what
+        # the sampling costs the GPU under test; PIRE_B200_CLOCKS_SMI=1 runs it beside NVML all the same
+        if self.nvml is not None and not os.environ.get("PIRE_B200_CLOCKS_SMI"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -120,7 +126,7 @@ class ClockSampler:
                 self.nvml_rows.append((t, sm, [name for bit, name in bits if mask & bit]))
             except Exception:
                 break
-            time.sleep(0.004)
+            time.sleep(self.poll_s)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -145,7 +151,7 @@ class ClockSampler:
         if rows:
             reasons = sorted({name for _, _, names in rows for name in names})
             return {"sm_mhz": statistics.median(sm for _, sm, _ in rows), "sm_max_mhz": self.nvml_max, "reasons": reasons,
-                    "samples": len(rows), "source": "nvml, polled every 4 ms"}
+                    "samples": len(rows), "source": "nvml, polled every %g ms" % (self.poll_s * 1e3)}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
