@@ -162,3 +162,18 @@ def test_shards_tile_the_batch():
                     assert lo == covered
                     covered = hi
             assert covered == n
+
+
+def test_staging_copy_equals_memcpy(tmp_path):
+    """pire_gpu_run_batch_host stages pageable input into pinned slots with non-temporal stores (x86) -- the copy is
+    header-only (pire_b200/csrc/stage_copy.hpp), so it runs here: every alignment, lengths around its block size and
+    threshold, 2 MiB slices, guard bytes on both sides."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    exe = str(tmp_path / "stage_copy_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "pire_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "stage_copy_check.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and " 0 bad" in out.stdout, out.stdout + out.stderr
